@@ -1,0 +1,356 @@
+"""azb200 — host-side mirror (Python, ctypes) of the reference's self-play API over libazb200.so.
+
+The product is the C-ABI library (include/azb200.h).  This module is the thin binding the
+tests and bench.py use; its names follow the reference crate:
+
+  ConnectFourGame  — trait Game           (src/game.rs:10-28, connect_four_game.rs)
+  AsyncMcts        — src/async_mcts.rs    (private in the reference; test hook here)
+  Coach            — src/coach.rs         (setup / execute_episode / self-play fan-out)
+
+There is no CPU fallback: if libazb200.so is missing the import fails, and every compute
+call fails with AZB_ERR_CUDA when no device is visible.
+"""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libazb200.so")
+
+Q1_WIN_RANGE_LITERAL = 1
+Q2_BACKUP_NO_ALTERNATE = 2
+Q3_POS_BACKUP_PLUS_ONE = 4
+Q4_VLABEL_LITERAL = 8
+PROFILE_REFERENCE = 15
+PROFILE_SANE = 0
+EVAL_UNIFORM = 0
+EVAL_HASH = 1
+EVAL_NNET = 2
+
+AZB_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = -1, -2, -3, -4
+
+STATE_DTYPE = np.dtype([("s", np.int8, (6, 7)), ("me", np.int8)])  # 43 bytes, packed
+assert STATE_DTYPE.itemsize == 43
+
+
+class AzbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"azb200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    """azb_config: the 15 positional parameters of Coach::setup (coach.rs:38-54) + engine fields."""
+
+    _fields_ = [
+        ("checkpoint_directory", C.c_char_p),
+        ("mcts_reserve_size", C.c_uint64),
+        ("update_threshold", C.c_float),
+        ("temp_threshold", C.c_uint64),
+        ("max_history_length", C.c_uint64),
+        ("max_queue_length", C.c_uint64),
+        ("inference_batch_size", C.c_uint64),
+        ("num_episode_threads", C.c_uint64),
+        ("num_arena_games", C.c_uint64),
+        ("num_iters", C.c_uint64),
+        ("num_eps", C.c_uint64),
+        ("num_sims", C.c_uint64),
+        ("num_sim_threads", C.c_uint64),
+        ("max_depth", C.c_uint64),
+        ("cpuct", C.c_int32),
+        ("quirks", C.c_uint32),
+        ("seed", C.c_uint64),
+        ("evaluator", C.c_int32),
+        ("device", C.c_int32),
+        ("max_concurrent_games", C.c_uint64),
+    ]
+
+
+class SelfPlayStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "games", "plies", "samples", "sims", "levels", "expansions", "terminal_hits",
+        "dup_links", "evals", "blocks_used_max", "owners_max")] + [("device_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build_module():
+    spec = importlib.util.spec_from_file_location("azb200_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python alphazero-rs_b200/build.py` "
+            "(the engine has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.azb_last_error.restype = C.c_char_p
+    lib.azb_config_default.argtypes = [C.POINTER(Config)]
+    lib.azb_config_default.restype = None
+    vp, sz, u64, u32, f32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_float
+    sigs = {
+        "azb_device_count": [],
+        "azb_c4_init": [vp, sz],
+        "azb_c4_feature_shape": [vp],
+        "azb_c4_next_state": [vp, vp, vp, sz, vp, vp],
+        "azb_c4_valid_moves": [vp, sz, vp],
+        "azb_c4_game_ended": [vp, vp, sz, u32, vp],
+        "azb_c4_canonical_form": [vp, vp, sz, vp],
+        "azb_c4_symmetries": [vp, vp, sz, vp, vp],
+        "azb_c4_eval_heuristic": [vp, sz, vp],
+        "azb_c4_to_features": [vp, sz, vp],
+        "azb_coach_setup": [C.POINTER(Config), C.POINTER(vp)],
+        "azb_coach_destroy": [vp],
+        "azb_coach_self_play": [vp, u64, u64, C.POINTER(SelfPlayStats)],
+        "azb_coach_traces": [vp, vp, vp, vp, vp, vp],
+        "azb_coach_num_samples": [vp, C.POINTER(u64)],
+        "azb_coach_export_samples": [vp, vp, vp, vp, u64, C.POINTER(u64)],
+        "azb_mcts_create": [C.POINTER(Config), u64, C.POINTER(vp)],
+        "azb_mcts_destroy": [vp],
+        "azb_mcts_get_action_prob": [vp, vp, f32, vp, vp],
+        "azb_mcts_counter_of": [vp, vp, vp],
+        "azb_mcts_stats": [vp, vp],
+        "azb_mcts_dump": [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(u64)],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    return lib, sorted(sigs) + ["azb_last_error", "azb_config_default"]
+
+
+lib, ABI_SYMBOLS = _load()
+
+
+def _check(rc):
+    if rc != AZB_OK:
+        raise AzbError(rc, lib.azb_last_error().decode())
+
+
+def device_count():
+    return lib.azb_device_count()
+
+
+def default_config(**kw):
+    cfg = Config()
+    lib.azb_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _states(a):
+    a = np.ascontiguousarray(a, dtype=STATE_DTYPE)
+    return a.reshape(-1)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ConnectFourGame:
+    """Batched `impl Game for ConnectFourGame` (connect_four_game.rs:81-238) on the device.
+
+    Every method takes/returns numpy arrays of STATE_DTYPE (the reference struct without the
+    redundant `heights`), n states per call.
+    """
+
+    HEIGHT, WIDTH, ACTIONS = 6, 7, 7
+
+    @staticmethod
+    def get_init_board(n=1):
+        out = np.zeros(n, STATE_DTYPE)
+        _check(lib.azb_c4_init(_ptr(out), n))
+        return out
+
+    @staticmethod
+    def get_feature_shape():
+        out = (C.c_size_t * 3)()
+        _check(lib.azb_c4_feature_shape(out))
+        return list(out)
+
+    @staticmethod
+    def get_next_state(states, player, action):
+        s = _states(states)
+        n = len(s)
+        player = np.ascontiguousarray(np.broadcast_to(np.asarray(player, np.int8), (n,)))
+        action = np.ascontiguousarray(np.broadcast_to(np.asarray(action, np.uint8), (n,)))
+        out = np.zeros(n, STATE_DTYPE)
+        nxt = np.zeros(n, np.int8)
+        _check(lib.azb_c4_next_state(_ptr(s), _ptr(player), _ptr(action), n, _ptr(out), _ptr(nxt)))
+        return out, nxt
+
+    @staticmethod
+    def get_valid_moves(states, player=1):
+        s = _states(states)
+        out = np.zeros((len(s), 7), np.uint8)
+        _check(lib.azb_c4_valid_moves(_ptr(s), len(s), _ptr(out)))
+        return out
+
+    @staticmethod
+    def get_game_ended(states, player, quirks=PROFILE_SANE):
+        s = _states(states)
+        n = len(s)
+        player = np.ascontiguousarray(np.broadcast_to(np.asarray(player, np.int8), (n,)))
+        out = np.zeros(n, np.float32)
+        _check(lib.azb_c4_game_ended(_ptr(s), _ptr(player), n, quirks, _ptr(out)))
+        return out
+
+    @staticmethod
+    def get_canonical_form(states, player):
+        s = _states(states)
+        n = len(s)
+        player = np.ascontiguousarray(np.broadcast_to(np.asarray(player, np.int8), (n,)))
+        out = np.zeros(n, STATE_DTYPE)
+        _check(lib.azb_c4_canonical_form(_ptr(s), _ptr(player), n, _ptr(out)))
+        return out
+
+    @staticmethod
+    def get_symmetries(states, pi):
+        s = _states(states)
+        n = len(s)
+        pi = np.ascontiguousarray(pi, np.float32).reshape(n, 7)
+        out_s = np.zeros((n, 2), STATE_DTYPE)
+        out_pi = np.zeros((n, 2, 7), np.float32)
+        _check(lib.azb_c4_symmetries(_ptr(s), _ptr(pi), n, _ptr(out_s), _ptr(out_pi)))
+        return out_s, out_pi
+
+    @staticmethod
+    def eval_heuristic(states):
+        s = _states(states)
+        out = np.zeros(len(s), np.float32)
+        _check(lib.azb_c4_eval_heuristic(_ptr(s), len(s), _ptr(out)))
+        return out
+
+    @staticmethod
+    def to_features(states):
+        s = _states(states)
+        out = np.zeros((len(s), 2, 6, 7), np.float32)
+        _check(lib.azb_c4_to_features(_ptr(s), len(s), _ptr(out)))
+        return out
+
+
+class AsyncMcts:
+    """n_trees independent search trees on the device (AsyncMcts::default, async_mcts.rs:27-48)."""
+
+    def __init__(self, n_trees=1, **cfg):
+        self.cfg = cfg.pop("config", None) or default_config(**cfg)
+        self.n_trees = n_trees
+        self._h = C.c_void_p()
+        _check(lib.azb_mcts_create(C.byref(self.cfg), n_trees, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.azb_mcts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def get_action_prob(self, states, temp):
+        """async_mcts.rs:74-115 for every tree: returns (counts[n,7] u16, pi[n,7] f32)."""
+        s = _states(states)
+        assert len(s) == self.n_trees
+        counts = np.zeros((self.n_trees, 7), np.uint16)
+        pi = np.zeros((self.n_trees, 7), np.float32)
+        _check(lib.azb_mcts_get_action_prob(self._h, _ptr(s), C.c_float(temp), _ptr(counts), _ptr(pi)))
+        return counts, pi
+
+    def counter_of(self, states):
+        s = _states(states)
+        assert len(s) == self.n_trees
+        out = np.zeros(self.n_trees, np.uint64)
+        _check(lib.azb_mcts_counter_of(self._h, _ptr(s), _ptr(out)))
+        return out
+
+    def stats(self):
+        out = np.zeros((self.n_trees, 8), np.uint64)
+        _check(lib.azb_mcts_stats(self._h, _ptr(out)))
+        return out
+
+    def dump(self, tree=0, cap=1 << 20):
+        keys = np.zeros(cap, np.uint64)
+        counters = np.zeros(cap, np.uint64)
+        e = np.zeros(cap, np.float32)
+        p = np.zeros((cap, 7), np.float32)
+        hp = np.zeros(cap, np.uint8)
+        n = C.c_uint64()
+        _check(lib.azb_mcts_dump(self._h, tree, cap, _ptr(keys), _ptr(counters), _ptr(e), _ptr(p), _ptr(hp), C.byref(n)))
+        n = min(n.value, cap)
+        order = np.argsort(keys[:n])
+        return keys[:n][order], counters[:n][order], e[:n][order], p[:n][order], hp[:n][order]
+
+
+class Coach:
+    """Coach::setup + the self-play half of Coach::learn (coach.rs:38-157, 241-272)."""
+
+    def __init__(self, **cfg):
+        self.cfg = cfg.pop("config", None) or default_config(**cfg)
+        self._h = C.c_void_p()
+        _check(lib.azb_coach_setup(C.byref(self.cfg), C.byref(self._h)))
+        self.n_games = 0
+
+    @classmethod
+    def setup(cls, checkpoint_directory, mcts_reserve_size, update_threshold, temp_threshold,
+              max_history_length, max_queue_length, inference_batch_size, num_episode_threads,
+              num_arena_games, num_iters, num_eps, num_sims, num_sim_threads, max_depth, cpuct, **extra):
+        """Same 15 positional parameters as Coach::setup (coach.rs:38-54)."""
+        return cls(checkpoint_directory=str(checkpoint_directory).encode(),
+                   mcts_reserve_size=mcts_reserve_size, update_threshold=update_threshold,
+                   temp_threshold=temp_threshold, max_history_length=max_history_length,
+                   max_queue_length=max_queue_length, inference_batch_size=inference_batch_size,
+                   num_episode_threads=num_episode_threads, num_arena_games=num_arena_games,
+                   num_iters=num_iters, num_eps=num_eps, num_sims=num_sims,
+                   num_sim_threads=num_sim_threads, max_depth=max_depth, cpuct=cpuct, **extra)
+
+    def close(self):
+        if self._h:
+            lib.azb_coach_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def self_play(self, n_games, first_game_id=0):
+        """n_games concurrent execute_episode calls (coach.rs:104-157); returns the stats dict."""
+        st = SelfPlayStats()
+        _check(lib.azb_coach_self_play(self._h, n_games, first_game_id, C.byref(st)))
+        self.n_games = n_games
+        return st.as_dict()
+
+    def execute_episode(self, episode_id=0):
+        """One game; returns its SOA samples like the reference's VecDeque<TrainingSample>."""
+        self.self_play(1, episode_id)
+        return self.export_samples()
+
+    def traces(self):
+        g = self.n_games
+        actions = np.zeros((g, 64), np.uint8)
+        counts = np.zeros((g, 64, 7), np.uint16)
+        plies = np.zeros(g, np.uint32)
+        final_r = np.zeros(g, np.float32)
+        final_player = np.zeros(g, np.int8)
+        _check(lib.azb_coach_traces(self._h, _ptr(actions), _ptr(counts), _ptr(plies), _ptr(final_r), _ptr(final_player)))
+        return dict(actions=actions, counts=counts, plies=plies, final_r=final_r, final_player=final_player)
+
+    def num_samples(self):
+        n = C.c_uint64()
+        _check(lib.azb_coach_num_samples(self._h, C.byref(n)))
+        return n.value
+
+    def export_samples(self, out=None):
+        """SOATrainingSamples (nnet.rs:33): (boards[n,2,6,7], pis[n,7], vs[n])."""
+        n = self.num_samples()
+        if out is None:
+            out = (np.zeros((n, 2, 6, 7), np.float32), np.zeros((n, 7), np.float32), np.zeros(n, np.float32))
+        boards, pis, vs = out
+        w = C.c_uint64()
+        _check(lib.azb_coach_export_samples(self._h, _ptr(boards), _ptr(pis), _ptr(vs), len(vs), C.byref(w)))
+        return boards[: w.value], pis[: w.value], vs[: w.value]

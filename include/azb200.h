@@ -1,0 +1,179 @@
+/* azb200.h — C ABI of the B200-native self-play engine (libazb200.so).
+ *
+ * Drop-in boundary for the self-play hot path of AnimatedRNG/alphazero-rs.  Every entry
+ * point cites the reference interface it replaces (paths relative to /root/reference).
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return 0 on success
+ * and a negative azb_status otherwise (the reference panics instead: unwrap/assert!);
+ * azb_last_error() gives the message for the calling thread.  Handles are opaque, created
+ * and destroyed by the library, and not thread-safe.  Bulk outputs go into caller-owned
+ * buffers.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * AZB_ERR_CUDA.
+ */
+#ifndef AZB200_H
+#define AZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum azb_status {
+  AZB_OK = 0,
+  AZB_ERR_INVALID = -1,   /* bad argument (reference: assert!/panic!) */
+  AZB_ERR_CUDA = -2,      /* CUDA runtime error, or no device */
+  AZB_ERR_CAPACITY = -3,  /* node pool / transposition table / sample buffer overflow
+                             (reference: assert!(idx < self.buf.len()), src/node.rs:237) */
+  AZB_ERR_UNSUPPORTED = -4
+} azb_status;
+
+/* Quirk flags: set = the LITERAL behaviour of the reference. */
+#define AZB_Q1_WIN_RANGE_LITERAL 1u    /* connect_four_game.rs:114,129 */
+#define AZB_Q2_BACKUP_NO_ALTERNATE 2u  /* src/async_mcts.rs:353,361-370 */
+#define AZB_Q3_POS_BACKUP_PLUS_ONE 4u  /* src/node.rs:85-91 */
+#define AZB_Q4_VLABEL_LITERAL 8u       /* src/coach.rs:146-153 */
+#define AZB_PROFILE_REFERENCE 15u
+#define AZB_PROFILE_SANE 0u
+
+/* Leaf evaluators standing behind trait NNet::predict (src/nnet.rs:40-44). */
+#define AZB_EVAL_UNIFORM 0 /* examples/connect_four.rs:26-42 DumbConnectFourNnet, fused inline */
+#define AZB_EVAL_HASH 1    /* deterministic integer-hash evaluator (tests), fused inline */
+#define AZB_EVAL_NNET 2    /* batched leaf evaluation by an azb_nnet (lock-step rounds) */
+
+const char* azb_last_error(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int azb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Game = ConnectFour.  trait Game, src/game.rs:10-28; the only implementation is
+ * examples/connect_four_lib/connect_four_game.rs.  State POD mirrors its struct (:18-23)
+ * without the redundant `heights`: s[row][col], row 0 = top (:99), cells in {-1,0,+1}.
+ * All calls are batched over n states: host buffers in, one bitboard kernel, host buffers
+ * out.
+ * ------------------------------------------------------------------------------------- */
+#pragma pack(push, 1)
+typedef struct azb_c4_state {
+  int8_t s[6][7];
+  int8_t me;
+} azb_c4_state; /* 43 bytes */
+#pragma pack(pop)
+
+#define AZB_C4_ACTIONS 7
+#define AZB_C4_FEATURES 84 /* 2*6*7 */
+
+/* Game::get_init_board — connect_four_game.rs:82-84 */
+int azb_c4_init(azb_c4_state* out, size_t n);
+/* Game::get_feature_shape — :86-88 → {2,6,7} */
+int azb_c4_feature_shape(size_t out[3]);
+/* Game::get_next_state(player, action) -> (state, -player) — :90-102 */
+int azb_c4_next_state(const azb_c4_state* in, const int8_t* player, const uint8_t* action,
+                      size_t n, azb_c4_state* out, int8_t* next_player);
+/* Game::get_valid_moves — :104-109 → out[n][7] of 0/1 */
+int azb_c4_valid_moves(const azb_c4_state* in, size_t n, uint8_t* out);
+/* Game::get_game_ended(player) — :111-196; quirks bit Q1 selects the literal scan ranges */
+int azb_c4_game_ended(const azb_c4_state* in, const int8_t* player, size_t n, uint32_t quirks,
+                      float* out);
+/* Game::get_canonical_form(player) — :198-203, repaired (F10): cells * player, me = +1 */
+int azb_c4_canonical_form(const azb_c4_state* in, const int8_t* player, size_t n,
+                          azb_c4_state* out);
+/* Game::get_symmetries(pi) — :205-211 → out_states[n][2], out_pi[n][2][7] (identity, mirror) */
+int azb_c4_symmetries(const azb_c4_state* in, const float* pi, size_t n, azb_c4_state* out_states,
+                      float* out_pi);
+/* Game::eval_heuristic — :214-216 (always 0) */
+int azb_c4_eval_heuristic(const azb_c4_state* in, size_t n, float* out);
+/* Game::to_features — :219-237, repaired (F11): out[n][2][6][7], ch0 = cells == me */
+int azb_c4_to_features(const azb_c4_state* in, size_t n, float* out);
+
+/* ---------------------------------------------------------------------------------------
+ * Coach — src/coach.rs.  azb_config carries the 15 positional parameters of Coach::setup
+ * (coach.rs:38-54) under the same names and in the same order, then this engine's own.
+ * ------------------------------------------------------------------------------------- */
+typedef struct azb_config {
+  const char* checkpoint_directory;
+  uint64_t mcts_reserve_size; /* node slots per tree (reference: 1,000,000); the pool is
+                                 sized min(this, what num_sims can ever allocate) */
+  float update_threshold;
+  uint64_t temp_threshold;
+  uint64_t max_history_length;
+  uint64_t max_queue_length;
+  uint64_t inference_batch_size; /* ignored: a round evaluates every pending leaf (F16) */
+  uint64_t num_episode_threads;  /* ignored: every game of a call runs concurrently */
+  uint64_t num_arena_games;
+  uint64_t num_iters;
+  uint64_t num_eps;
+  uint64_t num_sims;
+  uint64_t num_sim_threads; /* must be 1: deterministic mode, one simulation in flight per tree */
+  uint64_t max_depth;
+  int32_t cpuct;
+  /* engine additions */
+  uint32_t quirks;   /* AZB_Q* bits */
+  uint64_t seed;     /* Philox-4x32-10 key; stream = (seed, global game id, ply) */
+  int32_t evaluator; /* AZB_EVAL_* */
+  int32_t device;    /* CUDA ordinal */
+  uint64_t max_concurrent_games; /* trees resident in HBM at once; 0 = as many as requested */
+} azb_config;
+
+/* The reference's example parameters (examples/connect_four.rs:55-71), profile "sane". */
+void azb_config_default(azb_config* cfg);
+
+typedef struct azb_coach azb_coach;
+
+/* Coach::setup — coach.rs:38-102 (history resume is a next-row item). */
+int azb_coach_setup(const azb_config* cfg, azb_coach** out);
+int azb_coach_destroy(azb_coach* c);
+
+/* Per-call counters (device-side, summed over games). */
+typedef struct azb_selfplay_stats {
+  uint64_t games, plies, samples;
+  uint64_t sims, levels, expansions, terminal_hits, dup_links, evals;
+  uint64_t blocks_used_max, owners_max; /* pool high-water marks over trees */
+  double device_ms;                     /* CUDA-event time of the self-play kernels */
+} azb_selfplay_stats;
+
+/* Coach::execute_episode over n_games concurrent games — coach.rs:104-157 and the episode
+ * fan-out coach.rs:241-272.  Game g uses Philox stream (seed, first_game_id + g).  Games run
+ * entirely on the device; finished samples stay there until azb_coach_export_samples.
+ * Per-game traces (optional, may be NULL): actions[n_games][64] (0xFF padded),
+ * root_counts[n_games][64][7], plies[n_games], final_r[n_games], final_player[n_games]. */
+int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id,
+                        azb_selfplay_stats* stats);
+int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint32_t* plies,
+                     float* final_r, int8_t* final_player);
+/* Number of training samples the last self-play call produced (2 per ply: coach.rs:130-135). */
+int azb_coach_num_samples(azb_coach* c, uint64_t* n);
+/* SOATrainingSamples (src/nnet.rs:33): boards[n][2][6][7], pis[n][7], vs[n], ordered by game,
+ * ply, symmetry (coach.rs:132-135,243-270).  `capacity` is in samples. */
+int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs, uint64_t capacity,
+                             uint64_t* n_written);
+
+/* ---------------------------------------------------------------------------------------
+ * AsyncMcts test hooks — src/async_mcts.rs and src/node.rs are private modules of the
+ * reference (src/lib.rs:6,10); these exist so their behaviour can be checked directly.
+ * An azb_mcts is n_trees independent trees, each created on the initial board
+ * (AsyncMcts::default, async_mcts.rs:27-48).
+ * ------------------------------------------------------------------------------------- */
+typedef struct azb_mcts azb_mcts;
+int azb_mcts_create(const azb_config* cfg, uint64_t n_trees, azb_mcts** out);
+int azb_mcts_destroy(azb_mcts* m);
+/* AsyncMcts::get_action_prob — async_mcts.rs:74-115: for every tree i run cfg.num_sims
+ * simulations from the canonical state states[i] and return the root child visit counts
+ * counts[n_trees][7] and pi[n_trees][7] (temp 0 → one-hot, ties to the highest action). */
+int azb_mcts_get_action_prob(azb_mcts* m, const azb_c4_state* states, float temp, uint16_t* counts,
+                             float* pi);
+/* Raw packed counter (src/node.rs:17, 0xWWWWWWWWNNNNVVVV) of the node owning states[i];
+ * 0 when the state is not in tree i. */
+int azb_mcts_counter_of(azb_mcts* m, const azb_c4_state* states, uint64_t* counters);
+/* stats[n_trees][8]: sims, levels, expansions, terminal_hits, dup_links, evals,
+ * blocks_used, owners (= NodeStore.seen.len()). */
+int azb_mcts_stats(azb_mcts* m, uint64_t* stats);
+/* Dump tree `tree`: one row per unique state: 49-bit key, raw counter, terminal value e,
+ * prior vector and a has-policy flag.  Returns rows through n_rows (rows beyond cap are
+ * counted but not written). */
+int azb_mcts_dump(azb_mcts* m, uint64_t tree, uint64_t cap, uint64_t* keys, uint64_t* counters,
+                  float* e, float* p7, uint8_t* has_p, uint64_t* n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZB200_H */
