@@ -14,7 +14,7 @@ def check_games(azb, orc, coach, games, first_game_id, **okw):
     tr = coach.traces()
     boards, pis, vs = coach.export_samples()
     assert st["games"] == games and st["samples"] == 2 * st["plies"] == len(vs)
-    offs = np.concatenate([[0], np.cumsum(tr["plies"])])
+    offs = np.concatenate([[0], np.cumsum(tr["plies"].astype(np.int64))])
     tot = np.zeros(6, np.uint64)
     check = range(games) if games <= 64 else list(range(0, games, max(1, games // 24)))
     for g in check:
@@ -95,7 +95,7 @@ def test_full_size_properties(azb):
     # sample 2k and 2k+1 are mirror images with reversed pi
     assert np.array_equal(boards[0::2], boards[1::2][:, :, :, ::-1])
     assert np.array_equal(pis[0::2], pis[1::2][:, ::-1])
-    offs = np.concatenate([[0], np.cumsum(tr["plies"])])
+    offs = np.concatenate([[0], np.cumsum(tr["plies"].astype(np.int64))])
     assert np.array_equal(stones[2 * offs[:-1]], np.zeros(4096))  # every game starts on the empty board
     assert set(np.unique(np.abs(vs)).tolist()) <= {1.0, np.float32(1e-4)}
     st2 = coach.self_play(4096, 0)
