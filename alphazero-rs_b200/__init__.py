@@ -118,6 +118,7 @@ def _load():
         "azb_mcts_counter_of": [vp, vp, vp],
         "azb_mcts_stats": [vp, vp],
         "azb_mcts_dump": [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(u64)],
+        "azb_selftest_arith": [vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
@@ -129,6 +130,10 @@ def _load():
 lib, ABI_SYMBOLS = _load()
 
 
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
 def _check(rc):
     if rc != AZB_OK:
         raise AzbError(rc, lib.azb_last_error().decode())
@@ -136,6 +141,13 @@ def _check(rc):
 
 def device_count():
     return lib.azb_device_count()
+
+
+def selftest_arith():
+    """{reciprocal, sqrt, division} mismatches of the fast f32 helpers vs the IEEE intrinsics."""
+    out = np.zeros(3, np.uint64)
+    _check(lib.azb_selftest_arith(_ptr(out)))
+    return out.tolist()
 
 
 def default_config(**kw):

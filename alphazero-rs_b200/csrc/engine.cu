@@ -76,7 +76,7 @@ SearchParams make_params(const azb_config& c, uint64_t searches_per_tree) {
   uint64_t by_reserve = c.mcts_reserve_size / 7 + 2;
   uint64_t by_work = c.num_sims * searches_per_tree + 2 * (searches_per_tree + 1) + 8;
   uint64_t cap = std::min(by_reserve, by_work);
-  cap = std::min<uint64_t>(cap, kMaxBlockId - 1);
+  cap = std::min<uint64_t>(cap, (1u << 24) - 1);  // slot ids are packed with the action in 27+3 bits
   p.cap_blocks = static_cast<uint32_t>(cap);
   uint32_t entries = pow2_ceil(std::max<uint64_t>(64, cap + cap / 2));
   p.bucket_mask = entries / 8 - 1;
@@ -282,6 +282,18 @@ int azb_c4_eval_heuristic(const azb_c4_state* in, size_t n, float* out) {
 int azb_c4_to_features(const azb_c4_state* in, size_t n, float* out) {
   if (n && !out) return fail(AZB_ERR_INVALID, "NULL argument");
   return c4_batch(kOpFeatures, in, nullptr, nullptr, nullptr, 0, n, nullptr, 0, nullptr, nullptr, 0, out, 84);
+}
+
+int azb_selftest_arith(uint64_t mismatches[3]) {
+  if (!mismatches) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
+  DevBuf d;
+  AZB_CUDA(d.ensure(24));
+  AZB_CUDA(cudaMemset(d.p, 0, 24));
+  k_selftest_arith<<<256, 256>>>(d.as<unsigned long long>());
+  AZB_CUDA(cudaGetLastError());
+  AZB_CUDA(cudaMemcpy(mismatches, d.p, 24, cudaMemcpyDeviceToHost));
+  return AZB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

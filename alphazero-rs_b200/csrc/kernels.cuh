@@ -17,9 +17,11 @@ struct Pools {
 };
 
 __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchParams& p, uint32_t tree) {
+  __shared__ uint32_t s_path[kWarpsPerCta][kPathCap];
   WarpTree t;
   t.blocks = pools.blocks + static_cast<size_t>(tree) * p.cap_blocks * 8u;
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
+  t.path = s_path[(threadIdx.x >> 5) % kWarpsPerCta];
   t.n_blocks = t.n_owners = t.error = 0u;
   t.stat = 0u;
   return t;
@@ -99,7 +101,7 @@ __global__ void k_dump_tree(SearchParams p, Pools pools, uint32_t tree, uint64_t
     for (int a = 0; a < 7; ++a) p7[row * 7 + a] = 0.0f;
     if (meta_is_block(meta)) {
       const uint4* bp = t.blocks + static_cast<size_t>(meta) * 8u;
-      hp = (bp[7].z & kFlagHasPolicy) ? 1 : 0;
+      hp = (block_flags(t, meta) & kFlagHasPolicy) ? 1 : 0;
       if (hp)
         for (int a = 0; a < 7; ++a) p7[row * 7 + a] = __uint_as_float(bp[a].z);
     }
@@ -218,6 +220,31 @@ __global__ void k_export_samples(GameBufs g, const uint64_t* __restrict__ offset
       vs[row] = v;
     }
   }
+}
+
+// ---- arithmetic self-test: the slow-path-free division / sqrt used by the level loop against
+// the IEEE intrinsics, exhaustively over the integer domain they are used on ---------------------
+__global__ void k_selftest_arith(unsigned long long* mismatches) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0;
+  for (uint32_t b = 1u + tid; b <= 65536u; b += nthreads) {
+    const float fb = static_cast<float>(b);
+    if (rcp_int(fb) != __frcp_rn(fb)) bad_rcp++;
+    const float x = __fadd_rn(static_cast<float>(b - 1u), kEps);
+    if (sqrt_count(x) != __fsqrt_rn(x)) bad_sqrt++;
+    uint32_t s = b * 2654435761u;
+    for (int k = 0; k < 512; ++k) {
+      s = s * 1664525u + 1013904223u;
+      // t3-like numerators: all mantissas, exponents 2^-60 .. 2^60, both signs
+      float a = __uint_as_float((s & 0x807FFFFFu) | ((67u + (s >> 23) % 120u) << 23));
+      if (k == 0) a = 0.0f;
+      if (fdiv_by_int(a, fb) != __fdiv_rn(a, fb)) bad_div++;
+    }
+  }
+  if (bad_rcp) atomicAdd(mismatches + 0, bad_rcp);
+  if (bad_sqrt) atomicAdd(mismatches + 1, bad_sqrt);
+  if (bad_div) atomicAdd(mismatches + 2, bad_div);
 }
 
 // ---- batched connect-four over 43-byte states (trait Game, src/game.rs:10-28) -----------------

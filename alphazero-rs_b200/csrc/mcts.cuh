@@ -6,10 +6,19 @@
 //
 // One warp owns one tree and runs one simulation at a time, so every f32 rounding and every
 // tie-break happens in the reference's order and results are bit-exact with the oracle.
-// Per level the warp reads ONE 128-byte block (lanes 0-6 = the 7 edges, lane 7 = header),
-// resolves transposition links with one extra 8-byte load, evaluates PUCT per lane and
-// picks the last maximum with redux.max + ballot.  visit()/unvisit() of the reference are
-// folded: counters travel down the path in registers and are written once, at backup.
+//
+// The search is instruction-issue bound (ncu: profiles/r1_v1_selfplay_ncu.md), so the level
+// loop is kept minimal:
+//   * per level the warp reads ONE 128-byte block (lane a = edge a: {w, q, prior, meta} + n[a]),
+//     resolves transposition links with two small extra loads, computes
+//     u = q + (cpuct*P*sqrt(N_parent))/(1+n) per lane (Q is cached, one division left, done
+//     with an FMA sequence proven correctly rounded), and takes the LAST maximum with
+//     redux.max.f32 + ballot + clz;
+//   * visit()/unvisit() of the reference are folded into one read-modify-write per path node
+//     at backup (lane l handles path entry l), which also refreshes the cached q;
+//   * the board is not tracked during descent: only (slot, action) goes to a shared-memory
+//     path, and the leaf position is rebuilt lane-parallel from the root position and the path
+//     actions when (and only when) a placeholder is expanded.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -21,12 +30,13 @@
 namespace azb {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kPathCap = 48;  // <= 42 moves to a full board + dup-link hops never push
 
 enum : uint32_t { kErrNone = 0, kErrBlocks = 1, kErrTable = 2, kErrInternal = 3 };
 enum : int { kStatSims = 0, kStatLevels, kStatExpansions, kStatTerminal, kStatDupLinks, kStatEvals, kNumStats };
 
 struct SearchParams {
-  uint32_t cap_blocks;   // blocks per tree
+  uint32_t cap_blocks;   // blocks per tree (< 2^24)
   uint32_t bucket_mask;  // transposition table: (bucket_mask+1) buckets of 8 entries
   uint32_t num_sims;
   uint32_t max_depth;
@@ -48,28 +58,60 @@ struct TreeRec {
 
 // Per-warp view of one tree.  Every member is warp-uniform except `stat` (lane k = stat k).
 struct WarpTree {
-  uint4* blocks;  // slot id indexes this directly (16-byte slots, 8 per block)
-  uint4* table;   // HashEntry as uint4 {key.lo, key.hi, slot, meta}
+  uint4* blocks;   // slot id indexes this directly (16-byte slots, 8 per block)
+  uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}
+  uint32_t* path;  // shared memory, kPathCap entries: (slot << 3) | action
   uint32_t n_blocks, n_owners, error;
   uint32_t stat;
 };
 
+// ---- slot field access ------------------------------------------------------------------
+__device__ __forceinline__ uint16_t* n_ptr(const WarpTree& t, uint32_t slot) {
+  return reinterpret_cast<uint16_t*>(t.blocks + (slot | 7u)) + (slot & 7u);
+}
+__device__ __forceinline__ uint32_t ld_n(const WarpTree& t, uint32_t slot) { return *n_ptr(t, slot); }
+__device__ __forceinline__ uint32_t ld_w(const WarpTree& t, uint32_t slot) {
+  return *reinterpret_cast<const uint32_t*>(t.blocks + slot);
+}
+__device__ __forceinline__ float ld_q(const WarpTree& t, uint32_t slot) {
+  return reinterpret_cast<const float*>(t.blocks + slot)[1];
+}
 __device__ __forceinline__ uint64_t ld_counter(const WarpTree& t, uint32_t slot) {
-  return *reinterpret_cast<const uint64_t*>(t.blocks + slot);
+  return counter_pack(ld_w(t, slot), ld_n(t, slot));
 }
-__device__ __forceinline__ void st_counter(const WarpTree& t, uint32_t slot, uint64_t c) {
-  *reinterpret_cast<uint64_t*>(t.blocks + slot) = c;
+
+// ---- exact f32 helpers without slow-path calls ---------------------------------------------
+// a / b for b an integer-valued float in [1, 65536]: r = RN(1/b) (MUFU.RCP + one Newton step,
+// checked exhaustively against __frcp_rn by azb_selftest_arith), then Markstein's correction
+// twice: with an exact reciprocal and a faithful quotient the FMA residual step returns the
+// correctly rounded quotient (no overflow/underflow: callers route tiny/huge `a` to __fdiv_rn).
+__device__ __forceinline__ float rcp_int(float b) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
+  const float e = __fmaf_rn(-b, r0, 1.0f);
+  return __fmaf_rn(r0, e, r0);
 }
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-  uint32_t lo = __shfl_sync(kFull, static_cast<uint32_t>(v), src);
-  uint32_t hi = __shfl_sync(kFull, static_cast<uint32_t>(v >> 32), src);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
+__device__ __forceinline__ float fdiv_by_int(float a, float b) {
+  const float r = rcp_int(b);
+  const float q0 = __fmul_rn(a, r);
+  const float e0 = __fmaf_rn(-b, q0, a);
+  const float q1 = __fmaf_rn(e0, r, q0);
+  const float e1 = __fmaf_rn(-b, q1, a);
+  return __fmaf_rn(e1, r, q1);
 }
-// Order-preserving f32 -> u32 (finite values; -0.0 is canonicalised to +0.0 first so that it
-// compares Equal to +0.0 like partial_cmp does, node.rs:366).
-__device__ __forceinline__ uint32_t ordered_key(float u) {
-  uint32_t b = __float_as_uint(__fadd_rn(u, 0.0f));
-  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+// sqrt(x) for x = N + 1e-6, N in [0, 65535] (checked exhaustively against __fsqrt_rn).
+__device__ __forceinline__ float sqrt_count(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  float s = __fmul_rn(x, y);
+  const float h = __fmul_rn(0.5f, y);
+  const float d = __fmaf_rn(-s, s, x);
+  return __fmaf_rn(d, h, s);
+}
+__device__ __forceinline__ float redux_max_f32(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
 }
 
 // ---- transposition table (NodeStore.seen): buckets of 8 entries = one 128-byte line ------
@@ -79,17 +121,16 @@ __device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask,
                                         int lane, uint32_t& slot, uint32_t& meta, uint32_t& ins) {
   uint32_t b = hash_bucket(key, bucket_mask);
   for (uint32_t probe = 0; probe <= bucket_mask; ++probe) {
-    uint4 e = make_uint4(1u, 0u, 0u, 0u);
-    if (lane < 8) e = t.table[b * 8u + lane];
-    uint64_t k = (static_cast<uint64_t>(e.y) << 32) | e.x;
-    uint32_t hit = __ballot_sync(kFull, lane < 8 && k == key);
+    const uint4 e = t.table[b * 8u + (lane & 7)];
+    const uint64_t k = (static_cast<uint64_t>(e.y) << 32) | e.x;
+    const uint32_t hit = __ballot_sync(kFull, k == key) & 0xFFu;
     if (hit) {
-      int l = __ffs(hit) - 1;
+      const int l = __ffs(hit) - 1;
       slot = __shfl_sync(kFull, e.z, l);
       meta = __shfl_sync(kFull, e.w, l);
       return true;
     }
-    uint32_t emp = __ballot_sync(kFull, lane < 8 && k == 0ull);
+    const uint32_t emp = __ballot_sync(kFull, k == 0ull) & 0xFFu;
     if (emp) {
       ins = b * 8u + (__ffs(emp) - 1);
       return false;
@@ -134,17 +175,18 @@ __device__ __forceinline__ float mask_normalise(float pi, uint32_t vm, int lane)
   return __fdiv_rn(pi, s2);
 }
 
-__device__ __forceinline__ void write_child_block(const WarpTree& t, uint32_t blk, uint64_t key,
-                                                  uint32_t vm, float prior, uint32_t flags,
-                                                  uint32_t self_slot, int lane) {
+// A fresh child block: every legal action is a placeholder with W = bias, N = 0, q = 0.
+__device__ __forceinline__ void write_child_block(const WarpTree& t, uint32_t blk, uint32_t vm,
+                                                  float prior, uint32_t flags, int lane) {
   uint4 out;
   if (lane < 7)
-    out = make_uint4(static_cast<uint32_t>(kCounterInit), static_cast<uint32_t>(kCounterInit >> 32),
-                     __float_as_uint(prior), ((vm >> lane) & 1u) ? kMetaPlaceholder : kMetaInvalid);
+    out = make_uint4(kWBias, 0u, __float_as_uint(prior), ((vm >> lane) & 1u) ? kMetaPlaceholder : kMetaInvalid);
   else
-    out = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32),
-                     flags | (vm << 8), self_slot);
+    out = make_uint4(0u, 0u, 0u, flags << 16);  // n[0..6] = 0, flags in the last u16
   if (lane < 8) t.blocks[blk * 8u + lane] = out;
+}
+__device__ __forceinline__ uint32_t block_flags(const WarpTree& t, uint32_t blk) {
+  return reinterpret_cast<const uint32_t*>(t.blocks + blk * 8u + 7u)[3] >> 16;
 }
 
 // push + upgrade of a state that is not in the tree, as a stand-alone root
@@ -168,16 +210,51 @@ __device__ __forceinline__ bool make_root(WarpTree& t, const SearchParams& p, BB
     root_meta = kMetaTerminal | static_cast<uint32_t>(code);
   } else {
     root_meta = t.n_blocks++;
-    write_child_block(t, root_meta, key, valid_mask(s.cur | s.opp), 0.0f, 0u, root_slot, lane);
+    write_child_block(t, root_meta, valid_mask(s.cur | s.opp), 0.0f, 0u, lane);
   }
-  uint4 out = make_uint4(static_cast<uint32_t>(kCounterInit), static_cast<uint32_t>(kCounterInit >> 32),
-                         0u, lane == 0 ? root_meta : kMetaInvalid);
-  if (lane == 7) out = make_uint4(0u, 0u, kFlagRootHolder, root_slot);
+  uint4 out = make_uint4(kWBias, 0u, 0u, lane == 0 ? root_meta : kMetaInvalid);
+  if (lane == 7) out = make_uint4(0u, 0u, 0u, kFlagRootHolder << 16);
   if (lane < 8) t.blocks[holder * 8u + lane] = out;
   tt_insert(t, ins, key, root_slot, root_meta, lane);
   t.n_owners++;
   __syncwarp();
   return true;
+}
+
+// The position reached from `root` by the path actions path[0..plen) (each entry's low 3 bits),
+// in canonical form for the side to move there.  Lane i places move i: its row follows from
+// the root column height plus the number of earlier path moves in the same column.
+__device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t plen, int lane) {
+  uint64_t even = 0ull, odd = 0ull;  // stones added by the root's side to move / by the other side
+  const uint64_t occ = root.cur | root.opp;
+  for (uint32_t base = 0; base < plen; base += 32u) {
+    const uint32_t i = base + lane;
+    const bool on = i < plen;
+    const uint32_t col = on ? (t.path[i] & 7u) : (8u + lane);
+    const uint32_t same = __match_any_sync(kFull, col);
+    uint64_t bit = 0ull;
+    if (on) {
+      const uint64_t filled = occ | even | odd;
+      const uint32_t h = __popcll(filled & (kCol0 << col)) + __popc(same & ((1u << lane) - 1u));
+      bit = 1ull << ((5u - h) * 7u + col);
+    }
+    const uint64_t e = (i & 1u) ? 0ull : bit, o = (i & 1u) ? bit : 0ull;
+    even |= (static_cast<uint64_t>(__reduce_or_sync(kFull, static_cast<uint32_t>(e >> 32))) << 32) |
+            __reduce_or_sync(kFull, static_cast<uint32_t>(e));
+    odd |= (static_cast<uint64_t>(__reduce_or_sync(kFull, static_cast<uint32_t>(o >> 32))) << 32) |
+           __reduce_or_sync(kFull, static_cast<uint32_t>(o));
+  }
+  const BB abs{root.cur | even, root.opp | odd};
+  return (plen & 1u) ? BB{abs.opp, abs.cur} : abs;
+}
+
+// unvisit of one path node, folded with the visit that preceded it (node.rs:77-92), and refresh
+// of the cached q.
+__device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
+  uint64_t c = ld_counter(t, slot) + kVisit;
+  c = counter_unvisit(c, v, quirks);
+  *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q(c)));
+  *n_ptr(t, slot) = static_cast<uint16_t>(counter_n(c));
 }
 
 // ---- search_iteration x nsims (async_mcts.rs:191-371) ------------------------
@@ -186,73 +263,76 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
                                          uint32_t root_slot, uint32_t root_meta, uint32_t nsims,
                                          int lane) {
   const bool alternate = !(p.quirks & AZB_Q2_BACKUP_NO_ALTERNATE);
-  for (uint32_t sim = 0; sim < nsims; ++sim) {
+  const float neg_inf = __uint_as_float(0xFF800000u);
+  uint32_t sim = 0;
+  // Repair F1: an existing, non-terminal node that was never evaluated (a stand-alone root at
+  // its first visit) is evaluated when first reached; this consumes one simulation.  Only a
+  // root can be in that state: every other node is evaluated by the simulation that creates it.
+  if (nsims > 0 && meta_is_block(root_meta)) {
+    const uint32_t flags = block_flags(t, root_meta);
+    if (!(flags & kFlagHasPolicy)) {
+      uint4* bp = t.blocks + static_cast<size_t>(root_meta) * 8u;
+      const uint32_t m = lane < 7 ? bp[lane].w : kMetaInvalid;
+      const uint32_t vm = __ballot_sync(kFull, m != kMetaInvalid) & 0x7Fu;
+      float pi, val;
+      evaluate_inline<EVAL>(root, lane, pi, val);
+      pi = mask_normalise(pi, vm, lane);
+      if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
+      if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
+      if (lane == 0) backup_node(t, root_slot, __fmul_rn(1.0f, -val), p.quirks);
+      if (lane == kStatEvals || lane == kStatSims || lane == kStatLevels) t.stat++;
+      __syncwarp();
+      sim = 1;
+    }
+  }
+  for (; sim < nsims; ++sim) {
     uint32_t cur_slot = root_slot, cur_meta = root_meta;
-    uint64_t cur_cnt = ld_counter(t, cur_slot);
-    BB S = root;
-    uint32_t depth = 0, plen = 0;
-    uint32_t ps0 = 0, ps1 = 0;  // node_path, lane l holds entries l and l+32
-    uint64_t pc0 = 0, pc1 = 0;
+    uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
+    uint32_t depth = 0, plen = 0, levels = 0;
     float v = 0.0f;
     for (;;) {
-      if (lane == kStatLevels) t.stat++;
+      levels++;
       if (depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
-        cur_cnt += kVisit;
         v = 0.0f;
         break;
       }
-      if (meta_is_terminal(cur_meta)) {  // :246-249 (+F6)
-        cur_cnt += kVisit;
+      if (cur_meta >= kMaxBlockId) {  // :246-249 (+F6) terminal node: value e
         v = terminal_e(cur_meta & 3u);
         if (lane == kStatTerminal) t.stat++;
         break;
       }
-      uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
-      uint4 w = make_uint4(0u, 0u, 0u, kMetaInvalid);
-      if (lane < 8) w = bp[lane];
-      const uint32_t flags = __shfl_sync(kFull, w.z, 7);
-      if (!(flags & kFlagHasPolicy)) {  // repair F1: an existing node that was never evaluated
-        cur_cnt += kVisit;
-        float pi, val;
-        evaluate_inline<EVAL>(S, lane, pi, val);
-        pi = mask_normalise(pi, (flags >> 8) & 0x7Fu, lane);
-        if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;             // set_policy
-        if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[2] = flags | kFlagHasPolicy;
-        if (lane == kStatEvals) t.stat++;
-        v = -val;
-        break;
-      }
-      cur_cnt += kVisit;  // :251 visit()
-      // best_child (node.rs:343-370): parent N is read after the visit
-      const float sq = __fsqrt_rn(__fadd_rn(static_cast<float>(counter_n(cur_cnt)), kEps));
-      uint64_t ccnt = (static_cast<uint64_t>(w.y) << 32) | w.x;
-      const float prior = __uint_as_float(w.z);
+      // best_child (node.rs:343-370); parent N is read after this simulation's visit()
+      const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
+      const uint4 w = bp[lane & 7];
+      uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
+      const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
       const uint32_t meta = w.w;
       const bool ok = lane < 7 && meta != kMetaInvalid;
-      uint32_t c_slot = cur_meta * 8u + lane, c_meta = meta;
+      float q = __uint_as_float(w.y);
       if (ok && meta == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
-        c_slot = w.x;
-        c_meta = w.y;
-        ccnt = ld_counter(t, c_slot);
+        q = ld_q(t, w.x);
+        nn = ld_n(t, w.x);
       }
-      const float u = ok ? puct_u(ccnt, prior, sq, p.cpuct_f) : 0.0f;
-      const uint32_t okey = ok ? ordered_key(u) : 0u;
-      const uint32_t mx = __reduce_max_sync(kFull, okey);
-      const uint32_t ball = __ballot_sync(kFull, ok && okey == mx);
-      if (ball == 0u) { t.error = kErrInternal; return; }  // node.rs:367 unwrap on empty
-      const int a = 31 - __clz(ball);  // max_by keeps the LAST maximum
-      const uint32_t ch_raw = __shfl_sync(kFull, meta, a);
-      const uint32_t ch_slot = __shfl_sync(kFull, c_slot, a);
-      const uint32_t ch_meta = __shfl_sync(kFull, c_meta, a);
-      const uint64_t ch_cnt = shfl64(ccnt, a);
-      // node_path.push(current_head_id) (:270 / F3)
-      if (lane == static_cast<int>(plen & 31u)) {
-        if (plen < 32u) { ps0 = cur_slot; pc0 = cur_cnt; } else { ps1 = cur_slot; pc1 = cur_cnt; }
-      }
+      const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
+      const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
+      const float at3 = fabsf(t3);
+      const bool risky = ok && (!((at3 >= 1e-30f && at3 < 1e30f) || t3 == 0.0f) || t4 == 0.0f);
+      float ex;
+      if (__any_sync(kFull, risky)) ex = __fdiv_rn(t3, t4);
+      else ex = fdiv_by_int(t3, t4);
+      const float u = ok ? __fadd_rn(q, ex) : neg_inf;
+      const float mx = redux_max_f32(u);
+      const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+      const int a = 31 - __clz(ball);  // max_by keeps the LAST maximum (node.rs:366)
+      if (a < 0) { t.error = kErrInternal; return; }  // node.rs:367 unwrap on an empty/NaN set
+      const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
+      // node_path.push(current_head_id) (:270 / F3) together with the action taken
+      if (lane == 0) t.path[plen] = (cur_slot << 3) | static_cast<uint32_t>(a);
       plen++;
-      const BB S2 = play_canonical(S, a);  // :284-287 with F4, F10
-      if (ch_raw == kMetaPlaceholder) {
+      if (ch_meta == kMetaPlaceholder) {
+        __syncwarp();
         const uint32_t my_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+        const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
         const uint64_t key2 = state_key(S2);
         uint32_t o_slot, o_meta, ins;
         if (tt_find(t, p.bucket_mask, key2, lane, o_slot, o_meta, ins)) {
@@ -263,8 +343,7 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
           __syncwarp();
           cur_slot = o_slot;
           cur_meta = o_meta;
-          cur_cnt = ld_counter(t, o_slot);
-          S = S2;
+          par_n = ld_n(t, o_slot);
           continue;
         }
         if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return; }
@@ -282,7 +361,7 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
           evaluate_inline<EVAL>(S2, lane, pi, val);
           const uint32_t vm = valid_mask(S2.cur | S2.opp);
           pi = mask_normalise(pi, vm, lane);
-          write_child_block(t, new_meta, key2, vm, pi, kFlagHasPolicy, my_slot, lane);
+          write_child_block(t, new_meta, vm, pi, kFlagHasPolicy, lane);
           if (lane == kStatEvals) t.stat++;
           v = -val;  // :353
         }
@@ -290,42 +369,43 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
         tt_insert(t, ins, key2, my_slot, new_meta, lane);
         t.n_owners++;
         if (lane == kStatExpansions) t.stat++;
-        cur_slot = my_slot;
-        cur_cnt = kCounterInit + kVisit;  // :309 visit() of the fresh node
+        cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
         break;
       }
-      cur_slot = ch_slot;
-      cur_meta = ch_meta;
-      cur_cnt = ch_cnt;
-      S = S2;
+      if (ch_meta == kMetaLink) {
+        cur_slot = __shfl_sync(kFull, w.x, a);
+        cur_meta = __shfl_sync(kFull, w.y, a);
+      } else {
+        cur_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+        cur_meta = ch_meta;
+      }
+      par_n = __shfl_sync(kFull, nn, a);
       depth++;
     }
-    // backup (:361-370): the leaf gets +v, then up node_path; Q2 corrected alternates the sign
-    {
-      if (lane < static_cast<int>(plen)) {
-        const bool neg = alternate && ((plen - static_cast<uint32_t>(lane)) & 1u);
-        st_counter(t, ps0, counter_unvisit(pc0, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks));
+    // backup (:361-370): the leaf gets +v, then up node_path; Q2 corrected alternates the sign.
+    // Entry l < plen is path node l, entry plen is the leaf; the sign flips with distance.
+    __syncwarp();
+    for (uint32_t base = 0; base <= plen; base += 32u) {
+      const uint32_t l = base + lane;
+      if (l <= plen) {
+        const uint32_t slot = l < plen ? (t.path[l] >> 3) : cur_slot;
+        const bool neg = alternate && ((plen - l) & 1u);
+        backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
       }
-      if (lane + 32 < static_cast<int>(plen)) {
-        const bool neg = alternate && ((plen - static_cast<uint32_t>(lane) - 32u) & 1u);
-        st_counter(t, ps1, counter_unvisit(pc1, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks));
-      }
-      if (lane == 0) st_counter(t, cur_slot, counter_unvisit(cur_cnt, __fmul_rn(1.0f, v), p.quirks));
-      if (lane == kStatSims) t.stat++;
     }
+    if (lane == kStatSims) t.stat++;
+    if (lane == kStatLevels) t.stat += levels;
     __syncwarp();
   }
 }
 
 // counts[a] = N of the (resolved) root child (async_mcts.rs:87-94 with F7).  Lane a returns it.
 __device__ __forceinline__ uint32_t root_child_count(const WarpTree& t, uint32_t root_meta, int lane) {
-  if (!meta_is_block(root_meta)) return 0u;
-  uint4 w = make_uint4(0u, 0u, 0u, kMetaInvalid);
-  if (lane < 7) w = t.blocks[static_cast<size_t>(root_meta) * 8u + lane];
-  if (lane >= 7 || w.w == kMetaInvalid) return 0u;
-  uint64_t c = (static_cast<uint64_t>(w.y) << 32) | w.x;
-  if (w.w == kMetaLink) c = ld_counter(t, w.x);
-  return counter_n(c);
+  if (!meta_is_block(root_meta) || lane >= 7) return 0u;
+  const uint32_t slot = root_meta * 8u + lane;
+  const uint4 w = t.blocks[slot];
+  if (w.w == kMetaInvalid) return 0u;
+  return ld_n(t, w.w == kMetaLink ? w.x : slot);
 }
 
 // pi from counts (async_mcts.rs:96-114 with F8, App. B.7).  temp == 0: one-hot on the last

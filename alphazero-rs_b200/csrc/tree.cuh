@@ -3,19 +3,23 @@
 // Replaces src/node.rs of the reference (Node, NodeStore).  One tree = one pool of 128-byte
 // child blocks in HBM plus one open-addressing transposition table:
 //
-//   block (128 B, one cache line, one coalesced warp load per selection level)
-//     slot[a], a = 0..6  {u64 counter; f32 prior; u32 meta}   the edge "play action a"
-//     header             {u64 key;     u32 flags; u32 self_slot}
+//   block (128 B = one cache line, read once per selection level)
+//     slot[a], a = 0..6  {u32 w; f32 q; f32 prior; u32 meta}     the edge "play action a"
+//     header (slot 7)    {u16 n[7]; u16 flags}
 //
-// * counter = the reference's packed word 0xWWWWWWWWNNNNVVVV (node.rs:17,36) of the node
-//   the slot OWNS (the reference's child slot is the node itself once upgraded).
-// * prior   = P[a] of the parent: edge data stays on the raw slot (repair F7).
-// * meta    = what the slot is: INVALID (illegal action), PLACEHOLDER (node.rs NodeState::
-//   PlaceHolder), a block id (expanded owner: its children live in that block), TERMINAL|code
-//   (owner whose game has ended, no children), or LINK (NodeState::Exists(false), a
-//   transposition link, node.rs:284-289): then the counter field holds
-//   {lo32 = owner slot id, hi32 = the owner's meta} so one extra 8-byte load resolves it.
-// * slot id = block_id*8 + a.
+// * (w, n[a]) = the W and N fields of the reference's packed word 0xWWWWWWWWNNNNVVVV
+//   (node.rs:17,36) of the node the slot OWNS.  The VL field is not stored: in deterministic
+//   mode (one simulation in flight per tree) it is 0 whenever a counter is at rest, and the
+//   search reconstructs the full 64-bit word for every update, so carries (N overflowing into
+//   W, quirk Q6) behave exactly like the reference's fetch_add/fetch_sub.
+// * q = compute_q() (node.rs:51-58) of that word, cached when the word changes (backup), so
+//   that selection needs no division for Q.
+// * prior = P[a] of the parent: edge data stays on the raw slot (repair F7).
+// * meta = what the slot is: INVALID (illegal action), PLACEHOLDER (NodeState::PlaceHolder),
+//   a block id (expanded owner: its children live in that block), TERMINAL|code (owner whose
+//   game has ended, no children), or LINK (NodeState::Exists(false), a transposition link,
+//   node.rs:284-289): then {w, q} hold {owner slot id, owner meta}.
+// * slot id = block_id*8 + a (indexes the pool as an array of 16-byte slots).
 #pragma once
 #include <cstdint>
 
@@ -41,6 +45,11 @@ constexpr uint32_t kMaxBlockId = 0xFFFFFF00u;
 
 constexpr uint32_t kFlagHasPolicy = 1u;
 constexpr uint32_t kFlagRootHolder = 2u;
+constexpr uint32_t kWBias = 0x7FFFFFFFu;  // W field of a fresh node (node.rs:36)
+
+AZB_HD uint64_t counter_pack(uint32_t w, uint32_t n) {
+  return (static_cast<uint64_t>(w) << 32) | (static_cast<uint64_t>(n & 0xFFFFu) << 16);
+}
 
 AZB_HD bool meta_is_block(uint32_t m) { return m < kMaxBlockId; }
 AZB_HD bool meta_is_terminal(uint32_t m) { return (m & 0xFFFFFFFCu) == kMetaTerminal && (m & 3u); }
@@ -99,6 +108,15 @@ AZB_HD float puct_u(uint64_t child, float prior, float sqrt_parent, float cpuct_
   float t3 = AZB_FMUL(AZB_FMUL(cpuct_f, prior), sqrt_parent);
   float t4 = static_cast<float>((1u + n) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
   return AZB_FADD(q, AZB_FDIV(t3, t4));
+}
+
+// compute_q (node.rs:51-58) of a full counter word.
+AZB_HD float counter_q(uint64_t c) {
+  uint32_t n = counter_n(c);
+  if (n == 0) return 0.0f;
+  long long w_raw = static_cast<long long>(c >> 32) - 0x7FFFFFFFll;
+  float w = AZB_FDIV(static_cast<float>(w_raw), kWinScale);
+  return AZB_FDIV(AZB_FSUB(w, static_cast<float>(counter_vl(c))), static_cast<float>(n));
 }
 
 // Transposition table entry (NodeStore.seen, node.rs:135): key -> owner slot + owner meta.

@@ -173,6 +173,11 @@ int azb_mcts_stats(azb_mcts* m, uint64_t* stats);
 int azb_mcts_dump(azb_mcts* m, uint64_t tree, uint64_t cap, uint64_t* keys, uint64_t* counters,
                   float* e, float* p7, uint8_t* has_p, uint64_t* n_rows);
 
+/* Diagnostic: compares the level loop's slow-path-free f32 division / square root with the
+ * IEEE-rounded CUDA intrinsics, exhaustively over the integer denominators / visit counts they
+ * are used on.  mismatches[3] = {reciprocal, sqrt, division}; all must be 0. */
+int azb_selftest_arith(uint64_t mismatches[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,3 +94,8 @@ def test_pool_overflow_is_an_error(azb, oracle):
     with pytest.raises(azb.AzbError) as e:
         m.get_action_prob(oracle.init_board(1), 1.0)
     assert e.value.code == azb.ERR_CAPACITY
+
+
+def test_fast_arithmetic_is_ieee_exact(azb):
+    # the level loop's division / sqrt without slow-path calls vs __frcp_rn/__fsqrt_rn/__fdiv_rn
+    assert azb.selftest_arith() == [0, 0, 0]
