@@ -138,6 +138,9 @@ int capacity_error(uint32_t code) {
 template <int EVAL>
 static int resident_trees(int device, uint32_t* out) {
   int per_sm = 0, sms = 0;
+  // the search lives on L1 hits of the hot tree top: keep the unified L1/shared array as L1
+  AZB_CUDA(cudaFuncSetAttribute(k_selfplay<EVAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                8 /* percent: 7 CTAs x (768 B + 1 KB reserved) fit in the 16 KB configuration */));
   AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay<EVAL>, kWarpsPerCta * 32, 0));
   AZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   *out = static_cast<uint32_t>(per_sm * sms * kWarpsPerCta);

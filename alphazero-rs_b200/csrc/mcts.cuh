@@ -254,7 +254,12 @@ __device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, fl
   uint64_t c = ld_counter(t, slot) + kVisit;
   c = counter_unvisit(c, v, quirks);
   *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q(c)));
-  *n_ptr(t, slot) = static_cast<uint16_t>(counter_n(c));
+  // n[] is updated with a 32-bit read-modify-write: sub-word global stores knock the whole line
+  // out of L1 (measured: profiles/r1_v2_selfplay_ncu.md), and the next simulation re-reads it.
+  // No other lane touches this block's header during a backup (path nodes sit in distinct blocks).
+  uint32_t* word = reinterpret_cast<uint32_t*>(t.blocks + (slot | 7u)) + ((slot & 7u) >> 1);
+  const uint32_t sh = (slot & 1u) * 16u;
+  *word = (*word & ~(0xFFFFu << sh)) | (counter_n(c) << sh);
 }
 
 // ---- search_iteration x nsims (async_mcts.rs:191-371) ------------------------
