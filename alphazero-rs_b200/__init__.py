@@ -145,7 +145,7 @@ def device_count():
 
 def selftest_arith():
     """{reciprocal, sqrt, division} mismatches of the fast f32 helpers vs the IEEE intrinsics."""
-    out = np.zeros(3, np.uint64)
+    out = np.zeros(4, np.uint64)
     _check(lib.azb_selftest_arith(_ptr(out)))
     return out.tolist()
 

@@ -287,15 +287,15 @@ int azb_c4_to_features(const azb_c4_state* in, size_t n, float* out) {
   return c4_batch(kOpFeatures, in, nullptr, nullptr, nullptr, 0, n, nullptr, 0, nullptr, nullptr, 0, out, 84);
 }
 
-int azb_selftest_arith(uint64_t mismatches[3]) {
+int azb_selftest_arith(uint64_t mismatches[4]) {
   if (!mismatches) return fail(AZB_ERR_INVALID, "NULL argument");
   if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
   DevBuf d;
-  AZB_CUDA(d.ensure(24));
-  AZB_CUDA(cudaMemset(d.p, 0, 24));
+  AZB_CUDA(d.ensure(32));
+  AZB_CUDA(cudaMemset(d.p, 0, 32));
   k_selftest_arith<<<256, 256>>>(d.as<unsigned long long>());
   AZB_CUDA(cudaGetLastError());
-  AZB_CUDA(cudaMemcpy(mismatches, d.p, 24, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(mismatches, d.p, 32, cudaMemcpyDeviceToHost));
   return AZB_OK;
 }
 

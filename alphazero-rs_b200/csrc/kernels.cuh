@@ -22,7 +22,7 @@ __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchPa
   t.blocks = pools.blocks + static_cast<size_t>(tree) * p.cap_blocks * 8u;
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
   t.path = s_path[(threadIdx.x >> 5) % kWarpsPerCta];
-  t.n_blocks = t.n_owners = t.error = 0u;
+  t.n_blocks = t.n_owners = t.error = t.slow = 0u;
   t.stat = 0u;
   return t;
 }
@@ -47,6 +47,7 @@ k_mcts_search(SearchParams p, Pools pools, const BB* __restrict__ states, float 
   t.n_owners = rec->n_owners;
   t.error = rec->error;
   if (t.error) return;
+  t.slow = rec->slow | (rec->stat[kStatSims] + p.num_sims >= kSafeVisits ? 1u : 0u);
   const BB s = states[tree];
   uint32_t rs = 0, rm = 0;
   if (make_root(t, p, s, lane, rs, rm)) {  // lookup_state_id (:81), F12 on a miss
@@ -64,6 +65,7 @@ k_mcts_search(SearchParams p, Pools pools, const BB* __restrict__ states, float 
     rec->n_blocks = t.n_blocks;
     rec->n_owners = t.n_owners;
     rec->error = t.error;
+    rec->slow = t.slow;
   }
   if (lane < kNumStats) rec->stat[lane] += t.stat;
 }
@@ -137,7 +139,7 @@ k_selfplay(SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n
     if (gi >= n_games) break;
     // AsyncMcts::default (coach.rs:246-255): a fresh tree per episode
     clear_table(t, p, lane);
-    t.n_blocks = t.n_owners = t.error = 0u;
+    t.n_blocks = t.n_owners = t.error = t.slow = 0u;
     t.stat = 0u;
     BB board{0ull, 0ull};  // canonical board of the side to move (coach.rs:120)
     int player = 1;        // :114
@@ -148,6 +150,7 @@ k_selfplay(SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n
       const float temp = step < p.temp_threshold ? 1.0f : 0.0f;  // :122-126
       uint32_t rs = 0, rm = 0;
       if (!make_root(t, p, board, lane, rs, rm)) break;          // get_action_prob :81 (+F12)
+      if (step * p.num_sims >= kSafeVisits) t.slow = 1u;
       run_sims<EVAL>(t, p, board, rs, rm, p.num_sims, lane);     // :82
       if (t.error) break;
       const uint32_t cnt = root_child_count(t, rm, lane);
@@ -227,7 +230,7 @@ __global__ void k_export_samples(GameBufs g, const uint64_t* __restrict__ offset
 __global__ void k_selftest_arith(unsigned long long* mismatches) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
-  unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0;
+  unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0, bad_q = 0;
   for (uint32_t b = 1u + tid; b <= 65536u; b += nthreads) {
     const float fb = static_cast<float>(b);
     if (rcp_int(fb) != __frcp_rn(fb)) bad_rcp++;
@@ -240,8 +243,13 @@ __global__ void k_selftest_arith(unsigned long long* mismatches) {
       float a = __uint_as_float((s & 0x807FFFFFu) | ((67u + (s >> 23) % 120u) << 23));
       if (k == 0) a = 0.0f;
       if (fdiv_by_int(a, fb) != __fdiv_rn(a, fb)) bad_div++;
+      // counters at rest: N = b (mod 2^16), W_raw spread over +-2^25 (dense) and the full range
+      const uint32_t wr = (k & 1) ? (0x7FFFFFFFu + (s >> 6) - (1u << 25)) : (s ^ (s << 7));
+      const uint64_t c = counter_pack(wr, b);
+      if (__float_as_uint(counter_q_fast(c)) != __float_as_uint(counter_q(c))) bad_q++;
     }
   }
+  if (bad_q) atomicAdd(mismatches + 3, bad_q);
   if (bad_rcp) atomicAdd(mismatches + 0, bad_rcp);
   if (bad_sqrt) atomicAdd(mismatches + 1, bad_sqrt);
   if (bad_div) atomicAdd(mismatches + 2, bad_div);

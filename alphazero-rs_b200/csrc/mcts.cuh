@@ -52,7 +52,7 @@ struct TreeRec {
   uint32_t n_blocks;
   uint32_t n_owners;  // == NodeStore.seen.len()
   uint32_t error;
-  uint32_t pad;
+  uint32_t slow;      // sticky: see WarpTree::slow
   uint32_t stat[8];
 };
 
@@ -62,8 +62,18 @@ struct WarpTree {
   uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}
   uint32_t* path;  // shared memory, kPathCap entries: (slot << 3) | action
   uint32_t n_blocks, n_owners, error;
+  uint32_t slow;  // != 0: use __fdiv_rn in the level loop (a prior outside the range the FMA division
+                  // is proven for, or visit counts that may wrap the 16-bit N field, quirk Q6)
   uint32_t stat;
 };
+
+// Visit counts stay below this => (1 + n) & 0xFFFF is never 0 in the level loop.
+constexpr uint32_t kSafeVisits = 65000u;
+// cpuct * prior * sqrt(N) (sqrt(N) in [1, 256]) must stay a normal, finite float for fdiv_by_int.
+__device__ __forceinline__ bool prior_needs_slow_div(float cpuct_f, float prior) {
+  const float at = fabsf(__fmul_rn(cpuct_f, prior));
+  return !(at == 0.0f || (at >= 1e-28f && at < 1e27f));
+}
 
 // ---- slot field access ------------------------------------------------------------------
 __device__ __forceinline__ uint16_t* n_ptr(const WarpTree& t, uint32_t slot) {
@@ -107,6 +117,23 @@ __device__ __forceinline__ float sqrt_count(float x) {
   const float h = __fmul_rn(0.5f, y);
   const float d = __fmaf_rn(-s, s, x);
   return __fmaf_rn(d, h, s);
+}
+// compute_q (node.rs:51-58) of a counter at rest (VL = 0) without slow-path calls: W/100 with the
+// constant reciprocal RN(1/100) and two Markstein corrections, then /N by fdiv_by_int.  Checked
+// against counter_q() by azb_selftest_arith.
+__device__ __forceinline__ float counter_q_fast(uint64_t c) {
+  const uint32_t n = counter_n(c);
+  const uint32_t hi = static_cast<uint32_t>(c >> 32);
+  if (n == 0u) return 0.0f;
+  if (hi > 0xFFFFFF00u || counter_vl(c) != 0u) return counter_q(c);
+  const float wf = static_cast<float>(static_cast<int>(hi - 0x7FFFFFFFu));
+  const float r = 0.01f;  // RN(1/100)
+  const float q0 = __fmul_rn(wf, r);
+  const float e0 = __fmaf_rn(-kWinScale, q0, wf);
+  const float q1 = __fmaf_rn(e0, r, q0);
+  const float e1 = __fmaf_rn(-kWinScale, q1, wf);
+  const float w = __fmaf_rn(e1, r, q1);
+  return fdiv_by_int(w, static_cast<float>(n));
 }
 __device__ __forceinline__ float redux_max_f32(float v) {
   float m;
@@ -253,7 +280,7 @@ __device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t p
 __device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
   uint64_t c = ld_counter(t, slot) + kVisit;
   c = counter_unvisit(c, v, quirks);
-  *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q(c)));
+  *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q_fast(c)));
   // n[] is updated with a 32-bit read-modify-write: sub-word global stores knock the whole line
   // out of L1 (measured: profiles/r1_v2_selfplay_ncu.md), and the next simulation re-reads it.
   // No other lane touches this block's header during a backup (path nodes sit in distinct blocks).
@@ -269,6 +296,9 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
                                          int lane) {
   const bool alternate = !(p.quirks & AZB_Q2_BACKUP_NO_ALTERNATE);
   const float neg_inf = __uint_as_float(0xFF800000u);
+  // depth counts moves into existing nodes: at most 42 on this board, so the check is dead
+  // unless max_depth is smaller
+  const bool depth_check = p.max_depth < 43u;
   uint32_t sim = 0;
   // Repair F1: an existing, non-terminal node that was never evaluated (a stand-alone root at
   // its first visit) is evaluated when first reached; this consumes one simulation.  Only a
@@ -282,6 +312,7 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
       float pi, val;
       evaluate_inline<EVAL>(root, lane, pi, val);
       pi = mask_normalise(pi, vm, lane);
+      if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
       if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
       if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
       if (lane == 0) backup_node(t, root_slot, __fmul_rn(1.0f, -val), p.quirks);
@@ -297,7 +328,7 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
     float v = 0.0f;
     for (;;) {
       levels++;
-      if (depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
+      if (depth_check && depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
         v = 0.0f;
         break;
       }
@@ -314,22 +345,25 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
       const uint32_t meta = w.w;
       const bool ok = lane < 7 && meta != kMetaInvalid;
       float q = __uint_as_float(w.y);
-      if (ok && meta == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
-        q = ld_q(t, w.x);
-        nn = ld_n(t, w.x);
+      const bool is_link = ok && meta == kMetaLink;
+      if (__any_sync(kFull, is_link)) {  // resolve(): statistics come from the owner (node.rs:179-201)
+        if (is_link) {
+          q = ld_q(t, w.x);
+          nn = ld_n(t, w.x);
+        }
       }
       const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
       const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
-      const float at3 = fabsf(t3);
-      const bool risky = ok && (!((at3 >= 1e-30f && at3 < 1e30f) || t3 == 0.0f) || t4 == 0.0f);
       float ex;
-      if (__any_sync(kFull, risky)) ex = __fdiv_rn(t3, t4);
+      if (t.slow) ex = __fdiv_rn(t3, t4);
       else ex = fdiv_by_int(t3, t4);
       const float u = ok ? __fadd_rn(q, ex) : neg_inf;
       const float mx = redux_max_f32(u);
       const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
-      const int a = 31 - __clz(ball);  // max_by keeps the LAST maximum (node.rs:366)
-      if (a < 0) { t.error = kErrInternal; return; }  // node.rs:367 unwrap on an empty/NaN set
+      // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
+      // unwrap panics) flags the tree and lets this simulation run out on lane 0's slot.
+      if (ball == 0u) t.error = kErrInternal;
+      const int a = 31 - __clz(ball | 1u);
       const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
       // node_path.push(current_head_id) (:270 / F3) together with the action taken
       if (lane == 0) t.path[plen] = (cur_slot << 3) | static_cast<uint32_t>(a);
@@ -366,6 +400,7 @@ __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB 
           evaluate_inline<EVAL>(S2, lane, pi, val);
           const uint32_t vm = valid_mask(S2.cur | S2.opp);
           pi = mask_normalise(pi, vm, lane);
+          if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
           write_child_block(t, new_meta, vm, pi, kFlagHasPolicy, lane);
           if (lane == kStatEvals) t.stat++;
           v = -val;  // :353

@@ -175,8 +175,8 @@ int azb_mcts_dump(azb_mcts* m, uint64_t tree, uint64_t cap, uint64_t* keys, uint
 
 /* Diagnostic: compares the level loop's slow-path-free f32 division / square root with the
  * IEEE-rounded CUDA intrinsics, exhaustively over the integer denominators / visit counts they
- * are used on.  mismatches[3] = {reciprocal, sqrt, division}; all must be 0. */
-int azb_selftest_arith(uint64_t mismatches[3]);
+ * are used on.  mismatches[4] = {reciprocal, sqrt, division, cached Q}; all must be 0. */
+int azb_selftest_arith(uint64_t mismatches[4]);
 
 #ifdef __cplusplus
 }

@@ -98,4 +98,4 @@ def test_pool_overflow_is_an_error(azb, oracle):
 
 def test_fast_arithmetic_is_ieee_exact(azb):
     # the level loop's division / sqrt without slow-path calls vs __frcp_rn/__fsqrt_rn/__fdiv_rn
-    assert azb.selftest_arith() == [0, 0, 0]
+    assert azb.selftest_arith() == [0, 0, 0, 0]
