@@ -135,13 +135,12 @@ int capacity_error(uint32_t code) {
   }
 }
 
-template <int EVAL>
 static int resident_trees(int device, uint32_t* out) {
   int per_sm = 0, sms = 0;
   // the search lives on L1 hits of the hot tree top: keep the unified L1/shared array as L1
-  AZB_CUDA(cudaFuncSetAttribute(k_selfplay<EVAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  AZB_CUDA(cudaFuncSetAttribute(k_selfplay, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 8 /* percent: 7 CTAs x (768 B + 1 KB reserved) fit in the 16 KB configuration */));
-  AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay<EVAL>, kWarpsPerCta * 32, 0));
+  AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay, kWarpsPerCta * 32, 0));
   AZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   *out = static_cast<uint32_t>(per_sm * sms * kWarpsPerCta);
   return AZB_OK;
@@ -352,12 +351,8 @@ int azb_mcts_get_action_prob(azb_mcts* m, const azb_c4_state* states, float temp
   AZB_CUDA(cudaMemset(m->d_counts.p, 0, n * 7 * sizeof(uint16_t)));
   AZB_CUDA(cudaMemset(m->d_pi.p, 0, n * 7 * sizeof(float)));
   const unsigned grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (m->cfg.evaluator == AZB_EVAL_UNIFORM)
-    k_mcts_search<AZB_EVAL_UNIFORM><<<grid, kWarpsPerCta * 32>>>(m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
-                                                                 m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
-  else
-    k_mcts_search<AZB_EVAL_HASH><<<grid, kWarpsPerCta * 32>>>(m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
-                                                              m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
+  k_mcts_search<<<grid, kWarpsPerCta * 32>>>(m->cfg.evaluator, m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
+                                             m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
   AZB_CUDA(cudaGetLastError());
   AZB_CUDA(cudaDeviceSynchronize());
   AZB_CUDA(cudaMemcpy(counts, m->d_counts.p, n * 7 * sizeof(uint16_t), cudaMemcpyDeviceToHost));
@@ -451,8 +446,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   const SearchParams p = make_params(c->cfg, kMaxPlies);
   // how many trees live in HBM at once: all games, capped by co-resident warps, memory and config
   uint32_t resident = 0;
-  int rc = c->cfg.evaluator == AZB_EVAL_UNIFORM ? resident_trees<AZB_EVAL_UNIFORM>(c->cfg.device, &resident)
-                                                : resident_trees<AZB_EVAL_HASH>(c->cfg.device, &resident);
+  int rc = resident_trees(c->cfg.device, &resident);
   if (rc) return rc;
   size_t free_b = 0, total_b = 0;
   AZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -499,14 +493,8 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   AZB_CUDA(cudaEventCreate(&e1));
   const unsigned grid = static_cast<unsigned>((n_trees + kWarpsPerCta - 1) / kWarpsPerCta);
   AZB_CUDA(cudaEventRecord(e0));
-  if (c->cfg.evaluator == AZB_EVAL_UNIFORM)
-    k_selfplay<AZB_EVAL_UNIFORM><<<grid, kWarpsPerCta * 32>>>(p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
-                                                              static_cast<uint32_t>(G), first_game_id,
-                                                              c->next_game.as<unsigned int>());
-  else
-    k_selfplay<AZB_EVAL_HASH><<<grid, kWarpsPerCta * 32>>>(p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
-                                                           static_cast<uint32_t>(G), first_game_id,
-                                                           c->next_game.as<unsigned int>());
+  k_selfplay<<<grid, kWarpsPerCta * 32>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
+                                          static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
   AZB_CUDA(cudaGetLastError());
   AZB_CUDA(cudaEventRecord(e1));
   AZB_CUDA(cudaEventSynchronize(e1));

@@ -34,9 +34,8 @@ __device__ __forceinline__ void clear_table(const WarpTree& t, const SearchParam
 }
 
 // ---- AsyncMcts::get_action_prob for n_trees persistent trees (test hook) --------------------
-template <int EVAL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_mcts_search(SearchParams p, Pools pools, const BB* __restrict__ states, float temp,
+k_mcts_search(int ev_kind, SearchParams p, Pools pools, const BB* __restrict__ states, float temp,
               uint16_t* __restrict__ counts, float* __restrict__ pi_out, uint32_t n_trees) {
   const uint32_t tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -51,7 +50,7 @@ k_mcts_search(SearchParams p, Pools pools, const BB* __restrict__ states, float 
   const BB s = states[tree];
   uint32_t rs = 0, rm = 0;
   if (make_root(t, p, s, lane, rs, rm)) {  // lookup_state_id (:81), F12 on a miss
-    run_sims<EVAL>(t, p, s, rs, rm, p.num_sims, lane);
+    run_sims(t, p, ev_kind, s, rs, rm, p.num_sims, lane);
     if (!t.error) {
       const uint32_t cnt = root_child_count(t, rm, lane);
       const float pi = counts_to_pi(cnt, temp, lane);
@@ -124,9 +123,8 @@ struct GameBufs {
   uint32_t* stats;        // [n_games][8]  6 search stats, blocks used, owners
 };
 
-template <int EVAL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_selfplay(SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n_games,
+k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n_games,
            uint64_t first_game_id, unsigned int* next_game) {
   const uint32_t tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,7 +149,7 @@ k_selfplay(SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n
       uint32_t rs = 0, rm = 0;
       if (!make_root(t, p, board, lane, rs, rm)) break;          // get_action_prob :81 (+F12)
       if (step * p.num_sims >= kSafeVisits) t.slow = 1u;
-      run_sims<EVAL>(t, p, board, rs, rm, p.num_sims, lane);     // :82
+      run_sims(t, p, ev_kind, board, rs, rm, p.num_sims, lane);     // :82
       if (t.error) break;
       const uint32_t cnt = root_child_count(t, rm, lane);
       const float pi = counts_to_pi(cnt, temp, lane);

@@ -174,10 +174,9 @@ __device__ __forceinline__ void tt_insert(const WarpTree& t, uint32_t ins, uint6
 }
 
 // ---- leaf evaluators fused into the search (NNet::predict, src/nnet.rs:40-44) --------------
-// Lane a (< 7) returns pi[a]; `v` is warp-uniform.
-template <int EVAL>
-__device__ __forceinline__ void evaluate_inline(BB s, int lane, float& pi, float& v) {
-  if (EVAL == AZB_EVAL_UNIFORM) {  // examples/connect_four.rs:34-38
+// Lane a (< 7) returns pi[a]; `v` is warp-uniform.  `kind` is warp-uniform.
+__device__ __forceinline__ void evaluate_inline(int kind, BB s, int lane, float& pi, float& v) {
+  if (kind == AZB_EVAL_UNIFORM) {  // examples/connect_four.rs:34-38
     pi = __fdiv_rn(1.0f, 7.0f);
     v = 1.0f;
   } else {  // SURVEY App. B.6 hash evaluator
@@ -289,154 +288,209 @@ __device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, fl
   *word = (*word & ~(0xFFFFu << sh)) | (counter_n(c) << sh);
 }
 
-// ---- search_iteration x nsims (async_mcts.rs:191-371) ------------------------
-template <int EVAL>
-__device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, BB root,
-                                         uint32_t root_slot, uint32_t root_meta, uint32_t nsims,
-                                         int lane) {
+// ---- search_iteration (async_mcts.rs:219-371) --------------------------------
+// A simulation either completes, or — when the leaf must be evaluated by the batched network
+// (evaluator kind AZB_EVAL_NNET) — suspends after storing what is needed to finish it later.
+enum : uint32_t { kPendNone = 0, kPendRoot = 1, kPendExpand = 2 };
+struct Pending {
+  uint32_t kind;      // kPend*
+  uint32_t my_slot;   // expansion: the placeholder being upgraded
+  uint32_t new_meta;  // expansion: its freshly allocated child block
+  uint32_t vm;        // valid-move mask of the evaluated position
+  uint32_t plen;      // node_path length
+  uint32_t ins;       // free transposition-table entry for the new state
+  uint32_t levels;    // levels walked (statistic)
+  uint32_t pad;
+  uint64_t key;       // state key of the new node
+};
+
+// backup (:361-370): the leaf gets +v, then up node_path; Q2 corrected alternates the sign.
+// Entry l < plen is path node l, entry plen is the leaf; the sign flips with distance.
+__device__ __forceinline__ void backup_path(WarpTree& t, const SearchParams& p, uint32_t plen,
+                                            uint32_t leaf_slot, float v, uint32_t levels, int lane) {
   const bool alternate = !(p.quirks & AZB_Q2_BACKUP_NO_ALTERNATE);
+  __syncwarp();
+  for (uint32_t base = 0; base <= plen; base += 32u) {
+    const uint32_t l = base + lane;
+    if (l <= plen) {
+      const uint32_t slot = l < plen ? (t.path[l] >> 3) : leaf_slot;
+      const bool neg = alternate && ((plen - l) & 1u);
+      backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+    }
+  }
+  if (lane == kStatSims) t.stat++;
+  if (lane == kStatLevels) t.stat += levels;
+  __syncwarp();
+}
+
+// Repair F1, second half: the root's raw policy (lane a = pi[a]) and value are known.
+__device__ __forceinline__ void finish_root_eval(WarpTree& t, const SearchParams& p, uint32_t root_slot,
+                                                 uint32_t root_meta, float pi, float val, int lane) {
+  uint4* bp = t.blocks + static_cast<size_t>(root_meta) * 8u;
+  const uint32_t m = lane < 7 ? bp[lane].w : kMetaInvalid;
+  const uint32_t vm = __ballot_sync(kFull, m != kMetaInvalid) & 0x7Fu;
+  pi = mask_normalise(pi, vm, lane);
+  if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
+  if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
+  if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
+  if (lane == kStatEvals) t.stat++;
+  backup_path(t, p, 0u, root_slot, -val, 1u, lane);
+}
+
+// upgrade -> Some(true), second half (node.rs:290-322, async_mcts.rs:317-353): mask + normalise
+// the policy, publish the new node, back the value up.
+__device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p, const Pending& pd,
+                                              float pi, float val, int lane) {
+  pi = mask_normalise(pi, pd.vm, lane);
+  if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
+  write_child_block(t, pd.new_meta, pd.vm, pi, kFlagHasPolicy, lane);
+  if (lane == 0) reinterpret_cast<uint32_t*>(t.blocks + pd.my_slot)[3] = pd.new_meta;
+  tt_insert(t, pd.ins, pd.key, pd.my_slot, pd.new_meta, lane);
+  t.n_owners++;
+  if (lane == kStatEvals || lane == kStatExpansions) t.stat++;
+  backup_path(t, p, pd.plen, pd.my_slot, -val, pd.levels, lane);  // :353 returns -v
+}
+
+// True when the node needs the F1 root evaluation before it can be searched.
+__device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root_meta) {
+  return meta_is_block(root_meta) && !(block_flags(t, root_meta) & kFlagHasPolicy);
+}
+
+// One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
+// network evaluation: then `pd` describes the pending expansion and `leaf` is the position to
+// evaluate.  ev_kind < AZB_EVAL_NNET evaluates inline and never suspends.
+__device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
+                                        uint32_t root_slot, uint32_t root_meta, int lane,
+                                        Pending& pd, BB& leaf) {
   const float neg_inf = __uint_as_float(0xFF800000u);
   // depth counts moves into existing nodes: at most 42 on this board, so the check is dead
   // unless max_depth is smaller
   const bool depth_check = p.max_depth < 43u;
+  uint32_t cur_slot = root_slot, cur_meta = root_meta;
+  uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
+  uint32_t depth = 0, plen = 0, levels = 0;
+  float v = 0.0f;
+  for (;;) {
+    levels++;
+    if (depth_check && depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
+      v = 0.0f;
+      break;
+    }
+    if (cur_meta >= kMaxBlockId) {  // :246-249 (+F6) terminal node: value e
+      v = terminal_e(cur_meta & 3u);
+      if (lane == kStatTerminal) t.stat++;
+      break;
+    }
+    // best_child (node.rs:343-370); parent N is read after this simulation's visit()
+    const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
+    const uint4 w = bp[lane & 7];
+    uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
+    const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
+    const uint32_t meta = w.w;
+    const bool ok = lane < 7 && meta != kMetaInvalid;
+    float q = __uint_as_float(w.y);
+    const bool is_link = ok && meta == kMetaLink;
+    if (__any_sync(kFull, is_link)) {  // resolve(): statistics come from the owner (node.rs:179-201)
+      if (is_link) {
+        q = ld_q(t, w.x);
+        nn = ld_n(t, w.x);
+      }
+    }
+    const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
+    const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
+    float ex;
+    if (t.slow) ex = __fdiv_rn(t3, t4);
+    else ex = fdiv_by_int(t3, t4);
+    const float u = ok ? __fadd_rn(q, ex) : neg_inf;
+    const float mx = redux_max_f32(u);
+    const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+    // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
+    // unwrap panics) flags the tree and lets this simulation run out on lane 0's slot.
+    if (ball == 0u) t.error = kErrInternal;
+    const int a = 31 - __clz(ball | 1u);
+    const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
+    // node_path.push(current_head_id) (:270 / F3) together with the action taken
+    if (lane == 0) t.path[plen] = (cur_slot << 3) | static_cast<uint32_t>(a);
+    plen++;
+    if (ch_meta == kMetaPlaceholder) {
+      __syncwarp();
+      const uint32_t my_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+      const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
+      const uint64_t key2 = state_key(S2);
+      uint32_t o_slot, o_meta, ins;
+      if (tt_find(t, p.bucket_mask, key2, lane, o_slot, o_meta, ins)) {
+        // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
+        // owner without incrementing depth (async_mcts.rs:293-299)
+        if (lane == a) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
+        if (lane == kStatDupLinks) t.stat++;
+        __syncwarp();
+        cur_slot = o_slot;
+        cur_meta = o_meta;
+        par_n = ld_n(t, o_slot);
+        continue;
+      }
+      if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return true; }
+      // upgrade -> Some(true) (node.rs:290-322)
+      const int code = game_ended_code(S2, p.quirks);
+      if (code) {  // repair F5: terminal leaf, the net is skipped
+        const uint32_t new_meta = kMetaTerminal | static_cast<uint32_t>(code);
+        v = terminal_e(static_cast<uint32_t>(code));
+        if (lane == a) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+        tt_insert(t, ins, key2, my_slot, new_meta, lane);
+        t.n_owners++;
+        if (lane == kStatTerminal || lane == kStatExpansions) t.stat++;
+        cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
+        break;
+      }
+      if (t.n_blocks >= p.cap_blocks) { t.error = kErrBlocks; return true; }
+      pd.kind = kPendExpand;
+      pd.my_slot = my_slot;
+      pd.new_meta = t.n_blocks++;
+      pd.vm = valid_mask(S2.cur | S2.opp);
+      pd.plen = plen;
+      pd.ins = ins;
+      pd.levels = levels;
+      pd.key = key2;
+      if (ev_kind >= AZB_EVAL_NNET) {
+        leaf = S2;
+        return false;
+      }
+      float pi, val;
+      evaluate_inline(ev_kind, S2, lane, pi, val);
+      finish_expand(t, p, pd, pi, val, lane);
+      return true;
+    }
+    if (ch_meta == kMetaLink) {
+      cur_slot = __shfl_sync(kFull, w.x, a);
+      cur_meta = __shfl_sync(kFull, w.y, a);
+    } else {
+      cur_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+      cur_meta = ch_meta;
+    }
+    par_n = __shfl_sync(kFull, nn, a);
+    depth++;
+  }
+  backup_path(t, p, plen, cur_slot, v, levels, lane);
+  return true;
+}
+
+// search (:191-217) with num_threads = 1 and a fused evaluator: nsims simulations from `root`.
+__device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
+                                         uint32_t root_slot, uint32_t root_meta, uint32_t nsims,
+                                         int lane) {
   uint32_t sim = 0;
   // Repair F1: an existing, non-terminal node that was never evaluated (a stand-alone root at
   // its first visit) is evaluated when first reached; this consumes one simulation.  Only a
   // root can be in that state: every other node is evaluated by the simulation that creates it.
-  if (nsims > 0 && meta_is_block(root_meta)) {
-    const uint32_t flags = block_flags(t, root_meta);
-    if (!(flags & kFlagHasPolicy)) {
-      uint4* bp = t.blocks + static_cast<size_t>(root_meta) * 8u;
-      const uint32_t m = lane < 7 ? bp[lane].w : kMetaInvalid;
-      const uint32_t vm = __ballot_sync(kFull, m != kMetaInvalid) & 0x7Fu;
-      float pi, val;
-      evaluate_inline<EVAL>(root, lane, pi, val);
-      pi = mask_normalise(pi, vm, lane);
-      if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
-      if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
-      if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
-      if (lane == 0) backup_node(t, root_slot, __fmul_rn(1.0f, -val), p.quirks);
-      if (lane == kStatEvals || lane == kStatSims || lane == kStatLevels) t.stat++;
-      __syncwarp();
-      sim = 1;
-    }
+  if (nsims > 0 && root_needs_eval(t, root_meta)) {
+    float pi, val;
+    evaluate_inline(ev_kind, root, lane, pi, val);
+    finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
+    sim = 1;
   }
-  for (; sim < nsims; ++sim) {
-    uint32_t cur_slot = root_slot, cur_meta = root_meta;
-    uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
-    uint32_t depth = 0, plen = 0, levels = 0;
-    float v = 0.0f;
-    for (;;) {
-      levels++;
-      if (depth_check && depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
-        v = 0.0f;
-        break;
-      }
-      if (cur_meta >= kMaxBlockId) {  // :246-249 (+F6) terminal node: value e
-        v = terminal_e(cur_meta & 3u);
-        if (lane == kStatTerminal) t.stat++;
-        break;
-      }
-      // best_child (node.rs:343-370); parent N is read after this simulation's visit()
-      const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
-      const uint4 w = bp[lane & 7];
-      uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
-      const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
-      const uint32_t meta = w.w;
-      const bool ok = lane < 7 && meta != kMetaInvalid;
-      float q = __uint_as_float(w.y);
-      const bool is_link = ok && meta == kMetaLink;
-      if (__any_sync(kFull, is_link)) {  // resolve(): statistics come from the owner (node.rs:179-201)
-        if (is_link) {
-          q = ld_q(t, w.x);
-          nn = ld_n(t, w.x);
-        }
-      }
-      const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
-      const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
-      float ex;
-      if (t.slow) ex = __fdiv_rn(t3, t4);
-      else ex = fdiv_by_int(t3, t4);
-      const float u = ok ? __fadd_rn(q, ex) : neg_inf;
-      const float mx = redux_max_f32(u);
-      const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
-      // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
-      // unwrap panics) flags the tree and lets this simulation run out on lane 0's slot.
-      if (ball == 0u) t.error = kErrInternal;
-      const int a = 31 - __clz(ball | 1u);
-      const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
-      // node_path.push(current_head_id) (:270 / F3) together with the action taken
-      if (lane == 0) t.path[plen] = (cur_slot << 3) | static_cast<uint32_t>(a);
-      plen++;
-      if (ch_meta == kMetaPlaceholder) {
-        __syncwarp();
-        const uint32_t my_slot = cur_meta * 8u + static_cast<uint32_t>(a);
-        const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
-        const uint64_t key2 = state_key(S2);
-        uint32_t o_slot, o_meta, ins;
-        if (tt_find(t, p.bucket_mask, key2, lane, o_slot, o_meta, ins)) {
-          // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
-          // owner without incrementing depth (async_mcts.rs:293-299)
-          if (lane == a) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
-          if (lane == kStatDupLinks) t.stat++;
-          __syncwarp();
-          cur_slot = o_slot;
-          cur_meta = o_meta;
-          par_n = ld_n(t, o_slot);
-          continue;
-        }
-        if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return; }
-        // upgrade -> Some(true) (node.rs:290-322)
-        const int code = game_ended_code(S2, p.quirks);
-        uint32_t new_meta;
-        if (code) {  // repair F5: terminal leaf, the net is skipped
-          new_meta = kMetaTerminal | static_cast<uint32_t>(code);
-          v = terminal_e(static_cast<uint32_t>(code));
-          if (lane == kStatTerminal) t.stat++;
-        } else {
-          if (t.n_blocks >= p.cap_blocks) { t.error = kErrBlocks; return; }
-          new_meta = t.n_blocks++;
-          float pi, val;
-          evaluate_inline<EVAL>(S2, lane, pi, val);
-          const uint32_t vm = valid_mask(S2.cur | S2.opp);
-          pi = mask_normalise(pi, vm, lane);
-          if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
-          write_child_block(t, new_meta, vm, pi, kFlagHasPolicy, lane);
-          if (lane == kStatEvals) t.stat++;
-          v = -val;  // :353
-        }
-        if (lane == a) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
-        tt_insert(t, ins, key2, my_slot, new_meta, lane);
-        t.n_owners++;
-        if (lane == kStatExpansions) t.stat++;
-        cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
-        break;
-      }
-      if (ch_meta == kMetaLink) {
-        cur_slot = __shfl_sync(kFull, w.x, a);
-        cur_meta = __shfl_sync(kFull, w.y, a);
-      } else {
-        cur_slot = cur_meta * 8u + static_cast<uint32_t>(a);
-        cur_meta = ch_meta;
-      }
-      par_n = __shfl_sync(kFull, nn, a);
-      depth++;
-    }
-    // backup (:361-370): the leaf gets +v, then up node_path; Q2 corrected alternates the sign.
-    // Entry l < plen is path node l, entry plen is the leaf; the sign flips with distance.
-    __syncwarp();
-    for (uint32_t base = 0; base <= plen; base += 32u) {
-      const uint32_t l = base + lane;
-      if (l <= plen) {
-        const uint32_t slot = l < plen ? (t.path[l] >> 3) : cur_slot;
-        const bool neg = alternate && ((plen - l) & 1u);
-        backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
-      }
-    }
-    if (lane == kStatSims) t.stat++;
-    if (lane == kStatLevels) t.stat += levels;
-    __syncwarp();
-  }
+  Pending pd;
+  BB leaf;
+  for (; sim < nsims && !t.error; ++sim) one_sim(t, p, ev_kind, root, root_slot, root_meta, lane, pd, leaf);
 }
 
 // counts[a] = N of the (resolved) root child (async_mcts.rs:87-94 with F7).  Lane a returns it.
