@@ -66,16 +66,26 @@ class Config(C.Structure):
         ("evaluator", C.c_int32),
         ("device", C.c_int32),
         ("max_concurrent_games", C.c_uint64),
+        ("schedule", C.c_uint32),
+        ("plies_per_launch", C.c_uint32),
     ]
 
 
 class SelfPlayStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "games", "plies", "samples", "sims", "levels", "expansions", "terminal_hits",
-        "dup_links", "evals", "blocks_used_max", "owners_max")] + [("device_ms", C.c_double)]
+        "dup_links", "evals", "blocks_used_max", "owners_max")] + [("device_ms", C.c_double), ("launches", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class NnetConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("blocks", C.c_int32), ("precision", C.c_int32),
+                ("reserved", C.c_int32), ("seed", C.c_uint64)]
+
+
+NNET_BF16_TC, NNET_FP32 = 0, 1
 
 
 def build_module():
@@ -119,6 +129,15 @@ def _load():
         "azb_mcts_stats": [vp, vp],
         "azb_mcts_dump": [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(u64)],
         "azb_selftest_arith": [vp],
+        "azb_nnet_create": [C.POINTER(NnetConfig), C.POINTER(vp)],
+        "azb_nnet_destroy": [vp],
+        "azb_nnet_predict": [vp, vp, sz, sz, vp, vp],
+        "azb_nnet_num_params": [vp, C.POINTER(u64)],
+        "azb_nnet_get_params": [vp, vp, u64],
+        "azb_nnet_set_params": [vp, vp, u64],
+        "azb_coach_set_nnet": [vp, vp],
+        "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
+                                 C.POINTER(SelfPlayStats)],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
@@ -304,11 +323,14 @@ class AsyncMcts:
 class Coach:
     """Coach::setup + the self-play half of Coach::learn (coach.rs:38-157, 241-272)."""
 
-    def __init__(self, **cfg):
+    def __init__(self, nnet=None, **cfg):
         self.cfg = cfg.pop("config", None) or default_config(**cfg)
         self._h = C.c_void_p()
         _check(lib.azb_coach_setup(C.byref(self.cfg), C.byref(self._h)))
         self.n_games = 0
+        self.nnet = nnet
+        if nnet is not None:
+            _check(lib.azb_coach_set_nnet(self._h, nnet._h))
 
     @classmethod
     def setup(cls, checkpoint_directory, mcts_reserve_size, update_threshold, temp_threshold,
@@ -366,3 +388,68 @@ class Coach:
         w = C.c_uint64()
         _check(lib.azb_coach_export_samples(self._h, _ptr(boards), _ptr(pis), _ptr(vs), len(vs), C.byref(w)))
         return boards[: w.value], pis[: w.value], vs[: w.value]
+
+
+class NNet:
+    """trait NNet (src/nnet.rs:35-45): new / predict (+ parameter access).  One handle = one model."""
+
+    def __init__(self, seed=7, blocks=6, precision=NNET_BF16_TC, device=0):
+        self.cfg = NnetConfig(device, blocks, precision, 0, seed)
+        self._h = C.c_void_p()
+        _check(lib.azb_nnet_create(C.byref(self.cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.azb_nnet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def predict(self, boards, model_id=0):
+        """boards[B,2,6,7] f32 -> (pi[B,7], v[B])  (nnet.rs:40-44)"""
+        boards = np.ascontiguousarray(boards, np.float32).reshape(-1, 2, 6, 7)
+        n = len(boards)
+        pi = np.zeros((n, 7), np.float32)
+        v = np.zeros(n, np.float32)
+        _check(lib.azb_nnet_predict(self._h, _ptr(boards), n, model_id, _ptr(pi), _ptr(v)))
+        return pi, v
+
+    def num_params(self):
+        n = C.c_uint64()
+        _check(lib.azb_nnet_num_params(self._h, C.byref(n)))
+        return n.value
+
+    def get_params(self):
+        out = np.zeros(self.num_params(), np.float32)
+        _check(lib.azb_nnet_get_params(self._h, _ptr(out), len(out)))
+        return out
+
+    def set_params(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        _check(lib.azb_nnet_set_params(self._h, _ptr(w), len(w)))
+
+
+def param_layout(blocks=6, channels=128):
+    """Offsets/shapes of the flat parameter vector (csrc/nnet.cuh NetLayout)."""
+    c = channels
+    spec = [("stem_w", (9, 2, c)), ("stem_b", (c,)), ("tower_w", (2 * blocks, 9, c, c)), ("tower_b", (2 * blocks, c)),
+            ("pol_w", (c, 2)), ("pol_b", (2,)), ("pol_fc_w", (84, 7)), ("pol_fc_b", (7,)), ("val_w", (c,)),
+            ("val_b", (1,)), ("val_fc1_w", (42, 64)), ("val_fc1_b", (64,)), ("val_fc2_w", (64,)), ("val_fc2_b", (1,))]
+    out, o = {}, 0
+    for name, shape in spec:
+        n = int(np.prod(shape))
+        out[name] = (o, shape)
+        o += n
+    out["total"] = o
+    return out
+
+
+def arena_play_games(num, eval_a, eval_b, net_a=None, net_b=None, k_open=0, **cfg):
+    """arena::play_games (src/arena.rs:62-99) with two MCTS players; returns ((win, loss, draw), results, stats)."""
+    config = cfg.pop("config", None) or default_config(**cfg)
+    counts = np.zeros(3, np.uint64)
+    results = np.zeros(max(1, 2 * (num // 2)), np.int8)
+    st = SelfPlayStats()
+    _check(lib.azb_arena_play_games(C.byref(config), num, eval_a, eval_b, net_a._h if net_a else None,
+                                    net_b._h if net_b else None, k_open, _ptr(counts), _ptr(results), C.byref(st)))
+    return tuple(int(x) for x in counts), results[: 2 * (num // 2)], st.as_dict()

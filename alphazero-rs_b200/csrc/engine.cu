@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -12,6 +13,8 @@
 
 #include "../../include/azb200.h"
 #include "kernels.cuh"
+#include "nnet.cuh"
+#include "rounds.cuh"
 
 using namespace azb;
 
@@ -62,8 +65,8 @@ int validate(const azb_config* cfg) {
     return fail(AZB_ERR_UNSUPPORTED,
                 "num_sim_threads must be 1 (deterministic mode: one simulation in flight per tree)");
   if (cfg->num_sims == 0 || cfg->num_sims > 60000) return fail(AZB_ERR_INVALID, "num_sims out of range");
-  if (cfg->evaluator != AZB_EVAL_UNIFORM && cfg->evaluator != AZB_EVAL_HASH)
-    return fail(AZB_ERR_UNSUPPORTED, "evaluator: only the fused UNIFORM and HASH evaluators exist yet");
+  if (cfg->evaluator < AZB_EVAL_UNIFORM || cfg->evaluator > AZB_EVAL_NNET)
+    return fail(AZB_ERR_INVALID, "evaluator must be AZB_EVAL_UNIFORM, AZB_EVAL_HASH or AZB_EVAL_NNET");
   if (cfg->mcts_reserve_size < 16) return fail(AZB_ERR_INVALID, "mcts_reserve_size too small");
   return AZB_OK;
 }
@@ -154,16 +157,140 @@ struct azb_mcts {
   DevBuf d_states, d_counts, d_pi, d_u64;
 };
 
+// ---- network handle (NNet::new / predict, src/nnet.rs:35-45) -----------------------------------
+struct azb_nnet {
+  azb_nnet_config cfg;
+  NetLayout L;
+  std::vector<float> h_params;
+  DevBuf d_params;
+  DevBuf d_feat, d_states, d_pi, d_v;  // azb_nnet_predict staging
+  int upload() {
+    AZB_CUDA(d_params.ensure(L.total * 4));
+    AZB_CUDA(cudaMemcpy(d_params.p, h_params.data(), L.total * 4, cudaMemcpyHostToDevice));
+    return AZB_OK;
+  }
+};
+
+namespace {
+// One dense forward pass over the first *d_count (or max_batch) positions.
+int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
+                 float* d_v, cudaStream_t st) {
+  if (max_batch == 0) return AZB_OK;
+  const size_t smem = (2 * kCells * kNetC + 256) * sizeof(float);
+  const unsigned grid = std::min<uint32_t>(max_batch, 148u * 4u);
+  k_nnet_fp32<<<grid, 128, smem, st>>>(net->d_params.as<float>(), net->L, d_states, d_count, max_batch, d_pi, d_v);
+  AZB_CUDA(cudaGetLastError());
+  return AZB_OK;
+}
+
+// Per-game outputs of a self-play / arena call.
+struct GameStore {
+  DevBuf plies, final_r, final_player, error, actions, counts, sample_state, sample_pi, stats, arena_result;
+  GameBufs g{};
+  int alloc(uint64_t G, bool samples) {
+    AZB_CUDA(plies.ensure(G * 4));
+    AZB_CUDA(final_r.ensure(G * 4));
+    AZB_CUDA(final_player.ensure(G));
+    AZB_CUDA(error.ensure(G * 4));
+    AZB_CUDA(actions.ensure(G * kTraceStride));
+    AZB_CUDA(counts.ensure(G * kTraceStride * 7 * 2));
+    if (samples) {
+      AZB_CUDA(sample_state.ensure(G * kMaxPlies * 16));
+      AZB_CUDA(sample_pi.ensure(G * kMaxPlies * 32));
+    }
+    AZB_CUDA(stats.ensure(G * 32));
+    AZB_CUDA(arena_result.ensure(G));
+    AZB_CUDA(cudaMemset(actions.p, 0xFF, G * kTraceStride));
+    AZB_CUDA(cudaMemset(counts.p, 0, G * kTraceStride * 7 * 2));
+    AZB_CUDA(cudaMemset(plies.p, 0, G * 4));
+    AZB_CUDA(cudaMemset(error.p, 0, G * 4));
+    AZB_CUDA(cudaMemset(stats.p, 0, G * 32));
+    AZB_CUDA(cudaMemset(arena_result.p, 0, G));
+    g.plies = plies.as<uint32_t>();
+    g.final_r = final_r.as<float>();
+    g.final_player = final_player.as<int8_t>();
+    g.error = error.as<uint32_t>();
+    g.actions = actions.as<uint8_t>();
+    g.counts = counts.as<uint16_t>();
+    g.sample_state = sample_state.as<uint4>();
+    g.sample_pi = sample_pi.as<float>();
+    g.stats = stats.as<uint32_t>();
+    return AZB_OK;
+  }
+};
+
+// Device state of the lock-step round engine (csrc/rounds.cuh).
+struct RoundEngine {
+  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v;
+  uint32_t n_slots = 0;
+  int alloc(uint32_t slots) {
+    n_slots = slots;
+    AZB_CUDA(recs.ensure(static_cast<size_t>(slots) * sizeof(GameRec)));
+    AZB_CUDA(active.ensure(static_cast<size_t>(slots) * 4));
+    AZB_CUDA(ctl_words.ensure(16));
+    AZB_CUDA(leaf_state.ensure(static_cast<size_t>(slots) * 2 * 16));
+    AZB_CUDA(leaf_count.ensure(8));
+    AZB_CUDA(leaf_pi.ensure(static_cast<size_t>(slots) * 2 * 32));
+    AZB_CUDA(leaf_v.ensure(static_cast<size_t>(slots) * 2 * 4));
+    AZB_CUDA(cudaMemset(recs.p, 0, static_cast<size_t>(slots) * sizeof(GameRec)));  // phase = Empty
+    AZB_CUDA(cudaMemset(ctl_words.p, 0, 16));
+    AZB_CUDA(cudaMemset(leaf_count.p, 0, 8));
+    return AZB_OK;
+  }
+  // Runs every game of the call to completion.  nets[k] evaluates the leaves of player k.
+  int run(const RoundParams& rp, const Pools& pools, GameStore& gs, azb_nnet* nets[2], uint64_t* launches) {
+    Control ctl{};
+    ctl.next_game = ctl_words.as<unsigned int>();
+    ctl.n_active = ctl_words.as<unsigned int>() + 1;
+    ctl.active_list = active.as<uint32_t>();
+    ctl.arena_result = gs.arena_result.as<int8_t>();
+    LeafBufs leaf{};
+    leaf.state = leaf_state.as<uint4>();
+    leaf.count = leaf_count.as<uint32_t>();
+    leaf.pi = leaf_pi.as<float>();
+    leaf.v = leaf_v.as<float>();
+    const bool any_net = rp.ev_kind[0] >= AZB_EVAL_NNET || (rp.mode == kModeArena && rp.ev_kind[1] >= AZB_EVAL_NNET);
+    const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int check_every = any_net ? 16 : 1;
+    uint64_t n_launch = 0;
+    for (uint64_t it = 0;; ++it) {
+      k_compact<<<1, 1024>>>(rp, recs.as<GameRec>(), ctl, leaf);
+      if (it % check_every == 0) {
+        unsigned int n_active = 0;
+        AZB_CUDA(cudaMemcpy(&n_active, ctl.n_active, 4, cudaMemcpyDeviceToHost));
+        if (n_active == 0) break;
+      }
+      k_round<<<grid, kWarpsPerCta * 32>>>(rp, pools, recs.as<GameRec>(), ctl, leaf, gs.g);
+      n_launch += 2;
+      if (any_net) {
+        for (int k = 0; k < 2; ++k) {
+          if (!nets[k] || rp.ev_kind[k] < AZB_EVAL_NNET) continue;
+          if (k == 1 && rp.mode != kModeArena) continue;
+          int rc = nnet_forward(nets[k], leaf.state + static_cast<size_t>(k) * rp.n_slots, leaf.count + k, rp.n_slots,
+                                leaf.pi + static_cast<size_t>(k) * rp.n_slots * 8, leaf.v + static_cast<size_t>(k) * rp.n_slots, 0);
+          if (rc) return rc;
+          n_launch += 1;
+        }
+      }
+      AZB_CUDA(cudaGetLastError());
+    }
+    if (launches) *launches = n_launch;
+    return AZB_OK;
+  }
+};
+}  // namespace
+
 struct azb_coach {
   azb_config cfg;
   TreePool pool;
   bool pool_ready = false;
+  azb_nnet* net = nullptr;
+  RoundEngine engine;
+  GameStore gs;
   // last self-play call
-  uint64_t n_games = 0, n_samples = 0;
-  DevBuf plies, final_r, final_player, error, actions, counts, sample_state, sample_pi, stats, next_game;
-  DevBuf offsets, out_boards, out_pis, out_vs;
+  uint64_t n_games = 0, n_samples = 0, launches = 0;
+  DevBuf next_game, offsets, out_boards, out_pis, out_vs;
   std::vector<uint32_t> h_plies;
-  GameBufs g{};
 };
 
 extern "C" {
@@ -201,6 +328,8 @@ void azb_config_default(azb_config* c) {  // examples/connect_four.rs:55-71
   c->evaluator = AZB_EVAL_UNIFORM;
   c->device = 0;
   c->max_concurrent_games = 0;
+  c->schedule = 0;
+  c->plies_per_launch = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -460,42 +589,46 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     c->pool_ready = true;
   }
   const uint64_t G = n_games;
-  AZB_CUDA(c->plies.ensure(G * 4));
-  AZB_CUDA(c->final_r.ensure(G * 4));
-  AZB_CUDA(c->final_player.ensure(G));
-  AZB_CUDA(c->error.ensure(G * 4));
-  AZB_CUDA(c->actions.ensure(G * kTraceStride));
-  AZB_CUDA(c->counts.ensure(G * kTraceStride * 7 * 2));
-  AZB_CUDA(c->sample_state.ensure(G * kMaxPlies * 16));
-  AZB_CUDA(c->sample_pi.ensure(G * kMaxPlies * 32));
-  AZB_CUDA(c->stats.ensure(G * 32));
-  AZB_CUDA(c->next_game.ensure(4));
-  AZB_CUDA(cudaMemset(c->actions.p, 0xFF, G * kTraceStride));
-  AZB_CUDA(cudaMemset(c->counts.p, 0, G * kTraceStride * 7 * 2));
-  AZB_CUDA(cudaMemset(c->plies.p, 0, G * 4));
-  AZB_CUDA(cudaMemset(c->next_game.p, 0, 4));
-  GameBufs g{};
-  g.plies = c->plies.as<uint32_t>();
-  g.final_r = c->final_r.as<float>();
-  g.final_player = c->final_player.as<int8_t>();
-  g.error = c->error.as<uint32_t>();
-  g.actions = c->actions.as<uint8_t>();
-  g.counts = c->counts.as<uint16_t>();
-  g.sample_state = c->sample_state.as<uint4>();
-  g.sample_pi = c->sample_pi.as<float>();
-  g.stats = c->stats.as<uint32_t>();
-  c->g = g;
+  rc = c->gs.alloc(G, true);
+  if (rc) return rc;
+  GameBufs g = c->gs.g;
   c->n_games = 0;
   c->n_samples = 0;
+  if (c->cfg.evaluator >= AZB_EVAL_NNET && !c->net)
+    return fail(AZB_ERR_INVALID, "evaluator NNET needs azb_coach_set_nnet first");
+  // schedule: 1 = one persistent kernel, a warp plays a whole game (fused evaluators only);
+  //           2 = lock-step rounds (k_compact / k_round [/ network forward]); 0 = pick
+  uint32_t schedule = c->cfg.schedule;
+  if (c->cfg.evaluator >= AZB_EVAL_NNET) schedule = 2;
+  else if (schedule == 0) schedule = 2;
 
   cudaEvent_t e0, e1;
   AZB_CUDA(cudaEventCreate(&e0));
   AZB_CUDA(cudaEventCreate(&e1));
-  const unsigned grid = static_cast<unsigned>((n_trees + kWarpsPerCta - 1) / kWarpsPerCta);
   AZB_CUDA(cudaEventRecord(e0));
-  k_selfplay<<<grid, kWarpsPerCta * 32>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
-                                          static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
-  AZB_CUDA(cudaGetLastError());
+  if (schedule == 1) {
+    AZB_CUDA(c->next_game.ensure(4));
+    AZB_CUDA(cudaMemset(c->next_game.p, 0, 4));
+    const unsigned grid = static_cast<unsigned>((n_trees + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_selfplay<<<grid, kWarpsPerCta * 32>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
+                                            static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
+    AZB_CUDA(cudaGetLastError());
+    c->launches = 1;
+  } else {
+    rc = c->engine.alloc(static_cast<uint32_t>(n_trees));
+    if (rc) return rc;
+    RoundParams rp{};
+    rp.p = p;
+    rp.mode = kModeSelfPlay;
+    rp.ev_kind[0] = rp.ev_kind[1] = c->cfg.evaluator;
+    rp.plies_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 0u : (c->cfg.plies_per_launch ? c->cfg.plies_per_launch : 2u);
+    rp.n_slots = static_cast<uint32_t>(n_trees);
+    rp.n_games = static_cast<uint32_t>(G);
+    rp.first_game_id = first_game_id;
+    azb_nnet* nets[2] = {c->net, nullptr};
+    rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches);
+    if (rc) return rc;
+  }
   AZB_CUDA(cudaEventRecord(e1));
   AZB_CUDA(cudaEventSynchronize(e1));
   float ms = 0.0f;
@@ -505,9 +638,9 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
 
   c->h_plies.resize(G);
   std::vector<uint32_t> h_err(G), h_stats(G * 8);
-  AZB_CUDA(cudaMemcpy(c->h_plies.data(), c->plies.p, G * 4, cudaMemcpyDeviceToHost));
-  AZB_CUDA(cudaMemcpy(h_err.data(), c->error.p, G * 4, cudaMemcpyDeviceToHost));
-  AZB_CUDA(cudaMemcpy(h_stats.data(), c->stats.p, G * 32, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(c->h_plies.data(), c->gs.plies.p, G * 4, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(h_err.data(), c->gs.error.p, G * 4, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(h_stats.data(), c->gs.stats.p, G * 32, cudaMemcpyDeviceToHost));
   azb_selfplay_stats s{};
   for (uint64_t i = 0; i < G; ++i) {
     if (h_err[i]) return capacity_error(h_err[i]);
@@ -524,6 +657,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   s.games = G;
   s.samples = s.plies * 2;
   s.device_ms = ms;
+  s.launches = c->launches;
   c->n_games = G;
   c->n_samples = s.samples;
   if (stats) *stats = s;
@@ -536,11 +670,11 @@ int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint
   if (c->n_games == 0) return fail(AZB_ERR_INVALID, "no self-play results");
   AZB_CUDA(cudaSetDevice(c->cfg.device));
   const uint64_t G = c->n_games;
-  if (actions) AZB_CUDA(cudaMemcpy(actions, c->actions.p, G * kTraceStride, cudaMemcpyDeviceToHost));
-  if (root_counts) AZB_CUDA(cudaMemcpy(root_counts, c->counts.p, G * kTraceStride * 14, cudaMemcpyDeviceToHost));
-  if (plies) AZB_CUDA(cudaMemcpy(plies, c->plies.p, G * 4, cudaMemcpyDeviceToHost));
-  if (final_r) AZB_CUDA(cudaMemcpy(final_r, c->final_r.p, G * 4, cudaMemcpyDeviceToHost));
-  if (final_player) AZB_CUDA(cudaMemcpy(final_player, c->final_player.p, G, cudaMemcpyDeviceToHost));
+  if (actions) AZB_CUDA(cudaMemcpy(actions, c->gs.actions.p, G * kTraceStride, cudaMemcpyDeviceToHost));
+  if (root_counts) AZB_CUDA(cudaMemcpy(root_counts, c->gs.counts.p, G * kTraceStride * 14, cudaMemcpyDeviceToHost));
+  if (plies) AZB_CUDA(cudaMemcpy(plies, c->gs.plies.p, G * 4, cudaMemcpyDeviceToHost));
+  if (final_r) AZB_CUDA(cudaMemcpy(final_r, c->gs.final_r.p, G * 4, cudaMemcpyDeviceToHost));
+  if (final_player) AZB_CUDA(cudaMemcpy(final_player, c->gs.final_player.p, G, cudaMemcpyDeviceToHost));
   return AZB_OK;
 }
 
@@ -568,7 +702,7 @@ int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs,
   AZB_CUDA(c->out_boards.ensure(N * 84 * 4));
   AZB_CUDA(c->out_pis.ensure(N * 7 * 4));
   AZB_CUDA(c->out_vs.ensure(N * 4));
-  k_export_samples<<<static_cast<unsigned>(G), 128>>>(c->g, c->offsets.as<uint64_t>(), c->cfg.quirks,
+  k_export_samples<<<static_cast<unsigned>(G), 128>>>(c->gs.g, c->offsets.as<uint64_t>(), c->cfg.quirks,
                                                       c->out_boards.as<float>(), c->out_pis.as<float>(),
                                                       c->out_vs.as<float>(), N);
   AZB_CUDA(cudaGetLastError());
@@ -576,6 +710,201 @@ int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs,
   AZB_CUDA(cudaMemcpy(pis, c->out_pis.p, N * 7 * 4, cudaMemcpyDeviceToHost));
   AZB_CUDA(cudaMemcpy(vs, c->out_vs.p, N * 4, cudaMemcpyDeviceToHost));
   if (n_written) *n_written = N;
+  return AZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NNet
+// ---------------------------------------------------------------------------------------------
+static uint64_t sm64(uint64_t& x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static void he_normal(float* w, size_t n, size_t fan_in, uint64_t& st) {
+  const double sd = std::sqrt(2.0 / static_cast<double>(fan_in));
+  for (size_t i = 0; i < n; i += 2) {
+    const double u1 = (static_cast<double>(sm64(st) >> 11) + 1.0) / 9007199254740993.0;
+    const double u2 = static_cast<double>(sm64(st) >> 11) / 9007199254740992.0;
+    const double r = std::sqrt(-2.0 * std::log(u1));
+    w[i] = static_cast<float>(sd * r * std::cos(6.283185307179586 * u2));
+    if (i + 1 < n) w[i + 1] = static_cast<float>(sd * r * std::sin(6.283185307179586 * u2));
+  }
+}
+
+int azb_nnet_create(const azb_nnet_config* cfg, azb_nnet** out) {
+  if (!cfg || !out) return fail(AZB_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (cfg->blocks < 1 || cfg->blocks > 40) return fail(AZB_ERR_INVALID, "blocks out of range");
+  if (cfg->precision != AZB_NNET_BF16_TC && cfg->precision != AZB_NNET_FP32) return fail(AZB_ERR_INVALID, "precision");
+  if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
+  AZB_CUDA(cudaSetDevice(cfg->device));
+  auto n = std::make_unique<azb_nnet>();
+  n->cfg = *cfg;
+  n->L = net_layout(cfg->blocks);
+  const NetLayout& L = n->L;
+  n->h_params.assign(L.total, 0.0f);
+  float* w = n->h_params.data();
+  uint64_t st = cfg->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  he_normal(w + L.stem_w, 9 * 2 * kNetC, 9 * 2, st);
+  he_normal(w + L.tower_w, static_cast<size_t>(2 * L.R) * 9 * kNetC * kNetC, 9 * kNetC, st);
+  he_normal(w + L.pol_w, kNetC * 2, kNetC, st);
+  he_normal(w + L.pol_fc_w, 84 * 7, 84, st);
+  he_normal(w + L.val_w, kNetC, kNetC, st);
+  he_normal(w + L.val_fc1_w, 42 * 64, 42, st);
+  he_normal(w + L.val_fc2_w, 64, 64, st);
+  int rc = n->upload();
+  if (rc) return rc;
+  *out = n.release();
+  return AZB_OK;
+}
+int azb_nnet_destroy(azb_nnet* n) {
+  delete n;
+  return AZB_OK;
+}
+int azb_nnet_num_params(azb_nnet* n, uint64_t* count) {
+  if (!n || !count) return fail(AZB_ERR_INVALID, "NULL argument");
+  *count = n->L.total;
+  return AZB_OK;
+}
+int azb_nnet_get_params(azb_nnet* n, float* out, uint64_t capacity) {
+  if (!n || !out) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (capacity < n->L.total) return fail(AZB_ERR_CAPACITY, "parameter buffer too small");
+  std::memcpy(out, n->h_params.data(), n->L.total * 4);
+  return AZB_OK;
+}
+int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count) {
+  if (!n || !in) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (count != n->L.total) return fail(AZB_ERR_INVALID, "parameter count mismatch");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  std::memcpy(n->h_params.data(), in, count * 4);
+  return n->upload();
+}
+int azb_nnet_predict(azb_nnet* n, const float* boards, size_t batch, size_t /*model_id*/, float* pi, float* v) {
+  if (!n || (batch && (!boards || !pi || !v))) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (batch == 0) return AZB_OK;
+  if (batch > (1u << 26)) return fail(AZB_ERR_INVALID, "batch too large");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  AZB_CUDA(n->d_feat.ensure(batch * 84 * 4));
+  AZB_CUDA(n->d_states.ensure(batch * 16));
+  AZB_CUDA(n->d_pi.ensure(batch * 32));
+  AZB_CUDA(n->d_v.ensure(batch * 4));
+  AZB_CUDA(cudaMemcpy(n->d_feat.p, boards, batch * 84 * 4, cudaMemcpyHostToDevice));
+  const uint32_t B = static_cast<uint32_t>(batch);
+  k_features_to_bb<<<(B + 127) / 128, 128>>>(n->d_feat.as<float>(), B, n->d_states.as<uint4>());
+  int rc = nnet_forward(n, n->d_states.as<uint4>(), nullptr, B, n->d_pi.as<float>(), n->d_v.as<float>(), 0);
+  if (rc) return rc;
+  AZB_CUDA(cudaGetLastError());
+  std::vector<float> h(batch * 8);
+  AZB_CUDA(cudaMemcpy(h.data(), n->d_pi.p, batch * 32, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < batch; ++i)
+    for (int a = 0; a < 7; ++a) pi[i * 7 + a] = h[i * 8 + a];
+  AZB_CUDA(cudaMemcpy(v, n->d_v.p, batch * 4, cudaMemcpyDeviceToHost));
+  return AZB_OK;
+}
+int azb_coach_set_nnet(azb_coach* c, azb_nnet* n) {
+  if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (n && n->cfg.device != c->cfg.device) return fail(AZB_ERR_INVALID, "network and coach live on different devices");
+  c->net = n;
+  return AZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------------
+int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
+                         azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
+                         azb_selfplay_stats* stats) {
+  if (!out_counts) return fail(AZB_ERR_INVALID, "NULL argument");
+  int rc = validate(cfg);
+  if (rc) return rc;
+  for (int k = 0; k < 2; ++k) {
+    const int32_t ev = k ? eval_b : eval_a;
+    if (ev < AZB_EVAL_UNIFORM || ev > AZB_EVAL_NNET) return fail(AZB_ERR_INVALID, "bad evaluator kind");
+    if (ev == AZB_EVAL_NNET && !(k ? net_b : net_a)) return fail(AZB_ERR_INVALID, "evaluator NNET needs a network");
+  }
+  const uint64_t half = num / 2, G = 2 * half;  // arena.rs:83: num / 2 games per seat order
+  out_counts[0] = out_counts[1] = out_counts[2] = 0;
+  if (G == 0) return AZB_OK;
+  if (G > (1u << 26)) return fail(AZB_ERR_INVALID, "num out of range");
+  if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
+  AZB_CUDA(cudaSetDevice(cfg->device));
+  // each player's tree sees every second ply: at most 21 searches + F12 roots
+  const SearchParams p = make_params(*cfg, kMaxPlies / 2 + 1);
+  uint32_t resident = 0;
+  rc = resident_trees(cfg->device, &resident);
+  if (rc) return rc;
+  size_t free_b = 0, total_b = 0;
+  AZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t by_mem = static_cast<uint64_t>(free_b) * 8 / 10 / (2 * tree_bytes(p));
+  uint64_t n_slots = std::min<uint64_t>({G, resident, by_mem});
+  if (cfg->max_concurrent_games) n_slots = std::min<uint64_t>(n_slots, cfg->max_concurrent_games);
+  if (n_slots == 0) return fail(AZB_ERR_CAPACITY, "not enough device memory for one tree pair");
+  TreePool pool;
+  rc = pool.alloc(p, static_cast<uint32_t>(2 * n_slots));
+  if (rc) return rc;
+  GameStore gs;
+  rc = gs.alloc(G, false);
+  if (rc) return rc;
+  RoundEngine eng;
+  rc = eng.alloc(static_cast<uint32_t>(n_slots));
+  if (rc) return rc;
+  RoundParams rp{};
+  rp.p = p;
+  rp.mode = kModeArena;
+  rp.ev_kind[0] = eval_a;
+  rp.ev_kind[1] = eval_b;
+  const bool any_net = eval_a >= AZB_EVAL_NNET || eval_b >= AZB_EVAL_NNET;
+  rp.plies_per_launch = any_net ? 0u : (cfg->plies_per_launch ? cfg->plies_per_launch : 2u);
+  rp.n_slots = static_cast<uint32_t>(n_slots);
+  rp.n_games = static_cast<uint32_t>(G);
+  rp.half = static_cast<uint32_t>(half);
+  rp.k_open = k_open;
+  rp.first_game_id = 0;
+  azb_nnet* nets[2] = {net_a, net_b};
+  cudaEvent_t e0, e1;
+  AZB_CUDA(cudaEventCreate(&e0));
+  AZB_CUDA(cudaEventCreate(&e1));
+  AZB_CUDA(cudaEventRecord(e0));
+  uint64_t launches = 0;
+  rc = eng.run(rp, pool.pools, gs, nets, &launches);
+  if (rc) return rc;
+  AZB_CUDA(cudaEventRecord(e1));
+  AZB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  std::vector<int8_t> res(G);
+  std::vector<uint32_t> h_err(G), h_stats(G * 8), h_plies(G);
+  AZB_CUDA(cudaMemcpy(res.data(), gs.arena_result.p, G, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(h_err.data(), gs.error.p, G * 4, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(h_stats.data(), gs.stats.p, G * 32, cudaMemcpyDeviceToHost));
+  AZB_CUDA(cudaMemcpy(h_plies.data(), gs.plies.p, G * 4, cudaMemcpyDeviceToHost));
+  azb_selfplay_stats s{};
+  for (uint64_t i = 0; i < G; ++i) {
+    if (h_err[i]) return capacity_error(h_err[i]);
+    const int win_cond = i < half ? 1 : -1;  // arena.rs:80-81
+    if (res[i] == win_cond) out_counts[0]++;
+    else if (res[i] == -win_cond) out_counts[1]++;
+    else out_counts[2]++;
+    s.plies += h_plies[i];
+    s.sims += h_stats[i * 8 + 0];
+    s.levels += h_stats[i * 8 + 1];
+    s.expansions += h_stats[i * 8 + 2];
+    s.terminal_hits += h_stats[i * 8 + 3];
+    s.dup_links += h_stats[i * 8 + 4];
+    s.evals += h_stats[i * 8 + 5];
+    s.blocks_used_max = std::max<uint64_t>(s.blocks_used_max, h_stats[i * 8 + 6]);
+    s.owners_max = std::max<uint64_t>(s.owners_max, h_stats[i * 8 + 7]);
+  }
+  s.games = G;
+  s.device_ms = ms;
+  s.launches = launches;
+  if (results) std::memcpy(results, res.data(), G);
+  if (stats) *stats = s;
   return AZB_OK;
 }
 

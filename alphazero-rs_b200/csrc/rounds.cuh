@@ -1,0 +1,358 @@
+// Lock-step round engine: thousands of concurrent games as resumable per-slot state machines.
+//
+// Replaces the thread plumbing of the reference's self-play path: the rayon episode pool
+// (src/coach.rs:202-205,241-272), the per-move scoped search threads (src/async_mcts.rs:191-217),
+// the inference thread with its channels (src/async_mcts.rs:117-189) and the sequential arena
+// loop (src/arena.rs:62-99).  A *slot* holds one game (self-play: one tree; arena: two trees, one
+// per player) and its complete state in HBM (GameRec), so any warp can continue it:
+//
+//   k_compact : recycles finished slots for pending games, rebuilds the dense active list
+//               (re-dealing the live games evenly over the SMs), resets the leaf batches;
+//   k_round   : one warp per active slot runs its game forward until the slot
+//                 - has a leaf that the batched network must evaluate (evaluator NNET): the
+//                   position goes to the dense leaf batch of its model and the simulation is
+//                   suspended (Pending + path saved), or
+//                 - has played `plies_per_launch` plies (fused evaluators), or finished its game;
+//   nnet forward (csrc/nnet.cuh) evaluates every pending leaf of a model in ONE dense pass
+//               (repairs F15/F16: leaves grouped per model, batches of whatever size exists).
+#pragma once
+#include "kernels.cuh"
+
+namespace azb {
+
+enum : uint32_t { kPhaseEmpty = 0, kPhaseFresh, kPhaseNewMove, kPhaseSearch, kPhasePending, kPhaseDone };
+enum : uint32_t { kModeSelfPlay = 0, kModeArena = 1 };
+
+struct TreeVars {
+  uint32_t n_blocks, n_owners, error, slow;
+  uint32_t stat[8];
+};
+
+struct __align__(16) GameRec {
+  uint64_t cur, opp;  // canonical board of the side to move (coach.rs:120 / arena.rs:25)
+  uint32_t game;      // index of the game within the call
+  uint32_t phase;
+  int32_t player;     // +1 / -1 to move (coach.rs:114, arena.rs:14)
+  uint32_t step;      // plies played so far + 1 while searching (coach.rs:116-119)
+  uint32_t sims_done;
+  uint32_t root_slot, root_meta;
+  uint32_t leaf_idx;  // dense index of the pending leaf in its model's batch
+  uint32_t pad[3];
+  Pending pd;
+  TreeVars tv[2];
+  uint32_t path[kPathCap];
+};
+
+struct LeafBufs {
+  uint4* state;     // [2][n_slots]  {cur.lo, cur.hi, opp.lo, opp.hi}: the feature planes as bitboards
+  uint32_t* count;  // [2]           leaves per model this round
+  float* pi;        // [2][n_slots][8]  network policy (probabilities), row = dense leaf index
+  float* v;         // [2][n_slots]
+};
+
+struct RoundParams {
+  SearchParams p;
+  uint32_t mode;
+  int32_t ev_kind[2];  // evaluator of player A / B (self-play: [0])
+  uint32_t plies_per_launch;
+  uint32_t n_slots, n_games;
+  uint32_t half;    // arena: games [0, half) seat A first, [half, 2*half) seat B first (arena.rs:74-83)
+  uint32_t k_open;  // arena: random opening plies
+  uint64_t first_game_id;
+};
+
+struct Control {
+  unsigned int* next_game;   // games handed out so far
+  unsigned int* n_active;    // live slots after k_compact
+  uint32_t* active_list;     // [n_slots]
+  int8_t* arena_result;      // [n_games] play_game's return value (arena.rs:51)
+};
+
+// ---- k_compact: one CTA ---------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_compact(RoundParams rp, GameRec* recs, Control ctl, LeafBufs leaf) {
+  __shared__ uint32_t s_scan[1024];
+  __shared__ uint32_t s_base;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) s_base = 0;
+  if (tid < 2) leaf.count[tid] = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < rp.n_slots; start += 1024u) {
+    const uint32_t slot = start + tid;
+    uint32_t alive = 0;
+    if (slot < rp.n_slots) {
+      uint32_t ph = recs[slot].phase;
+      if (ph == kPhaseEmpty || ph == kPhaseDone) {
+        ph = kPhaseEmpty;
+        if (*ctl.next_game < rp.n_games) {  // cheap pre-check, then claim
+          const unsigned int g = atomicAdd(ctl.next_game, 1u);
+          if (g < rp.n_games) {
+            recs[slot].game = g;
+            ph = kPhaseFresh;
+          }
+        }
+        recs[slot].phase = ph;
+      }
+      alive = ph != kPhaseEmpty;
+    }
+    s_scan[tid] = alive;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {  // inclusive Hillis-Steele scan
+      const uint32_t v = tid >= off ? s_scan[tid - off] : 0u;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (alive) ctl.active_list[s_base + s_scan[tid] - 1u] = slot;
+    __syncthreads();
+    if (tid == 1023) s_base += s_scan[1023];
+    __syncthreads();
+  }
+  if (tid == 0) *ctl.n_active = s_base;
+}
+
+// ---- per-ply bookkeeping shared with k_selfplay ------------------------------------------------
+// get_action_prob's tail (async_mcts.rs:84-114) + execute_episode's move (coach.rs:130-155).
+// Returns the game_ended code of the position after the move (0 = game goes on).
+__device__ __forceinline__ uint32_t selfplay_move(const WarpTree& t, const SearchParams& p, GameBufs g,
+                                                  uint32_t gi, uint64_t game_id, uint32_t step, BB& board,
+                                                  int& player, uint32_t root_meta, int lane, uint32_t& err) {
+  const float temp = step < p.temp_threshold ? 1.0f : 0.0f;  // :122-126
+  const uint32_t cnt = root_child_count(t, root_meta, lane);
+  const float pi = counts_to_pi(cnt, temp, lane);
+  const uint32_t ply = step - 1u;
+  const size_t grow = static_cast<size_t>(gi) * kTraceStride + ply;
+  const size_t srow = static_cast<size_t>(gi) * kMaxPlies + ply;
+  if (lane < 7) {
+    g.counts[grow * 7u + lane] = static_cast<uint16_t>(cnt);
+    g.sample_pi[srow * 8u + lane] = pi;
+  }
+  if (lane == 7) g.sample_pi[srow * 8u + 7u] = static_cast<float>(player);
+  if (lane == 8)
+    g.sample_state[srow] = make_uint4(static_cast<uint32_t>(board.cur), static_cast<uint32_t>(board.cur >> 32),
+                                      static_cast<uint32_t>(board.opp), static_cast<uint32_t>(board.opp >> 32));
+  const float u = philox_uniform01(p.seed, game_id, ply, 0u);
+  const int a = choose_weighted(pi, u);  // :137-138
+  if (a < 0) { err = kErrInternal; return 0u; }
+  if (lane == 0) g.actions[grow] = static_cast<uint8_t>(a);
+  board = play_canonical(board, a);  // :140-142
+  player = -player;
+  return static_cast<uint32_t>(game_ended_code(board, p.quirks));  // :144
+}
+
+__device__ __forceinline__ void load_tree_vars(WarpTree& t, const TreeVars& tv, int lane) {
+  t.n_blocks = tv.n_blocks;
+  t.n_owners = tv.n_owners;
+  t.error = tv.error;
+  t.slow = tv.slow;
+  t.stat = lane < 8 ? tv.stat[lane] : 0u;
+}
+__device__ __forceinline__ void store_tree_vars(const WarpTree& t, TreeVars& tv, int lane) {
+  if (lane == 0) {
+    tv.n_blocks = t.n_blocks;
+    tv.n_owners = t.n_owners;
+    tv.error = t.error;
+    tv.slow = t.slow;
+  }
+  if (lane < 8) tv.stat[lane] = t.stat;
+}
+
+// ---- k_round ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
+k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, GameBufs g) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= *ctl.n_active) return;
+  const uint32_t slot = ctl.active_list[w];
+  GameRec* rec = recs + slot;
+  const SearchParams& p = rp.p;
+  const uint32_t tps = rp.mode == kModeArena ? 2u : 1u;
+
+  uint32_t phase = rec->phase;
+  const uint32_t gi = rec->game;
+  BB board{rec->cur, rec->opp};
+  int player = rec->player;
+  uint32_t step = rec->step, sims_done = rec->sims_done;
+  uint32_t root_slot = rec->root_slot, root_meta = rec->root_meta;
+  uint32_t plies_left = rp.plies_per_launch;
+
+  // which player's tree / evaluator is in use: self-play always 0; arena: the side to move
+  // (games [0, half): A holds +1; games [half, ..): B holds +1 — arena.rs:74-83)
+  auto side_of = [&](int pl) -> uint32_t {
+    if (rp.mode != kModeArena) return 0u;
+    const bool a_first = gi < rp.half;
+    return (pl > 0) == a_first ? 0u : 1u;
+  };
+  uint32_t side = 0;
+  WarpTree t = open_tree(pools, p, slot * tps);
+
+  if (phase == kPhaseFresh) {  // AsyncMcts::default (coach.rs:246-255): fresh tree(s) on the initial board
+    for (uint32_t k = 0; k < tps; ++k) {
+      WarpTree tk = open_tree(pools, p, slot * tps + k);
+      clear_table(tk, p, lane);
+      if (lane < 12) reinterpret_cast<uint32_t*>(&rec->tv[k])[lane] = 0u;
+    }
+    board = BB{0ull, 0ull};
+    player = 1;
+    step = 0;
+    phase = kPhaseNewMove;
+    __syncwarp();
+  }
+  side = side_of(player);
+  t = open_tree(pools, p, slot * tps + side);
+  load_tree_vars(t, rec->tv[side], lane);
+  uint32_t err = 0;
+
+  if (phase == kPhasePending) {  // the network's answer for the suspended simulation is in
+    Pending pd = rec->pd;
+    for (uint32_t i = lane; i < pd.plen; i += 32u) t.path[i] = rec->path[i];
+    __syncwarp();
+    const size_t row = static_cast<size_t>(side) * rp.n_slots + rec->leaf_idx;
+    const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
+    const float val = leaf.v[row];
+    if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
+    else finish_expand(t, p, pd, pi, val, lane);
+    sims_done++;
+    phase = kPhaseSearch;
+  }
+
+  for (;;) {
+    if (t.error) { err = t.error; break; }
+    if (phase == kPhaseNewMove) {
+      if (rp.mode == kModeArena) {
+        // arena.rs:18 — the loop condition is checked before every move
+        const uint32_t code = static_cast<uint32_t>(game_ended_code(board, p.quirks));
+        if (code) {
+          // arena.rs:51: cur_player * round(get_game_ended(cur_player)); the draw value rounds to 0
+          const int r = code == 1u ? 1 : (code == 2u ? -1 : 0);
+          if (lane == 0) {
+            ctl.arena_result[gi] = static_cast<int8_t>(player * r);
+            g.plies[gi] = step;
+          }
+          phase = kPhaseDone;
+          break;
+        }
+        if (step < rp.k_open) {  // random opening ply (not in the reference; k_open = 0 for parity)
+          const uint32_t vm = valid_mask(board.cur | board.opp);
+          const float wgt = (lane < 7 && ((vm >> lane) & 1u)) ? 1.0f : 0.0f;
+          const int a = choose_weighted(wgt, philox_uniform01(p.seed, rp.first_game_id + gi, step, 1u));
+          if (lane == 0) g.actions[static_cast<size_t>(gi) * kTraceStride + step] = static_cast<uint8_t>(a);
+          board = play_canonical(board, a);
+          player = -player;
+          step++;
+          continue;
+        }
+        const uint32_t ns = side_of(player);
+        if (ns != side) {  // the other player's tree takes over
+          store_tree_vars(t, rec->tv[side], lane);
+          side = ns;
+          t = open_tree(pools, p, slot * tps + side);
+          load_tree_vars(t, rec->tv[side], lane);
+        }
+      }
+      step++;                                             // coach.rs:119
+      if (!make_root(t, p, board, lane, root_slot, root_meta)) { err = t.error; break; }  // :81 (+F12)
+      if (step * p.num_sims >= kSafeVisits) t.slow = 1u;
+      sims_done = 0;
+      phase = kPhaseSearch;
+    }
+    // ---- search (async_mcts.rs:191-217) ----
+    const int ev = rp.ev_kind[side];
+    bool suspended = false;
+    Pending pd;
+    BB leaf_pos;
+    while (sims_done < p.num_sims && !t.error) {
+      if (sims_done == 0 && root_needs_eval(t, root_meta)) {  // repair F1
+        if (ev >= AZB_EVAL_NNET) {
+          pd.kind = kPendRoot;
+          pd.plen = 0;
+          leaf_pos = board;
+          suspended = true;
+          break;
+        }
+        float pi, val;
+        evaluate_inline(ev, board, lane, pi, val);
+        finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
+      } else if (!one_sim(t, p, ev, board, root_slot, root_meta, lane, pd, leaf_pos)) {
+        suspended = true;
+        break;
+      }
+      sims_done++;
+    }
+    if (t.error) { err = t.error; break; }
+    if (suspended) {  // hand the leaf to the batched evaluator of this side's model
+      uint32_t idx = 0;
+      if (lane == 0) idx = atomicAdd(leaf.count + side, 1u);
+      idx = __shfl_sync(kFull, idx, 0);
+      if (lane == 0) {
+        leaf.state[static_cast<size_t>(side) * rp.n_slots + idx] =
+            make_uint4(static_cast<uint32_t>(leaf_pos.cur), static_cast<uint32_t>(leaf_pos.cur >> 32),
+                       static_cast<uint32_t>(leaf_pos.opp), static_cast<uint32_t>(leaf_pos.opp >> 32));
+        rec->pd = pd;
+        rec->leaf_idx = idx;
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < pd.plen; i += 32u) rec->path[i] = t.path[i];
+      phase = kPhasePending;
+      break;
+    }
+    // ---- the move ----
+    if (rp.mode == kModeArena) {
+      // coach.rs:356-371: argmax of get_action_prob(s, temp = 0) — a one-hot on the most visited
+      // child, ties to the highest action
+      const uint32_t cnt = root_child_count(t, root_meta, lane);
+      const uint32_t mx = __reduce_max_sync(kFull, lane < 7 ? cnt : 0u);
+      const int a = 31 - __clz(__ballot_sync(kFull, lane < 7 && cnt == mx));
+      const uint32_t vm = valid_mask(board.cur | board.opp);
+      if (!((vm >> a) & 1u)) { err = kErrInternal; break; }  // arena.rs:29-35 assert
+      const size_t grow = static_cast<size_t>(gi) * kTraceStride + (step - 1u);
+      if (lane < 7) g.counts[grow * 7u + lane] = static_cast<uint16_t>(cnt);
+      if (lane == 0) g.actions[grow] = static_cast<uint8_t>(a);
+      board = play_canonical(board, a);
+      player = -player;
+      phase = kPhaseNewMove;
+    } else {
+      const uint32_t code = selfplay_move(t, p, g, gi, rp.first_game_id + gi, step, board, player, root_meta, lane, err);
+      if (err) break;
+      if (code || step >= static_cast<uint32_t>(kMaxPlies)) {
+        if (lane == 0) {
+          g.plies[gi] = step;
+          g.final_r[gi] = game_ended_value(static_cast<int>(code));
+          g.final_player[gi] = static_cast<int8_t>(player);
+        }
+        if (!code) err = kErrInternal;
+        phase = kPhaseDone;
+        break;
+      }
+      phase = kPhaseNewMove;
+    }
+    if (rp.plies_per_launch && --plies_left == 0u) break;
+  }
+
+  if (err) {
+    phase = kPhaseDone;
+    t.error = err;
+  }
+  store_tree_vars(t, rec->tv[side], lane);
+  __syncwarp();
+  if (phase == kPhaseDone) {  // per-game statistics (both trees for arena)
+    if (lane == 0) g.error[gi] = rec->tv[0].error | (tps > 1u ? rec->tv[1].error : 0u);
+    if (lane < 8) {
+      uint32_t s = rec->tv[0].stat[lane] + (tps > 1u ? rec->tv[1].stat[lane] : 0u);
+      if (lane == 6) s = max(rec->tv[0].n_blocks, tps > 1u ? rec->tv[1].n_blocks : 0u);
+      if (lane == 7) s = max(rec->tv[0].n_owners, tps > 1u ? rec->tv[1].n_owners : 0u);
+      g.stats[gi * 8u + lane] = s;
+    }
+  }
+  if (lane == 0) {
+    rec->cur = board.cur;
+    rec->opp = board.opp;
+    rec->phase = phase;
+    rec->player = player;
+    rec->step = step;
+    rec->sims_done = sims_done;
+    rec->root_slot = root_slot;
+    rec->root_meta = root_meta;
+  }
+}
+
+}  // namespace azb

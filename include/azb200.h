@@ -112,6 +112,9 @@ typedef struct azb_config {
   int32_t evaluator; /* AZB_EVAL_* */
   int32_t device;    /* CUDA ordinal */
   uint64_t max_concurrent_games; /* trees resident in HBM at once; 0 = as many as requested */
+  uint32_t schedule;         /* fused evaluators: 0/2 = lock-step rounds (live games re-dealt over the
+                                SMs every plies_per_launch plies), 1 = one persistent kernel */
+  uint32_t plies_per_launch; /* 0 = default (2) */
 } azb_config;
 
 /* The reference's example parameters (examples/connect_four.rs:55-71), profile "sane". */
@@ -129,6 +132,7 @@ typedef struct azb_selfplay_stats {
   uint64_t sims, levels, expansions, terminal_hits, dup_links, evals;
   uint64_t blocks_used_max, owners_max; /* pool high-water marks over trees */
   double device_ms;                     /* CUDA-event time of the self-play kernels */
+  uint64_t launches;                    /* kernels launched by the call */
 } azb_selfplay_stats;
 
 /* Coach::execute_episode over n_games concurrent games — coach.rs:104-157 and the episode
@@ -146,6 +150,50 @@ int azb_coach_num_samples(azb_coach* c, uint64_t* n);
  * ply, symmetry (coach.rs:132-135,243-270).  `capacity` is in samples. */
 int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs, uint64_t capacity,
                              uint64_t* n_written);
+
+/* ---------------------------------------------------------------------------------------
+ * NNet — src/nnet.rs:35-45.  One handle = one model (the reference addresses models by
+ * model_id inside one NNet; here every model is its own handle, model_id is accepted and
+ * ignored).  The architecture is this engine's own (the reference has no working network,
+ * SURVEY §0.5): conv3x3(2->128)+ReLU, `blocks` residual blocks of two conv3x3(128->128),
+ * policy head conv1x1(128->2)+ReLU+FC(84->7)+softmax, value head conv1x1(128->1)+ReLU+
+ * FC(42->64)+ReLU+FC(64->1)+tanh; BatchNorm folded into the conv bias.
+ * ------------------------------------------------------------------------------------- */
+#define AZB_NNET_BF16_TC 0 /* bf16 weights/activations, fp32 accumulate, tcgen05 tensor cores */
+#define AZB_NNET_FP32 1    /* fp32 reference path on CUDA cores (pins the numerics) */
+typedef struct azb_nnet_config {
+  int32_t device;
+  int32_t blocks;    /* residual blocks (6) */
+  int32_t precision; /* AZB_NNET_* */
+  int32_t reserved;
+  uint64_t seed;     /* He-normal initialisation (weights ~ N(0, 2/fan_in), biases 0) */
+} azb_nnet_config;
+typedef struct azb_nnet azb_nnet;
+/* NNet::new(checkpoint) — nnet.rs:36: random-init from cfg->seed (checkpoint files: next row N3) */
+int azb_nnet_create(const azb_nnet_config* cfg, azb_nnet** out);
+int azb_nnet_destroy(azb_nnet* n);
+/* NNet::predict(boards[B,2,6,7], model_id) -> (pi[B,7] probabilities, v[B]) — nnet.rs:40-44.
+ * boards are the 0/1 feature planes of Game::to_features. */
+int azb_nnet_predict(azb_nnet* n, const float* boards, size_t batch, size_t model_id, float* pi, float* v);
+/* Flat fp32 parameter vector (layout: alphazero-rs_b200/csrc/nnet.cuh NetLayout). */
+int azb_nnet_num_params(azb_nnet* n, uint64_t* count);
+int azb_nnet_get_params(azb_nnet* n, float* out, uint64_t capacity);
+int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count);
+/* The network that evaluates leaves when cfg.evaluator == AZB_EVAL_NNET (the NNet the
+ * reference's inference thread owns, async_mcts.rs:125).  The coach does not own it. */
+int azb_coach_set_nnet(azb_coach* c, azb_nnet* n);
+
+/* ---------------------------------------------------------------------------------------
+ * arena — src/arena.rs:7-99 with the two MCTS players of coach.rs:333-375 (temp 0, arg-max
+ * of get_action_prob, a fresh tree pair per game).  num/2 games with A moving first, num/2
+ * with B first; out_counts = {Win, Loss, Draw} of player A (arena.rs:54-59,86-92);
+ * results[2*(num/2)] (optional) = play_game's return value per game (arena.rs:51).
+ * eval_a / eval_b are AZB_EVAL_*; net_a / net_b are used when the kind is AZB_EVAL_NNET.
+ * k_open random opening plies per game (0 = the reference's behaviour).
+ * ------------------------------------------------------------------------------------- */
+int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
+                         azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
+                         azb_selfplay_stats* stats);
 
 /* ---------------------------------------------------------------------------------------
  * AsyncMcts test hooks — src/async_mcts.rs and src/node.rs are private modules of the

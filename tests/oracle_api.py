@@ -138,7 +138,7 @@ class Mcts:
 
     def __init__(self, num_sims=25, quirks=0, evaluator=EVAL_UNIFORM, root=None, callback=None, **kw):
         self.p = params(num_sims=num_sims, quirks=quirks, **kw)
-        self._cb = PREDICT_FN(callback) if callback else None
+        self._cb = make_callback(callback) if callback else None
         fn = C.cast(self._cb, vp) if self._cb else None
         r = _p(_states(root)) if root is not None else None
         self._h = L.azo_mcts_create(r, C.byref(self.p), evaluator, fn, None)
@@ -179,14 +179,27 @@ class Mcts:
         return keys[order], counters[order], e[order], p[order], hp[order]
 
 
-def execute_episode(num_sims=25, quirks=0, seed=1, episode_id=0, evaluator=EVAL_UNIFORM, **kw):
+def make_callback(predict):
+    """Wrap predict(boards[B,2,6,7]) -> (pi[B,7], v[B]) as the oracle's evaluator callback
+    (mirrors trait NNet::predict, nnet.rs:40-44)."""
+    def cb(boards, batch, pi, v, user):
+        b = np.ctypeslib.as_array(boards, shape=(batch, 2, 6, 7)).copy()
+        p_, v_ = predict(b)
+        np.ctypeslib.as_array(pi, shape=(batch, 7))[:] = p_
+        np.ctypeslib.as_array(v, shape=(batch,))[:] = v_
+    return PREDICT_FN(cb)
+
+
+def execute_episode(num_sims=25, quirks=0, seed=1, episode_id=0, evaluator=EVAL_UNIFORM, callback=None, **kw):
     """Coach::execute_episode of the oracle; returns a dict with the full trace."""
     p = params(num_sims=num_sims, quirks=quirks, seed=seed, **kw)
+    cb = make_callback(callback) if callback else None
+    fn = C.cast(cb, vp) if cb else None
     actions = np.full(64, 0xFF, np.uint8); counts = np.zeros((64, 7), np.uint16)
     boards = np.zeros((128, 2, 6, 7), np.float32); pis = np.zeros((128, 7), np.float32); vs = np.zeros(128, np.float32)
     ns = C.c_uint64(); fr = C.c_float(); fp = C.c_int8(); st = np.zeros(6, np.uint64)
     nl = C.c_uint64(); sl = C.c_uint64()
-    plies = L.azo_execute_episode(C.byref(p), episode_id, evaluator, None, None, _p(actions), _p(counts), _p(boards),
+    plies = L.azo_execute_episode(C.byref(p), episode_id, evaluator, fn, None, _p(actions), _p(counts), _p(boards),
                                   _p(pis), _p(vs), C.addressof(ns), C.addressof(fr), C.addressof(fp), _p(st),
                                   C.addressof(nl), C.addressof(sl))
     if plies < 0:

@@ -1,0 +1,114 @@
+"""NNet::predict (src/nnet.rs:40-44) and network-evaluated self-play.
+
+* fp32 path vs a torch fp32 restatement of the same architecture with the same weights: 1e-4
+  (the tolerance the north star states for fp32).
+* bf16 tensor-core path vs the fp32 path: stated bf16 tolerance.
+* self-play / arena with evaluator NNET (lock-step rounds, batched leaves) vs the oracle whose
+  evaluator callback is this very network: bit-exact visit counts and trajectories.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def random_features(oracle, n_games=40, seed=3):
+    rng = np.random.default_rng(seed)
+    feats = []
+    for _ in range(n_games):
+        s = oracle.init_board(1)
+        p = np.array([1], np.int8)
+        for _ply in range(int(rng.integers(0, 43))):
+            v = oracle.valid_moves(s)[0]
+            if not v.any():
+                break
+            s, p = oracle.next_state(s, p, rng.choice(np.flatnonzero(v)))
+            feats.append(oracle.to_features(oracle.canonical_form(s, p))[0])
+    feats.append(np.zeros((2, 6, 7), np.float32))
+    return np.stack(feats)
+
+
+def torch_forward(azb, params, blocks, boards):
+    import torch
+    import torch.nn.functional as F
+    L = azb.param_layout(blocks)
+
+    def get(name):
+        o, shape = L[name]
+        return torch.from_numpy(params[o:o + int(np.prod(shape))].reshape(shape).copy()).double()
+
+    x = torch.from_numpy(boards).double()
+    # stem_w [9][2][C] -> conv weight [C][2][3][3]
+    w = get("stem_w").reshape(3, 3, 2, 128).permute(3, 2, 0, 1)
+    x = F.relu(F.conv2d(x, w, get("stem_b"), padding=1))
+    tw, tb = get("tower_w"), get("tower_b")
+    for b in range(blocks):
+        w1 = tw[2 * b].reshape(3, 3, 128, 128).permute(3, 2, 0, 1)
+        w2 = tw[2 * b + 1].reshape(3, 3, 128, 128).permute(3, 2, 0, 1)
+        y = F.relu(F.conv2d(x, w1, tb[2 * b], padding=1))
+        y = F.conv2d(y, w2, tb[2 * b + 1], padding=1)
+        x = F.relu(x + y)
+    pol = F.relu(torch.einsum("bchw,cp->bphw", x, get("pol_w")) + get("pol_b").view(1, 2, 1, 1)).reshape(len(boards), 84)
+    logits = pol @ get("pol_fc_w") + get("pol_fc_b")
+    pi = torch.softmax(logits, dim=1)
+    val = F.relu(torch.einsum("bchw,c->bhw", x, get("val_w")) + get("val_b")).reshape(len(boards), 42)
+    h = F.relu(val @ get("val_fc1_w") + get("val_fc1_b"))
+    v = torch.tanh(h @ get("val_fc2_w") + get("val_fc2_b"))
+    return pi.numpy(), v.numpy()
+
+
+@pytest.mark.parametrize("blocks", [1, 6])
+def test_fp32_path_matches_torch(azb, oracle, blocks):
+    net = azb.NNet(seed=7, blocks=blocks, precision=azb.NNET_FP32)
+    feats = random_features(oracle)
+    pi, v = net.predict(feats)
+    rpi, rv = torch_forward(azb, net.get_params(), blocks, feats)
+    assert np.abs(pi - rpi).max() < 1e-4, np.abs(pi - rpi).max()
+    assert np.abs(v - rv).max() < 1e-4, np.abs(v - rv).max()
+    assert np.allclose(pi.sum(1), 1.0, atol=1e-5)
+    # non-degenerate: different positions give different outputs
+    assert np.abs(pi - pi[0]).max() > 1e-3 and np.ptp(v) > 1e-3
+
+
+def test_predict_is_batch_independent(azb, oracle):
+    net = azb.NNet(seed=8, blocks=2, precision=azb.NNET_FP32)
+    feats = random_features(oracle, 10)
+    pi, v = net.predict(feats)
+    for i in (0, 5, len(feats) - 1):
+        p1, v1 = net.predict(feats[i:i + 1])
+        assert np.array_equal(p1[0].view(np.uint32), pi[i].view(np.uint32)) and v1[0] == v[i]
+
+
+def test_set_params_roundtrip(azb, oracle):
+    net = azb.NNet(seed=1, blocks=1, precision=azb.NNET_FP32)
+    w = net.get_params()
+    assert len(w) == azb.param_layout(1)["total"]
+    feats = random_features(oracle, 3)
+    before = net.predict(feats)
+    w2 = w.copy()
+    o, shape = azb.param_layout(1)["val_fc2_b"]
+    w2[o] += 0.5
+    net.set_params(w2)
+    after = net.predict(feats)
+    assert np.array_equal(before[0], after[0]) and not np.array_equal(before[1], after[1])
+
+
+@pytest.mark.parametrize("quirks", [0, 15])
+def test_selfplay_with_network_matches_oracle(azb, oracle, quirks):
+    net = azb.NNet(seed=7, blocks=2, precision=azb.NNET_FP32)
+    coach = azb.Coach(nnet=net, num_sims=30, seed=4, quirks=quirks, evaluator=azb.EVAL_NNET)
+    st = coach.self_play(6, 10)
+    tr = coach.traces()
+    boards, pis, vs = coach.export_samples()
+    offs = np.concatenate([[0], np.cumsum(tr["plies"].astype(np.int64))])
+    for g in range(6):
+        o = oracle.execute_episode(num_sims=30, quirks=quirks, seed=4, episode_id=10 + g,
+                                   evaluator=oracle.EVAL_CALLBACK, callback=net.predict)
+        n = o["plies"]
+        assert tr["plies"][g] == n
+        assert tr["actions"][g, :n].tolist() == o["actions"][:n].tolist()
+        assert np.array_equal(tr["counts"][g, :n], o["counts"][:n])
+        a, b = 2 * offs[g], 2 * offs[g + 1]
+        assert np.array_equal(pis[a:b].view(np.uint32), o["pis"].view(np.uint32))
+        assert np.array_equal(vs[a:b], o["vs"])
+    assert st["evals"] > 0 and st["launches"] > 3 * st["evals"] / 6 / 2

@@ -9,6 +9,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["persistent", "rounds"])
+def schedule(request):
+    """1 = one persistent kernel (a warp plays a whole game), 2 = lock-step rounds."""
+    return request.param
+
+
 def check_games(azb, orc, coach, games, first_game_id, **okw):
     st = coach.self_play(games, first_game_id)
     tr = coach.traces()
@@ -37,38 +43,38 @@ def check_games(azb, orc, coach, games, first_game_id, **okw):
 
 @pytest.mark.parametrize("quirks", [0, 15])
 @pytest.mark.parametrize("evaluator", [0, 1])
-def test_example_config_25_sims(azb, oracle, quirks, evaluator):
+def test_example_config_25_sims(azb, oracle, quirks, evaluator, schedule):
     # examples/connect_four.rs:55-71: 25 sims/move, cpuct 1, temp_threshold 15, max_depth 1000
     coach = azb.Coach.setup("./checkpoint", 1000000, 0.6, 15, 20, 200000, 1, 1, 40, 1, 1, 25, 1, 1000, 1,
-                            quirks=quirks, evaluator=evaluator, seed=1)
+                            quirks=quirks, evaluator=evaluator, seed=1, schedule=schedule)
     check_games(azb, oracle, coach, 32, 0, num_sims=25, quirks=quirks, seed=1, evaluator=evaluator)
 
 
-def test_baseline_config1_50_sims(azb, oracle):
-    coach = azb.Coach(num_sims=50, seed=1)
+def test_baseline_config1_50_sims(azb, oracle, schedule):
+    coach = azb.Coach(num_sims=50, seed=1, schedule=schedule)
     check_games(azb, oracle, coach, 1, 0, num_sims=50, quirks=0, seed=1, evaluator=0)
     b, p, v = coach.execute_episode(3)
     o = oracle.execute_episode(num_sims=50, seed=1, episode_id=3)
     assert np.array_equal(b, o["boards"]) and np.array_equal(v, o["vs"])
 
 
-def test_more_games_than_resident_trees(azb, oracle):
+def test_more_games_than_resident_trees(azb, oracle, schedule):
     # 40 games on 8 resident trees: trees are recycled (table cleared) between games
-    coach = azb.Coach(num_sims=60, seed=5, evaluator=1, max_concurrent_games=8)
+    coach = azb.Coach(num_sims=60, seed=5, evaluator=1, max_concurrent_games=8, schedule=schedule)
     check_games(azb, oracle, coach, 40, 100, num_sims=60, quirks=0, seed=5, evaluator=1)
 
 
-def test_sampled_800_sims(azb, oracle):
+def test_sampled_800_sims(azb, oracle, schedule):
     # BASELINE config 2 parameters on a small batch: 800 sims/move, seed 0xA1FA0
-    coach = azb.Coach(num_sims=800, seed=0xA1FA0, evaluator=0)
+    coach = azb.Coach(num_sims=800, seed=0xA1FA0, evaluator=0, schedule=schedule)
     st = check_games(azb, oracle, coach, 256, 0, num_sims=800, quirks=0, seed=0xA1FA0, evaluator=0)
     assert st["sims"] == 800 * st["plies"]
 
 
-def test_oracle_fixture_on_device(azb):
+def test_oracle_fixture_on_device(azb, schedule):
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_episodes.json")))
     for e in fx["episodes"]:
-        coach = azb.Coach(num_sims=e["num_sims"], quirks=e["quirks"], seed=e["seed"], evaluator=e["evaluator"])
+        coach = azb.Coach(num_sims=e["num_sims"], quirks=e["quirks"], seed=e["seed"], evaluator=e["evaluator"], schedule=schedule)
         st = coach.self_play(1, e["episode_id"])
         tr = coach.traces()
         n = int(tr["plies"][0])
@@ -80,11 +86,11 @@ def test_oracle_fixture_on_device(azb):
         assert st["owners_max"] == e["seen_len"]
 
 
-def test_full_size_properties(azb):
+def test_full_size_properties(azb, schedule):
     """BASELINE config 2 at full width (4096 games) with fewer sims: size-independent
     properties — every game ends legally, samples are consistent, and the run is
     deterministic (same seed => identical traces)."""
-    coach = azb.Coach(num_sims=48, seed=0xA1FA0, evaluator=1)
+    coach = azb.Coach(num_sims=48, seed=0xA1FA0, evaluator=1, schedule=schedule)
     st = coach.self_play(4096, 0)
     tr = coach.traces()
     boards, pis, vs = coach.export_samples()
