@@ -14,6 +14,7 @@
 #include "../../include/azb200.h"
 #include "kernels.cuh"
 #include "nnet.cuh"
+#include "nnet_tc.cuh"
 #include "rounds.cuh"
 
 using namespace azb;
@@ -163,10 +164,39 @@ struct azb_nnet {
   NetLayout L;
   std::vector<float> h_params;
   DevBuf d_params;
+  DevBuf d_wtiles;                     // bf16 path: [2R][18] pre-swizzled 16-KB weight tiles
+  DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
   DevBuf d_feat, d_states, d_pi, d_v;  // azb_nnet_predict staging
+  static uint16_t bf16_rne(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);  // inf / nan
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+  }
   int upload() {
     AZB_CUDA(d_params.ensure(L.total * 4));
     AZB_CUDA(cudaMemcpy(d_params.p, h_params.data(), L.total * 4, cudaMemcpyHostToDevice));
+    if (cfg.precision == AZB_NNET_BF16_TC) {
+      // B operand tiles: tile(layer, kb = tap*2 + half)[n = out channel][k = in channel - 64*half], K-major,
+      // SWIZZLE_128B: byte = (n/8)*1024 + (n%8)*128 + (((k/8) ^ (n%8)) * 16) + (k%8)*2
+      const size_t n_tiles = static_cast<size_t>(2 * L.R) * kTcKBlocks;
+      std::vector<uint16_t> tiles(n_tiles * (kTcTileBytes / 2));
+      for (int layer = 0; layer < 2 * L.R; ++layer)
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          uint16_t* t = tiles.data() + (static_cast<size_t>(layer) * kTcKBlocks + kb) * (kTcTileBytes / 2);
+          const int tap = kb >> 1, half = kb & 1;
+          const float* w = h_params.data() + L.tower_w + (static_cast<size_t>(layer) * 9 + tap) * kNetC * kNetC;
+          for (int n = 0; n < 128; ++n)
+            for (int k = 0; k < 64; ++k) {
+              const size_t byte = (n / 8) * 1024 + (n % 8) * 128 + (((k / 8) ^ (n % 8)) * 16) + (k % 8) * 2;
+              t[byte / 2] = bf16_rne(w[static_cast<size_t>(half * 64 + k) * kNetC + n]);
+            }
+        }
+      AZB_CUDA(d_wtiles.ensure(tiles.size() * 2));
+      AZB_CUDA(cudaMemcpy(d_wtiles.p, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    }
     return AZB_OK;
   }
 };
@@ -176,9 +206,39 @@ namespace {
 int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
                  float* d_v, cudaStream_t st) {
   if (max_batch == 0) return AZB_OK;
-  const size_t smem = (2 * kCells * kNetC + 256) * sizeof(float);
-  const unsigned grid = std::min<uint32_t>(max_batch, 148u * 4u);
-  k_nnet_fp32<<<grid, 128, smem, st>>>(net->d_params.as<float>(), net->L, d_states, d_count, max_batch, d_pi, d_v);
+  if (net->cfg.precision == AZB_NNET_FP32) {
+    const size_t smem = (2 * kCells * kNetC + 256) * sizeof(float);
+    const unsigned grid = std::min<uint32_t>(max_batch, 148u * 4u);
+    k_nnet_fp32<<<grid, 128, smem, st>>>(net->d_params.as<float>(), net->L, d_states, d_count, max_batch, d_pi, d_v);
+    AZB_CUDA(cudaGetLastError());
+    return AZB_OK;
+  }
+  // bf16 tensor-core path: stem -> 2R x conv3x3 (tcgen05) -> heads
+  const size_t act_bytes = static_cast<size_t>(max_batch) * kCells * kNetC * 2;
+  for (auto& b : net->d_act) AZB_CUDA(b.ensure(act_bytes));
+  __nv_bfloat16* x = net->d_act[0].as<__nv_bfloat16>();
+  __nv_bfloat16* y = net->d_act[1].as<__nv_bfloat16>();
+  __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
+  const float* prm = net->d_params.as<float>();
+  const size_t total = static_cast<size_t>(max_batch) * kCells * kNetC;
+  k_stem_bf16<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prm, net->L, d_states, d_count, max_batch, x);
+  const uint32_t tiles = (max_batch * kCells + kTcTileM - 1) / kTcTileM;
+  const unsigned grid = std::min<uint32_t>(tiles, 148u);
+  for (int blk = 0; blk < net->L.R; ++blk) {
+    ConvTcArgs a{};
+    a.count = d_count;
+    a.max_batch = max_batch;
+    a.in = x; a.residual = nullptr; a.out = y;
+    a.w_tiles = net->d_wtiles.as<uint8_t>() + static_cast<size_t>(2 * blk) * kTcKBlocks * kTcTileBytes;
+    a.bias = prm + net->L.tower_b + (2 * blk) * kNetC;
+    k_conv3x3_tc<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    a.in = y; a.residual = x; a.out = z;
+    a.w_tiles += static_cast<size_t>(kTcKBlocks) * kTcTileBytes;
+    a.bias += kNetC;
+    k_conv3x3_tc<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    std::swap(x, z);
+  }
+  k_heads_bf16<<<std::min<uint32_t>(max_batch, 148u * 8u), 128, 0, st>>>(prm, net->L, x, d_count, max_batch, d_pi, d_v);
   AZB_CUDA(cudaGetLastError());
   return AZB_OK;
 }
@@ -600,7 +660,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   //           2 = lock-step rounds (k_compact / k_round [/ network forward]); 0 = pick
   uint32_t schedule = c->cfg.schedule;
   if (c->cfg.evaluator >= AZB_EVAL_NNET) schedule = 2;
-  else if (schedule == 0) schedule = 2;
+  else if (schedule == 0) schedule = 1;  // measured: re-dealing live games buys nothing at 7 warps/scheduler
 
   cudaEvent_t e0, e1;
   AZB_CUDA(cudaEventCreate(&e0));

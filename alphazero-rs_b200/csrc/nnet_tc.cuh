@@ -1,0 +1,318 @@
+// bf16 tensor-core path of the network tower (kernel family K6): 3x3 convolution C=128 -> 128 as an
+// implicit GEMM on the 5th-generation tensor cores.
+//
+//   D[m, n] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][n],   m = (position, cell) row, n = out channel
+//   M tile = 128 rows, N = 128, K = 9 taps x 128 channels = 18 k-blocks of 64
+//
+// * tcgen05.mma (cta_group::1, kind::f16, M128 N128 K16, bf16 x bf16 -> fp32) issued by ONE thread;
+//   the accumulator lives in TMEM (2 stages x 128 columns) and is read back with tcgen05.ld.
+// * B (weights) is pre-swizzled on the host into 16-KB K-major SWIZZLE_128B tiles; one bulk-TMA copy
+//   (cp.async.bulk, completes on an mbarrier) brings a tile into a pipeline stage.
+// * A (activations, bf16 [rows][128] in HBM/L2) has no im2col copy in memory: four producer warps
+//   gather the shifted rows of the tap (zeros outside the 6x7 board) straight into the swizzled
+//   stage (the shift is not expressible in a UMMA descriptor: rows come in groups of 8).
+// * Warp roles (320 threads): 0-3 A producers, 4-7 epilogue (TMEM lanes 32*(w%4)..), 8 MMA issuer,
+//   9 weight loader + TMEM allocator.  Three pipelines: smem full/empty (4 stages), TMEM full/empty.
+// * Epilogue fused: + bias (folded BN), + residual, ReLU, fp32 -> bf16, straight to HBM.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "nnet.cuh"
+
+namespace azb {
+
+constexpr int kTcTileM = 128;
+constexpr int kTcBlockK = 64;
+constexpr int kTcStages = 4;
+constexpr int kTcKBlocks = 18;              // 9 taps x 2 halves of 64 input channels
+constexpr uint32_t kTcTileBytes = 128 * 64 * 2;  // one A or B stage: 128 rows x 128 bytes
+constexpr int kTcThreads = 320;
+constexpr uint32_t kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 in [0,14), LBO [16,30) (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4 in
+// [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = BF16 (bits 7, 10),
+// both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct ConvTcArgs {
+  const __nv_bfloat16* in;        // [rows][128]
+  const __nv_bfloat16* residual;  // [rows][128] or nullptr
+  __nv_bfloat16* out;             // [rows][128]
+  const uint8_t* w_tiles;         // [18][16384] pre-swizzled B tiles of this layer
+  const float* bias;              // [128]
+  const uint32_t* count;          // positions this round (device), or nullptr
+  uint32_t max_batch;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
+  const uint32_t sA = base, sB = base + kTcStages * kTcTileBytes;
+  const uint32_t bars = sB + kTcStages * kTcTileBytes;
+  auto bar_full_a = [&](int s) { return bars + 8u * s; };
+  auto bar_full_b = [&](int s) { return bars + 32u + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 64u + 8u * s; };
+  auto bar_acc_full = [&](int a) { return bars + 96u + 8u * a; };
+  auto bar_acc_empty = [&](int a) { return bars + 112u + 8u * a; };
+  const uint32_t tmem_slot = bars + 128u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
+  const uint32_t rows = n_pos * kCells;
+  const uint32_t n_tiles = (rows + kTcTileM - 1) / kTcTileM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(bar_full_a(s), 128);
+      mbar_init(bar_full_b(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full(a), 1);
+      mbar_init(bar_acc_empty(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {  // TMEM: 2 accumulator stages x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // ===== A producers: thread t gathers row t of the tile for every (tap, half) =====
+    const int t = threadIdx.x;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t m = tile * kTcTileM + t;
+      const bool live = m < rows;
+      const uint32_t cell = m % kCells;
+      const int r = cell / 7, c = cell % 7;
+      const uint32_t sw = (t & 7);
+      const uint32_t row_off = (t >> 3) * 1024u + (t & 7) * 128u;
+      for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
+        const int s = it % kTcStages;
+        mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
+        const int tap = kb >> 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int rr = r + dy, cc = c + dx;
+        const bool ok = live && rr >= 0 && rr < 6 && cc >= 0 && cc < 7;
+        uint4 v[8];
+        if (ok) {
+          const uint4* src = reinterpret_cast<const uint4*>(g.in + (static_cast<size_t>(m) + dy * 7 + dx) * kNetC + (kb & 1) * kTcBlockK);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = src[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint32_t dst = sA + s * kTcTileBytes + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y),
+                       "r"(v[j].z), "r"(v[j].w)
+                       : "memory");
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+        mbar_arrive(bar_full_a(s));
+      }
+    }
+  } else if (warp < 8) {
+    // ===== epilogue: TMEM -> registers -> bias / residual / ReLU -> bf16 -> HBM =====
+    const int q = warp - 4;
+    uint32_t ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t a = ti & 1u;
+      mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t m = tile * kTcTileM + q * 32 + lane;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + ch * 32u, acc);
+        if (m < rows) {
+          const float* bias = g.bias + ch * 32;
+          uint32_t packed[16];
+          uint4 res[4];
+          if (g.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = rp[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x0 = __uint_as_float(acc[2 * j]) + bias[2 * j];
+            float x1 = __uint_as_float(acc[2 * j + 1]) + bias[2 * j + 1];
+            if (g.residual) {
+              const uint32_t rw = reinterpret_cast<const uint32_t*>(res)[j];
+              x0 += __uint_as_float(rw << 16);
+              x1 += __uint_as_float(rw & 0xFFFF0000u);
+            }
+            x0 = fmaxf(x0, 0.0f);
+            x1 = fmaxf(x1, 0.0f);
+            const __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
+            packed[j] = *reinterpret_cast<const uint32_t*>(&p);
+          }
+          uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(a));
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer: one elected thread =====
+    uint32_t it = 0, ti = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t a = ti & 1u;
+      mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
+        const int s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1u;
+        mbar_wait(bar_full_a(s), ph);
+        mbar_wait(bar_full_b(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ad = umma_desc_sw128(sA + s * kTcTileBytes);
+          const uint64_t bd = umma_desc_sw128(sB + s * kTcTileBytes);
+#pragma unroll
+          for (int k = 0; k < kTcBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+            umma_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128, (kb | k) ? 1u : 0u);
+          umma_commit(bar_empty(s));  // frees the stage when these MMAs have read it
+          if (kb == kTcKBlocks - 1) umma_commit(bar_acc_full(a));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== weight loader: bulk TMA of pre-swizzled 16-KB B tiles =====
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
+        const int s = it % kTcStages;
+        mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar_full_b(s), kTcTileBytes);
+          tma_bulk_g2s(sB + s * kTcTileBytes, g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes, kTcTileBytes, bar_full_b(s));
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+// Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, channel).
+__global__ void k_stem_bf16(const float* __restrict__ prm, NetLayout L, const uint4* __restrict__ states,
+                            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
+  const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_pos) * kCells * kNetC;
+  if (idx >= total) return;
+  const uint32_t co = idx % kNetC;
+  const uint32_t m = idx / kNetC, pos = m / kCells, cell = m % kCells;
+  const int r = cell / 7, c = cell % 7;
+  const uint4 st = states[pos];
+  const uint64_t cur = (static_cast<uint64_t>(st.y) << 32) | st.x, opp = (static_cast<uint64_t>(st.w) << 32) | st.z;
+  float acc = prm[L.stem_b + co];
+  for (int tap = 0; tap < 9; ++tap) {
+    const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
+    if (rr < 0 || rr >= 6 || cc < 0 || cc >= 7) continue;
+    const int b = rr * 7 + cc;
+    if ((cur >> b) & 1ull) acc += prm[L.stem_w + (tap * 2 + 0) * kNetC + co];
+    if ((opp >> b) & 1ull) acc += prm[L.stem_w + (tap * 2 + 1) * kNetC + co];
+  }
+  out[idx] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+}
+
+// Heads from the bf16 tower output: one CTA (128 threads) per position.
+__global__ void __launch_bounds__(128)
+k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __nv_bfloat16* __restrict__ act,
+             const uint32_t* __restrict__ count, uint32_t max_batch, float* __restrict__ pi_out, float* __restrict__ v_out) {
+  __shared__ float a0[kCells][kNetC];
+  __shared__ float scratch[256];
+  const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
+  for (uint32_t pos = blockIdx.x; pos < n_pos; pos += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCells * kNetC; i += 128)
+      a0[i / kNetC][i % kNetC] = __bfloat162float(act[static_cast<size_t>(pos) * kCells * kNetC + i]);
+    __syncthreads();
+    heads_from_smem(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
+  }
+}
+
+}  // namespace azb

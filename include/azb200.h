@@ -112,8 +112,9 @@ typedef struct azb_config {
   int32_t evaluator; /* AZB_EVAL_* */
   int32_t device;    /* CUDA ordinal */
   uint64_t max_concurrent_games; /* trees resident in HBM at once; 0 = as many as requested */
-  uint32_t schedule;         /* fused evaluators: 0/2 = lock-step rounds (live games re-dealt over the
-                                SMs every plies_per_launch plies), 1 = one persistent kernel */
+  uint32_t schedule;         /* fused evaluators: 0/1 = one persistent kernel (a warp plays a whole game),
+                                2 = lock-step rounds (live games re-dealt over the SMs every
+                                plies_per_launch plies); the NNET evaluator always runs in rounds */
   uint32_t plies_per_launch; /* 0 = default (2) */
 } azb_config;
 

@@ -6,7 +6,9 @@ azb = importlib.import_module("alphazero-rs_b200")
 games = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 800
 ev = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-coach = azb.Coach(num_sims=sims, seed=0xA1FA0, evaluator=ev)
+schedule = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+ppl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+coach = azb.Coach(num_sims=sims, seed=0xA1FA0, evaluator=ev, schedule=schedule, plies_per_launch=ppl)
 st = coach.self_play(games, 0)
-print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "device_ms")},
+print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "device_ms", "launches")},
       "sims/s=%.3e" % (st["sims"] / st["device_ms"] * 1e3))

@@ -112,3 +112,86 @@ def test_selfplay_with_network_matches_oracle(azb, oracle, quirks):
         assert np.array_equal(pis[a:b].view(np.uint32), o["pis"].view(np.uint32))
         assert np.array_equal(vs[a:b], o["vs"])
     assert st["evals"] > 0 and st["launches"] > 3 * st["evals"] / 6 / 2
+
+
+def torch_forward_bf16(azb, params, blocks, boards):
+    """The bf16 path's numerics restated in torch: fp32 stem -> bf16; tower convs with bf16 weights and
+    bf16 activations, fp32 accumulation, bias/residual/ReLU in fp32, bf16 store; heads in fp32."""
+    import torch
+    import torch.nn.functional as F
+    L = azb.param_layout(blocks)
+
+    def get(name):
+        o, shape = L[name]
+        return torch.from_numpy(params[o:o + int(np.prod(shape))].reshape(shape).copy())
+
+    def q(t):
+        return t.to(torch.bfloat16).to(torch.float64)
+
+    x = torch.from_numpy(boards).double()
+    w = get("stem_w").double().reshape(3, 3, 2, 128).permute(3, 2, 0, 1)
+    x = q(F.relu(F.conv2d(x, w, get("stem_b").double(), padding=1)).float())
+    tw, tb = get("tower_w"), get("tower_b").double()
+    for b in range(blocks):
+        w1 = q(tw[2 * b]).reshape(3, 3, 128, 128).permute(3, 2, 0, 1)
+        w2 = q(tw[2 * b + 1]).reshape(3, 3, 128, 128).permute(3, 2, 0, 1)
+        y = q(F.relu(F.conv2d(x, w1, tb[2 * b], padding=1)).float())
+        x = q(F.relu(F.conv2d(y, w2, tb[2 * b + 1], padding=1) + x).float())
+    pol = F.relu(torch.einsum("bchw,cp->bphw", x, get("pol_w").double()) + get("pol_b").double().view(1, 2, 1, 1)).reshape(len(boards), 84)
+    pi = torch.softmax(pol @ get("pol_fc_w").double() + get("pol_fc_b").double(), dim=1)
+    val = F.relu(torch.einsum("bchw,c->bhw", x, get("val_w").double()) + get("val_b").double()).reshape(len(boards), 42)
+    h = F.relu(val @ get("val_fc1_w").double() + get("val_fc1_b").double())
+    v = torch.tanh(h @ get("val_fc2_w").double() + get("val_fc2_b").double())
+    return pi.numpy(), v.numpy()
+
+
+@pytest.mark.parametrize("blocks", [1, 6])
+def test_bf16_tensor_core_path(azb, oracle, blocks):
+    net = azb.NNet(seed=7, blocks=blocks, precision=azb.NNET_BF16_TC)
+    feats = random_features(oracle, 60)          # ~1200 positions: many M tiles, ragged last tile
+    pi, v = net.predict(feats)
+    rpi, rv = torch_forward_bf16(azb, net.get_params(), blocks, feats)
+    # same quantisation points, only the fp32 accumulation order differs.  One layer pair: 5e-3.
+    # Through 12 layers a borderline bf16 rounding that flips one ulp (0.4 %) is amplified by the
+    # random-init tower, so the worst element gets the bf16 tolerance (5e-2) and the MEAN stays tight.
+    tol = 5e-3 if blocks == 1 else 5e-2
+    assert np.abs(pi - rpi).max() < tol, np.abs(pi - rpi).max()
+    assert np.abs(v - rv).max() < tol, np.abs(v - rv).max()
+    assert np.abs(pi - rpi).mean() < 2e-3 and np.abs(v - rv).mean() < 4e-3, (np.abs(pi - rpi).mean(), np.abs(v - rv).mean())
+    # against the fp32 network: stated bf16 tolerance 5e-2 (13 layers of bf16 rounding)
+    net32 = azb.NNet(seed=7, blocks=blocks, precision=azb.NNET_FP32)
+    p32, v32 = net32.predict(feats)
+    assert np.abs(pi - p32).max() < 5e-2 and np.abs(v - v32).max() < 5e-2
+    assert np.allclose(pi.sum(1), 1.0, atol=1e-5)
+
+
+def test_bf16_path_is_batch_independent(azb, oracle):
+    net = azb.NNet(seed=3, blocks=2, precision=azb.NNET_BF16_TC)
+    feats = random_features(oracle, 30)
+    pi, v = net.predict(feats)
+    for lo, hi in ((0, 1), (5, 6), (100, 300), (len(feats) - 1, len(feats))):
+        p1, v1 = net.predict(feats[lo:hi])
+        assert np.array_equal(p1.view(np.uint32), pi[lo:hi].view(np.uint32)) and np.array_equal(v1, v[lo:hi])
+
+
+def test_selfplay_with_tensor_core_network_matches_oracle(azb, oracle):
+    net = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
+    coach = azb.Coach(nnet=net, num_sims=25, seed=2, evaluator=azb.EVAL_NNET)
+    st = coach.self_play(4, 0)
+    tr = coach.traces()
+    for g in range(4):
+        o = oracle.execute_episode(num_sims=25, quirks=0, seed=2, episode_id=g, evaluator=oracle.EVAL_CALLBACK,
+                                   callback=net.predict)
+        n = o["plies"]
+        assert tr["plies"][g] == n
+        assert tr["actions"][g, :n].tolist() == o["actions"][:n].tolist()
+        assert np.array_equal(tr["counts"][g, :n], o["counts"][:n])
+
+
+def test_arena_two_networks(azb, oracle):
+    a = azb.NNet(seed=7, blocks=1, precision=azb.NNET_BF16_TC)
+    b = azb.NNet(seed=8, blocks=1, precision=azb.NNET_BF16_TC)
+    counts, res, st = azb.arena_play_games(8, azb.EVAL_NNET, azb.EVAL_NNET, a, b, k_open=2, num_sims=20, seed=5)
+    assert sum(counts) == 8 and st["evals"] > 0
+    counts2, res2, _ = azb.arena_play_games(8, azb.EVAL_NNET, azb.EVAL_NNET, a, b, k_open=2, num_sims=20, seed=5)
+    assert res.tolist() == res2.tolist()
