@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libazb200.so")
+LIB_PATH = os.environ.get("AZB200_LIB", os.path.join(_HERE, "libazb200.so"))  # override: kernel-variant sweeps
 
 Q1_WIN_RANGE_LITERAL = 1
 Q2_BACKUP_NO_ALTERNATE = 2
@@ -136,6 +136,7 @@ def _load():
         "azb_nnet_get_params": [vp, vp, u64],
         "azb_nnet_set_params": [vp, vp, u64],
         "azb_coach_set_nnet": [vp, vp],
+        "azb_nnet_benchmark": [vp, u64, u32, C.POINTER(C.c_double)],
         "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
                                  C.POINTER(SelfPlayStats)],
     }
@@ -413,6 +414,12 @@ class NNet:
         v = np.zeros(n, np.float32)
         _check(lib.azb_nnet_predict(self._h, _ptr(boards), n, model_id, _ptr(pi), _ptr(v)))
         return pi, v
+
+    def benchmark(self, batch, iters=10):
+        """Device-only mean milliseconds per forward pass over `batch` resident positions."""
+        ms = C.c_double()
+        _check(lib.azb_nnet_benchmark(self._h, batch, iters, C.byref(ms)))
+        return ms.value
 
     def num_params(self):
         n = C.c_uint64()

@@ -864,6 +864,41 @@ int azb_nnet_predict(azb_nnet* n, const float* boards, size_t batch, size_t /*mo
   AZB_CUDA(cudaMemcpy(v, n->d_v.p, batch * 4, cudaMemcpyDeviceToHost));
   return AZB_OK;
 }
+int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_per_pass) {
+  if (!n || !ms_per_pass || batch == 0 || iters == 0 || batch > (1u << 22)) return fail(AZB_ERR_INVALID, "bad argument");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  std::vector<uint4> h(batch);
+  uint64_t st = 42;
+  for (auto& x : h) {  // random disjoint stone sets (not necessarily reachable positions)
+    const uint64_t a = sm64(st) & kBoard42, b = sm64(st) & kBoard42 & ~a;
+    x = make_uint4(static_cast<uint32_t>(a), static_cast<uint32_t>(a >> 32), static_cast<uint32_t>(b), static_cast<uint32_t>(b >> 32));
+  }
+  AZB_CUDA(n->d_states.ensure(batch * 16));
+  AZB_CUDA(n->d_pi.ensure(batch * 32));
+  AZB_CUDA(n->d_v.ensure(batch * 4));
+  AZB_CUDA(cudaMemcpy(n->d_states.p, h.data(), batch * 16, cudaMemcpyHostToDevice));
+  const uint32_t B = static_cast<uint32_t>(batch);
+  for (int w = 0; w < 3; ++w) {
+    int rc = nnet_forward(n, n->d_states.as<uint4>(), nullptr, B, n->d_pi.as<float>(), n->d_v.as<float>(), 0);
+    if (rc) return rc;
+  }
+  cudaEvent_t e0, e1;
+  AZB_CUDA(cudaEventCreate(&e0));
+  AZB_CUDA(cudaEventCreate(&e1));
+  AZB_CUDA(cudaEventRecord(e0));
+  for (uint32_t i = 0; i < iters; ++i) {
+    int rc = nnet_forward(n, n->d_states.as<uint4>(), nullptr, B, n->d_pi.as<float>(), n->d_v.as<float>(), 0);
+    if (rc) return rc;
+  }
+  AZB_CUDA(cudaEventRecord(e1));
+  AZB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_pass = ms / iters;
+  return AZB_OK;
+}
 int azb_coach_set_nnet(azb_coach* c, azb_nnet* n) {
   if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
   if (n && n->cfg.device != c->cfg.device) return fail(AZB_ERR_INVALID, "network and coach live on different devices");

@@ -26,7 +26,17 @@ namespace azb {
 
 constexpr int kTcTileM = 128;
 constexpr int kTcBlockK = 64;
-constexpr int kTcStages = 4;
+#ifndef AZB_TC_STAGES
+#define AZB_TC_STAGES 6
+#endif
+#ifndef AZB_TC_LOOKAHEAD
+#define AZB_TC_LOOKAHEAD 4
+#endif
+#ifndef AZB_TC_CPASYNC
+#define AZB_TC_CPASYNC "cp.async.cg.shared.global"
+#endif
+constexpr int kTcStages = AZB_TC_STAGES;
+constexpr int kTcLookahead = AZB_TC_LOOKAHEAD;            // cp.async groups a producer thread keeps in flight (< stages)
 constexpr int kTcKBlocks = 18;              // 9 taps x 2 halves of 64 input channels
 constexpr uint32_t kTcTileBytes = 128 * 64 * 2;  // one A or B stage: 128 rows x 128 bytes
 constexpr int kTcThreads = 320;
@@ -118,11 +128,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   const uint32_t sA = base, sB = base + kTcStages * kTcTileBytes;
   const uint32_t bars = sB + kTcStages * kTcTileBytes;
   auto bar_full_a = [&](int s) { return bars + 8u * s; };
-  auto bar_full_b = [&](int s) { return bars + 32u + 8u * s; };
-  auto bar_empty = [&](int s) { return bars + 64u + 8u * s; };
-  auto bar_acc_full = [&](int a) { return bars + 96u + 8u * a; };
-  auto bar_acc_empty = [&](int a) { return bars + 112u + 8u * a; };
-  const uint32_t tmem_slot = bars + 128u;
+  auto bar_full_b = [&](int s) { return bars + 64u + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 128u + 8u * s; };
+  auto bar_acc_full = [&](int a) { return bars + 192u + 8u * a; };
+  auto bar_acc_empty = [&](int a) { return bars + 208u + 8u * a; };
+  const uint32_t tmem_slot = bars + 224u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
@@ -152,41 +162,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-    // ===== A producers: thread t gathers row t of the tile for every (tap, half) =====
+    // ===== A producers: 8 consecutive lanes fetch the 8 16-byte chunks of one 128-byte row-half, so
+    // every warp-wide cp.async covers 4 whole 128-byte lines; thread t owns chunk t%8 of rows t/8 + 16i =====
     const int t = threadIdx.x;
+    const uint32_t j = t & 7u;
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const uint32_t m = tile * kTcTileM + t;
-      const bool live = m < rows;
-      const uint32_t cell = m % kCells;
-      const int r = cell / 7, c = cell % 7;
-      const uint32_t sw = (t & 7);
-      const uint32_t row_off = (t >> 3) * 1024u + (t & 7) * 128u;
+      uint32_t rc[8];  // per owned row: (r << 8) | c, or 0xFFFF when the row is past the end
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t m = tile * kTcTileM + (t >> 3) + 16u * i;
+        const uint32_t cell = m % kCells;
+        rc[i] = m < rows ? ((cell / 7u) << 8) | (cell % 7u) : 0xFFFFu;
+      }
       for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
         const int s = it % kTcStages;
         mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
         const int tap = kb >> 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const int rr = r + dy, cc = c + dx;
-        const bool ok = live && rr >= 0 && rr < 6 && cc >= 0 && cc < 7;
-        uint4 v[8];
-        if (ok) {
-          const uint4* src = reinterpret_cast<const uint4*>(g.in + (static_cast<size_t>(m) + dy * 7 + dx) * kNetC + (kb & 1) * kTcBlockK);
+        const uint32_t stage = sA + s * kTcTileBytes;
+        const __nv_bfloat16* colbase = g.in + (kb & 1) * kTcBlockK + j * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = src[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t row = (t >> 3) + 16u * i;
+          const int rr = static_cast<int>(rc[i] >> 8) + dy, cc = static_cast<int>(rc[i] & 0xFFu) + dx;
+          const bool ok = rc[i] != 0xFFFFu && rr >= 0 && rr < 6 && cc >= 0 && cc < 7;
+          const size_t srow = static_cast<size_t>(tile * kTcTileM + row) + dy * 7 + dx;
+          const __nv_bfloat16* src = ok ? colbase + srow * kNetC : g.in;
+          // swizzle-128B: chunk j of row lands at chunk (j ^ row%8); src-size 0 zero-fills
+          const uint32_t dst = stage + (row >> 3) * 1024u + (row & 7u) * 128u + ((j ^ (row & 7u)) << 4);
+          asm volatile(AZB_TC_CPASYNC " [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
         }
-        const uint32_t dst = sA + s * kTcTileBytes + row_off;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y),
-                       "r"(v[j].z), "r"(v[j].w)
-                       : "memory");
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-        mbar_arrive(bar_full_a(s));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= static_cast<uint32_t>(kTcLookahead)) {  // the group issued kTcLookahead iterations ago has landed
+          asm volatile("cp.async.wait_group %0;" ::"n"(kTcLookahead) : "memory");
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+          mbar_arrive(bar_full_a((it - kTcLookahead) % kTcStages));
+        }
       }
     }
+    // drain: the last kTcLookahead groups
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async();
+    for (uint32_t k = (it > static_cast<uint32_t>(kTcLookahead) ? it - kTcLookahead : 0u); k < it; ++k)
+      mbar_arrive(bar_full_a(k % kTcStages));
   } else if (warp < 8) {
     // ===== epilogue: TMEM -> registers -> bias / residual / ReLU -> bf16 -> HBM =====
     const int q = warp - 4;

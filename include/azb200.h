@@ -180,6 +180,9 @@ int azb_nnet_predict(azb_nnet* n, const float* boards, size_t batch, size_t mode
 int azb_nnet_num_params(azb_nnet* n, uint64_t* count);
 int azb_nnet_get_params(azb_nnet* n, float* out, uint64_t capacity);
 int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count);
+/* Diagnostic: device-only timing of `iters` forward passes over `batch` synthetic positions that are
+ * already resident in HBM (CUDA events on the launching stream).  ms_per_pass is the mean. */
+int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_per_pass);
 /* The network that evaluates leaves when cfg.evaluator == AZB_EVAL_NNET (the NNet the
  * reference's inference thread owns, async_mcts.rs:125).  The coach does not own it. */
 int azb_coach_set_nnet(azb_coach* c, azb_nnet* n);
