@@ -220,7 +220,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   __nv_bfloat16* y = net->d_act[1].as<__nv_bfloat16>();
   __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
   const float* prm = net->d_params.as<float>();
-  const size_t total = static_cast<size_t>(max_batch) * kCells * kNetC;
+  const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prm, net->L, d_states, d_count, max_batch, x);
   const uint32_t tiles = (max_batch * kCells + kTcTileM - 1) / kTcTileM;
   const unsigned grid = std::min<uint32_t>(tiles, 148u);

@@ -54,8 +54,9 @@ inline NetLayout net_layout(int R) {
 
 // Policy + value heads on the tower output of one position (act[cell][C] in shared memory).
 // 128 threads.  Writes pi[0..6] (pi[7] = 0) and v.
+template <int STRIDE>
 __device__ __forceinline__ void heads_from_smem(const float* __restrict__ prm, const NetLayout& L,
-                                                const float (*act)[kNetC], float* scratch /* >= 256 floats */,
+                                                const float (*act)[STRIDE], float* scratch /* >= 256 floats */,
                                                 float* pi_out, float* v_out) {
   const int tid = threadIdx.x;
   float* pol = scratch;        // [84] plane*42 + cell
@@ -170,7 +171,7 @@ k_nnet_fp32(const float* __restrict__ prm, NetLayout L, const uint4* __restrict_
       for (int c = 0; c < kCells; ++c) a0[c][tid] = fmaxf(acc[c] + a0[c][tid], 0.0f);
       __syncthreads();
     }
-    heads_from_smem(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
+    heads_from_smem<kNetC>(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
   }
 }
 

@@ -294,42 +294,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
-// Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, channel).
+// Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, 8 channels).
 __global__ void k_stem_bf16(const float* __restrict__ prm, NetLayout L, const uint4* __restrict__ states,
                             const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(n_pos) * kCells * kNetC;
+  const size_t total = static_cast<size_t>(n_pos) * kCells * (kNetC / 8);
   if (idx >= total) return;
-  const uint32_t co = idx % kNetC;
-  const uint32_t m = idx / kNetC, pos = m / kCells, cell = m % kCells;
+  const uint32_t cg = idx % (kNetC / 8);
+  const uint32_t m = idx / (kNetC / 8), pos = m / kCells, cell = m % kCells;
   const int r = cell / 7, c = cell % 7;
   const uint4 st = states[pos];
   const uint64_t cur = (static_cast<uint64_t>(st.y) << 32) | st.x, opp = (static_cast<uint64_t>(st.w) << 32) | st.z;
-  float acc = prm[L.stem_b + co];
-  for (int tap = 0; tap < 9; ++tap) {
+  float acc[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(prm + L.stem_b + cg * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(prm + L.stem_b + cg * 8 + 4);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+  for (int tap = 0; tap < 9; ++tap) {  // accumulation order: tap-major, plane-minor (as the fp32 path)
     const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
     if (rr < 0 || rr >= 6 || cc < 0 || cc >= 7) continue;
     const int b = rr * 7 + cc;
-    if ((cur >> b) & 1ull) acc += prm[L.stem_w + (tap * 2 + 0) * kNetC + co];
-    if ((opp >> b) & 1ull) acc += prm[L.stem_w + (tap * 2 + 1) * kNetC + co];
+    for (int pl = 0; pl < 2; ++pl) {
+      if (!(((pl ? opp : cur) >> b) & 1ull)) continue;
+      const float* w = prm + L.stem_w + (tap * 2 + pl) * kNetC + cg * 8;
+      const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
+      acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w; acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+    }
   }
-  out[idx] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+  uint32_t pk[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[2 * k], 0.0f), fmaxf(acc[2 * k + 1], 0.0f));
+    pk[k] = *reinterpret_cast<const uint32_t*>(&p2);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-// Heads from the bf16 tower output: one CTA (128 threads) per position.
+// Heads from the bf16 tower output: one CTA (128 threads) per position.  Rows are padded to 129
+// floats so that threads working on different cells hit different banks.
 __global__ void __launch_bounds__(128)
 k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __nv_bfloat16* __restrict__ act,
              const uint32_t* __restrict__ count, uint32_t max_batch, float* __restrict__ pi_out, float* __restrict__ v_out) {
-  __shared__ float a0[kCells][kNetC];
+  __shared__ float a0[kCells][kNetC + 1];
   __shared__ float scratch[256];
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
   for (uint32_t pos = blockIdx.x; pos < n_pos; pos += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < kCells * kNetC; i += 128)
-      a0[i / kNetC][i % kNetC] = __bfloat162float(act[static_cast<size_t>(pos) * kCells * kNetC + i]);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(act + static_cast<size_t>(pos) * kCells * kNetC);
+    for (int i = threadIdx.x; i < kCells * kNetC / 2; i += 128) {
+      const uint32_t wd = src[i];
+      a0[(2 * i) / kNetC][(2 * i) % kNetC] = __uint_as_float(wd << 16);
+      a0[(2 * i) / kNetC][(2 * i) % kNetC + 1] = __uint_as_float(wd & 0xFFFF0000u);
+    }
     __syncthreads();
-    heads_from_smem(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
+    heads_from_smem<kNetC + 1>(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
   }
 }
 
