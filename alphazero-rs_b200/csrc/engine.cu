@@ -682,6 +682,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rp.mode = kModeSelfPlay;
     rp.ev_kind[0] = rp.ev_kind[1] = c->cfg.evaluator;
     rp.plies_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 0u : (c->cfg.plies_per_launch ? c->cfg.plies_per_launch : 2u);
+    rp.sims_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 16u : 0u;
     rp.n_slots = static_cast<uint32_t>(n_trees);
     rp.n_games = static_cast<uint32_t>(G);
     rp.first_game_id = first_game_id;
@@ -953,6 +954,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   rp.ev_kind[1] = eval_b;
   const bool any_net = eval_a >= AZB_EVAL_NNET || eval_b >= AZB_EVAL_NNET;
   rp.plies_per_launch = any_net ? 0u : (cfg->plies_per_launch ? cfg->plies_per_launch : 2u);
+  rp.sims_per_launch = any_net ? 16u : 0u;
   rp.n_slots = static_cast<uint32_t>(n_slots);
   rp.n_games = static_cast<uint32_t>(G);
   rp.half = static_cast<uint32_t>(half);

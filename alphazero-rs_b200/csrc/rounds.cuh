@@ -55,6 +55,8 @@ struct RoundParams {
   uint32_t mode;
   int32_t ev_kind[2];  // evaluator of player A / B (self-play: [0])
   uint32_t plies_per_launch;
+  uint32_t sims_per_launch;  // network rounds: a slot that needs no evaluation (endgame: terminal hits
+                             // only) yields after this many simulations, so a round never waits on it
   uint32_t n_slots, n_games;
   uint32_t half;    // arena: games [0, half) seat A first, [half, 2*half) seat B first (arena.rs:74-83)
   uint32_t k_open;  // arena: random opening plies
@@ -174,6 +176,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
   uint32_t step = rec->step, sims_done = rec->sims_done;
   uint32_t root_slot = rec->root_slot, root_meta = rec->root_meta;
   uint32_t plies_left = rp.plies_per_launch;
+  uint32_t sims_left = rp.sims_per_launch ? rp.sims_per_launch : 0xFFFFFFFFu;
 
   // which player's tree / evaluator is in use: self-play always 0; arena: the side to move
   // (games [0, half): A holds +1; games [half, ..): B holds +1 — arena.rs:74-83)
@@ -257,10 +260,12 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     }
     // ---- search (async_mcts.rs:191-217) ----
     const int ev = rp.ev_kind[side];
-    bool suspended = false;
+    bool suspended = false, yielded = false;
     Pending pd;
     BB leaf_pos;
     while (sims_done < p.num_sims && !t.error) {
+      if (sims_left == 0u) { yielded = true; break; }
+      sims_left--;
       if (sims_done == 0 && root_needs_eval(t, root_meta)) {  // repair F1
         if (ev >= AZB_EVAL_NNET) {
           pd.kind = kPendRoot;
@@ -279,6 +284,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
       sims_done++;
     }
     if (t.error) { err = t.error; break; }
+    if (yielded) break;  // phase stays Search; the slot continues next round
     if (suspended) {  // hand the leaf to the batched evaluator of this side's model
       uint32_t idx = 0;
       if (lane == 0) idx = atomicAdd(leaf.count + side, 1u);
