@@ -135,6 +135,12 @@ __device__ __forceinline__ float counter_q_fast(uint64_t c) {
   const float w = __fmaf_rn(e1, r, q1);
   return fdiv_by_int(w, static_cast<float>(n));
 }
+// index of the highest set bit (0xFFFFFFFF for 0): one FLO instead of 31 - clz
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
 __device__ __forceinline__ float redux_max_f32(float v) {
   float m;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
@@ -356,6 +362,17 @@ __device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root
   return meta_is_block(root_meta) && !(block_flags(t, root_meta) & kFlagHasPolicy);
 }
 
+// Rare path of best_child: children that are transposition links read Q and N from their owner.
+// Kept out of line so that the level loop carries no predicated-off instructions for it.
+__device__ __noinline__ uint2 resolve_links(const uint4* blocks, bool is_link, uint32_t owner_slot, uint32_t q_bits,
+                                            uint32_t nn) {
+  if (is_link) {
+    q_bits = reinterpret_cast<const uint32_t*>(blocks + owner_slot)[1];
+    nn = reinterpret_cast<const uint16_t*>(blocks + (owner_slot | 7u))[owner_slot & 7u];
+  }
+  return make_uint2(q_bits, nn);
+}
+
 // One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
 // network evaluation: then `pd` describes the pending expansion and `leaf` is the position to
 // evaluate.  ev_kind < AZB_EVAL_NNET evaluates inline and never suspends.
@@ -368,10 +385,11 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
   const bool depth_check = p.max_depth < 43u;
   uint32_t cur_slot = root_slot, cur_meta = root_meta;
   uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
-  uint32_t depth = 0, plen = 0, levels = 0;
+  uint32_t depth = 0, plen = 0;
+  uint32_t ball_min = 0xFFFFFFFFu;  // stays non-zero unless some level had no selectable child
+  uint32_t end_level = 1;           // levels walked = plen + end_level
   float v = 0.0f;
   for (;;) {
-    levels++;
     if (depth_check && depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
       v = 0.0f;
       break;
@@ -389,12 +407,10 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
     const uint32_t meta = w.w;
     const bool ok = lane < 7 && meta != kMetaInvalid;
     float q = __uint_as_float(w.y);
-    const bool is_link = ok && meta == kMetaLink;
-    if (__any_sync(kFull, is_link)) {  // resolve(): statistics come from the owner (node.rs:179-201)
-      if (is_link) {
-        q = ld_q(t, w.x);
-        nn = ld_n(t, w.x);
-      }
+    if (__any_sync(kFull, ok && meta == kMetaLink)) {  // resolve(): statistics come from the owner (node.rs:179-201)
+      const uint2 r2 = resolve_links(t.blocks, ok && meta == kMetaLink, w.x, w.y, nn);
+      q = __uint_as_float(r2.x);
+      nn = r2.y;
     }
     const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
     const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
@@ -405,23 +421,24 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
     const float mx = redux_max_f32(u);
     const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
     // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
-    // unwrap panics) flags the tree and lets this simulation run out on lane 0's slot.
-    if (ball == 0u) t.error = kErrInternal;
-    const int a = 31 - __clz(ball | 1u);
+    // unwrap panics) is detected after the walk (ball_min == 0); the walk itself stays in bounds.
+    ball_min = min(ball_min, ball);
+    const uint32_t a = bfind_u32(ball | 1u);
     const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
-    // node_path.push(current_head_id) (:270 / F3) together with the action taken
-    if (lane == 0) t.path[plen] = (cur_slot << 3) | static_cast<uint32_t>(a);
+    // node_path.push(current_head_id) (:270 / F3) together with the action taken; every lane
+    // stores the same word to the same address (cheaper than electing a lane)
+    t.path[plen] = (cur_slot << 3) | a;
     plen++;
     if (ch_meta == kMetaPlaceholder) {
       __syncwarp();
-      const uint32_t my_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+      const uint32_t my_slot = cur_meta * 8u + a;
       const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
       const uint64_t key2 = state_key(S2);
       uint32_t o_slot, o_meta, ins;
       if (tt_find(t, p.bucket_mask, key2, lane, o_slot, o_meta, ins)) {
         // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
         // owner without incrementing depth (async_mcts.rs:293-299)
-        if (lane == a) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
+        if (lane == static_cast<int>(a)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
         if (lane == kStatDupLinks) t.stat++;
         __syncwarp();
         cur_slot = o_slot;
@@ -430,16 +447,18 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
         continue;
       }
       if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return true; }
+      if (ball_min == 0u) { t.error = kErrInternal; return true; }
       // upgrade -> Some(true) (node.rs:290-322)
       const int code = game_ended_code(S2, p.quirks);
       if (code) {  // repair F5: terminal leaf, the net is skipped
         const uint32_t new_meta = kMetaTerminal | static_cast<uint32_t>(code);
         v = terminal_e(static_cast<uint32_t>(code));
-        if (lane == a) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+        if (lane == static_cast<int>(a)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
         tt_insert(t, ins, key2, my_slot, new_meta, lane);
         t.n_owners++;
         if (lane == kStatTerminal || lane == kStatExpansions) t.stat++;
         cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
+        end_level = 0;
         break;
       }
       if (t.n_blocks >= p.cap_blocks) { t.error = kErrBlocks; return true; }
@@ -449,7 +468,7 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
       pd.vm = valid_mask(S2.cur | S2.opp);
       pd.plen = plen;
       pd.ins = ins;
-      pd.levels = levels;
+      pd.levels = plen;
       pd.key = key2;
       if (ev_kind >= AZB_EVAL_NNET) {
         leaf = S2;
@@ -464,13 +483,14 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
       cur_slot = __shfl_sync(kFull, w.x, a);
       cur_meta = __shfl_sync(kFull, w.y, a);
     } else {
-      cur_slot = cur_meta * 8u + static_cast<uint32_t>(a);
+      cur_slot = cur_meta * 8u + a;
       cur_meta = ch_meta;
     }
     par_n = __shfl_sync(kFull, nn, a);
     depth++;
   }
-  backup_path(t, p, plen, cur_slot, v, levels, lane);
+  if (ball_min == 0u) { t.error = kErrInternal; return true; }
+  backup_path(t, p, plen, cur_slot, v, plen + end_level, lane);
   return true;
 }
 
