@@ -121,6 +121,7 @@ def _load():
         "azb_coach_self_play": [vp, u64, u64, C.POINTER(SelfPlayStats)],
         "azb_coach_traces": [vp, vp, vp, vp, vp, vp],
         "azb_coach_num_samples": [vp, C.POINTER(u64)],
+        "azb_coach_ply_times": [vp, vp],
         "azb_coach_export_samples": [vp, vp, vp, vp, u64, C.POINTER(u64)],
         "azb_mcts_create": [C.POINTER(Config), u64, C.POINTER(vp)],
         "azb_mcts_destroy": [vp],
@@ -129,6 +130,8 @@ def _load():
         "azb_mcts_stats": [vp, vp],
         "azb_mcts_dump": [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(u64)],
         "azb_selftest_arith": [vp],
+        "azb_host_alloc": [sz, C.POINTER(vp)],
+        "azb_host_free": [vp],
         "azb_nnet_create": [C.POINTER(NnetConfig), C.POINTER(vp)],
         "azb_nnet_destroy": [vp],
         "azb_nnet_predict": [vp, vp, sz, sz, vp, vp],
@@ -161,6 +164,25 @@ def _check(rc):
 
 def device_count():
     return lib.azb_device_count()
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory (azb_host_alloc)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = C.c_void_p()
+        _check(lib.azb_host_alloc(n, C.byref(self._p)))
+        buf = (C.c_char * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib.azb_host_free(self._p)
+            self._p = C.c_void_p()
+
+    __del__ = close
 
 
 def selftest_arith():
@@ -374,6 +396,11 @@ class Coach:
         final_player = np.zeros(g, np.int8)
         _check(lib.azb_coach_traces(self._h, _ptr(actions), _ptr(counts), _ptr(plies), _ptr(final_r), _ptr(final_player)))
         return dict(actions=actions, counts=counts, plies=plies, final_r=final_r, final_player=final_player)
+
+    def ply_times(self):
+        out = np.zeros((self.n_games, 64), np.uint64)
+        _check(lib.azb_coach_ply_times(self._h, _ptr(out)))
+        return out
 
     def num_samples(self):
         n = C.c_uint64()

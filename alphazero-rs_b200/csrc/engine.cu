@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -245,7 +246,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
 
 // Per-game outputs of a self-play / arena call.
 struct GameStore {
-  DevBuf plies, final_r, final_player, error, actions, counts, sample_state, sample_pi, stats, arena_result;
+  DevBuf plies, final_r, final_player, error, actions, counts, sample_state, sample_pi, stats, arena_result, ply_ns;
   GameBufs g{};
   int alloc(uint64_t G, bool samples) {
     AZB_CUDA(plies.ensure(G * 4));
@@ -275,6 +276,12 @@ struct GameStore {
     g.sample_state = sample_state.as<uint4>();
     g.sample_pi = sample_pi.as<float>();
     g.stats = stats.as<uint32_t>();
+    g.ply_ns = nullptr;
+    if (std::getenv("AZB200_PLY_TIMES")) {  // diagnostic: per-ply completion times
+      AZB_CUDA(ply_ns.ensure(G * kTraceStride * 8));
+      AZB_CUDA(cudaMemset(ply_ns.p, 0, G * kTraceStride * 8));
+      g.ply_ns = ply_ns.as<unsigned long long>();
+    }
     return AZB_OK;
   }
 };
@@ -364,6 +371,18 @@ int azb_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int azb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(AZB_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
+  AZB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return AZB_OK;
+}
+int azb_host_free(void* p) {
+  if (p) AZB_CUDA(cudaFreeHost(p));
+  return AZB_OK;
 }
 
 void azb_config_default(azb_config* c) {  // examples/connect_four.rs:55-71
@@ -739,6 +758,12 @@ int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint
   return AZB_OK;
 }
 
+int azb_coach_ply_times(azb_coach* c, uint64_t* ns) {
+  if (!c || !ns) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (c->n_games == 0 || !c->gs.g.ply_ns) return fail(AZB_ERR_INVALID, "no ply times (set AZB200_PLY_TIMES=1 before self-play)");
+  AZB_CUDA(cudaMemcpy(ns, c->gs.ply_ns.p, c->n_games * kTraceStride * 8, cudaMemcpyDeviceToHost));
+  return AZB_OK;
+}
 int azb_coach_num_samples(azb_coach* c, uint64_t* n) {
   if (!c || !n) return fail(AZB_ERR_INVALID, "NULL argument");
   *n = c->n_samples;

@@ -121,9 +121,10 @@ struct GameBufs {
   uint4* sample_state;    // [n_games][42] {cur.lo, cur.hi, opp.lo, opp.hi}
   float* sample_pi;       // [n_games][42][8]  pi[0..6], player in [7]
   uint32_t* stats;        // [n_games][8]  6 search stats, blocks used, owners
+  unsigned long long* ply_ns;  // [n_games][64] %globaltimer at the end of each ply (diagnostic), or nullptr
 };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n_games,
            uint64_t first_game_id, unsigned int* next_game) {
   const uint32_t tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -168,6 +169,11 @@ k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_tree
       const int a = choose_weighted(pi, u);                      // :137-138
       if (a < 0) { t.error = kErrInternal; break; }
       if (lane == 0) g.actions[grow] = static_cast<uint8_t>(a);
+      if (g.ply_ns && lane == 0) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        g.ply_ns[grow] = tns;
+      }
       board = play_canonical(board, a);                          // :140-142
       player = -player;
       code = static_cast<uint32_t>(game_ended_code(board, p.quirks));  // :144

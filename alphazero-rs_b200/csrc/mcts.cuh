@@ -149,12 +149,15 @@ __device__ __forceinline__ float redux_max_f32(float v) {
 
 // ---- transposition table (NodeStore.seen): buckets of 8 entries = one 128-byte line ------
 // Returns true and (slot, meta) when `key` is present; otherwise `ins` is the first free
-// entry on the probe path (0xFFFFFFFF when the table is full).
-__device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask, uint64_t key,
+// entry on the probe path (0xFFFFFFFF when the table is full).  `e` is the caller's (early) load of
+// entry (lane & 7) of the key's home bucket, so the miss latency overlaps the caller's other work.
+__device__ __forceinline__ uint4 tt_load_home(const WarpTree& t, uint32_t bucket_mask, uint64_t key, int lane) {
+  return t.table[hash_bucket(key, bucket_mask) * 8u + (lane & 7)];
+}
+__device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask, uint64_t key, uint4 e,
                                         int lane, uint32_t& slot, uint32_t& meta, uint32_t& ins) {
   uint32_t b = hash_bucket(key, bucket_mask);
   for (uint32_t probe = 0; probe <= bucket_mask; ++probe) {
-    const uint4 e = t.table[b * 8u + (lane & 7)];
     const uint64_t k = (static_cast<uint64_t>(e.y) << 32) | e.x;
     const uint32_t hit = __ballot_sync(kFull, k == key) & 0xFFu;
     if (hit) {
@@ -169,9 +172,14 @@ __device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask,
       return false;
     }
     b = (b + 1u) & bucket_mask;
+    e = t.table[b * 8u + (lane & 7)];
   }
   ins = 0xFFFFFFFFu;
   return false;
+}
+__device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask, uint64_t key,
+                                        int lane, uint32_t& slot, uint32_t& meta, uint32_t& ins) {
+  return tt_find(t, bucket_mask, key, tt_load_home(t, bucket_mask, key, lane), lane, slot, meta, ins);
 }
 __device__ __forceinline__ void tt_insert(const WarpTree& t, uint32_t ins, uint64_t key,
                                           uint32_t slot, uint32_t meta, int lane) {
@@ -262,8 +270,13 @@ __device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t p
   for (uint32_t base = 0; base < plen; base += 32u) {
     const uint32_t i = base + lane;
     const bool on = i < plen;
-    const uint32_t col = on ? (t.path[i] & 7u) : (8u + lane);
-    const uint32_t same = __match_any_sync(kFull, col);
+    const uint32_t col = on ? (t.path[i] & 7u) : 8u;
+    uint32_t same = 0u;  // lanes of this chunk that play the same column (7 independent ballots)
+#pragma unroll
+    for (uint32_t c = 0; c < 7u; ++c) {
+      const uint32_t bal = __ballot_sync(kFull, col == c);
+      if (col == c) same = bal;
+    }
     uint64_t bit = 0ull;
     if (on) {
       const uint64_t filled = occ | even | odd;
@@ -346,8 +359,8 @@ __device__ __forceinline__ void finish_root_eval(WarpTree& t, const SearchParams
 // upgrade -> Some(true), second half (node.rs:290-322, async_mcts.rs:317-353): mask + normalise
 // the policy, publish the new node, back the value up.
 __device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p, const Pending& pd,
-                                              float pi, float val, int lane) {
-  pi = mask_normalise(pi, pd.vm, lane);
+                                              float pi, float val, int lane, bool normalised = true) {
+  if (!normalised) pi = mask_normalise(pi, pd.vm, lane);
   if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
   write_child_block(t, pd.new_meta, pd.vm, pi, kFlagHasPolicy, lane);
   if (lane == 0) reinterpret_cast<uint32_t*>(t.blocks + pd.my_slot)[3] = pd.new_meta;
@@ -362,80 +375,99 @@ __device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root
   return meta_is_block(root_meta) && !(block_flags(t, root_meta) & kFlagHasPolicy);
 }
 
-// Rare path of best_child: children that are transposition links read Q and N from their owner.
-// Kept out of line so that the level loop carries no predicated-off instructions for it.
-__device__ __noinline__ uint2 resolve_links(const uint4* blocks, bool is_link, uint32_t owner_slot, uint32_t q_bits,
-                                            uint32_t nn) {
-  if (is_link) {
-    q_bits = reinterpret_cast<const uint32_t*>(blocks + owner_slot)[1];
-    nn = reinterpret_cast<const uint16_t*>(blocks + (owner_slot | 7u))[owner_slot & 7u];
-  }
-  return make_uint2(q_bits, nn);
-}
-
 // One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
 // network evaluation: then `pd` describes the pending expansion and `leaf` is the position to
 // evaluate.  ev_kind < AZB_EVAL_NNET evaluates inline and never suspends.
-__device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
-                                        uint32_t root_slot, uint32_t root_meta, int lane,
-                                        Pending& pd, BB& leaf) {
+// GENERIC = false is the hot variant: no max_depth check (depth counts moves into existing nodes, at
+// most 42 on this board, so the check is dead unless max_depth < 43) and the slow-path-free division;
+// GENERIC = true keeps the depth check and uses __fdiv_rn (trees whose `slow` flag is set).
+template <bool GENERIC>
+__device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
+                                             uint32_t root_slot, uint32_t root_meta, int lane,
+                                             Pending& pd, BB& leaf) {
   const float neg_inf = __uint_as_float(0xFF800000u);
-  // depth counts moves into existing nodes: at most 42 on this board, so the check is dead
-  // unless max_depth is smaller
-  const bool depth_check = p.max_depth < 43u;
   uint32_t cur_slot = root_slot, cur_meta = root_meta;
   uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
   uint32_t depth = 0, plen = 0;
   uint32_t ball_min = 0xFFFFFFFFu;  // stays non-zero unless some level had no selectable child
   uint32_t end_level = 1;           // levels walked = plen + end_level
   float v = 0.0f;
-  for (;;) {
-    if (depth_check && depth > p.max_depth) {  // :241-244 (+F6); eval_heuristic() == 0 for connect-four
-      v = 0.0f;
-      break;
-    }
-    if (cur_meta >= kMaxBlockId) {  // :246-249 (+F6) terminal node: value e
-      v = terminal_e(cur_meta & 3u);
-      if (lane == kStatTerminal) t.stat++;
-      break;
-    }
-    // best_child (node.rs:343-370); parent N is read after this simulation's visit()
-    const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
-    const uint4 w = bp[lane & 7];
-    uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
-    const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
-    const uint32_t meta = w.w;
-    const bool ok = lane < 7 && meta != kMetaInvalid;
-    float q = __uint_as_float(w.y);
-    if (__any_sync(kFull, ok && meta == kMetaLink)) {  // resolve(): statistics come from the owner (node.rs:179-201)
-      const uint2 r2 = resolve_links(t.blocks, ok && meta == kMetaLink, w.x, w.y, nn);
-      q = __uint_as_float(r2.x);
-      nn = r2.y;
-    }
-    const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
-    const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
-    float ex;
-    if (t.slow) ex = __fdiv_rn(t3, t4);
-    else ex = fdiv_by_int(t3, t4);
-    const float u = ok ? __fadd_rn(q, ex) : neg_inf;
-    const float mx = redux_max_f32(u);
-    const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
-    // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
-    // unwrap panics) is detected after the walk (ball_min == 0); the walk itself stays in bounds.
-    ball_min = min(ball_min, ball);
-    const uint32_t a = bfind_u32(ball | 1u);
-    const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
-    // node_path.push(current_head_id) (:270 / F3) together with the action taken; every lane
-    // stores the same word to the same address (cheaper than electing a lane)
-    t.path[plen] = (cur_slot << 3) | a;
-    plen++;
-    if (ch_meta == kMetaPlaceholder) {
+  // a node whose game has ended: value e (:246-249 + F6); the max_depth exit comes first (:241-244)
+  auto at_terminal = [&](uint32_t meta) {
+    if (GENERIC && depth > p.max_depth) return;  // v stays eval_heuristic() == 0
+    v = terminal_e(meta & 3u);
+    if (lane == kStatTerminal) t.stat++;
+  };
+  if (cur_meta >= kMaxBlockId) {
+    at_terminal(cur_meta);
+  } else {
+    for (;;) {
+      if (GENERIC && depth > p.max_depth) break;  // :241-244 (+F6): v = eval_heuristic() == 0
+      // best_child (node.rs:343-370); parent N is read after this simulation's visit()
+      const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
+      const uint4 w = bp[lane & 7];
+      uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
+      const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
+      const uint32_t meta = w.w;
+      const bool ok = lane < 7 && meta != kMetaInvalid;
+      float q = __uint_as_float(w.y);
+      if (ok && meta == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
+        q = ld_q(t, w.x);
+        nn = ld_n(t, w.x);
+      }
+      const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
+      const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
+      const float ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
+      const float u = ok ? __fadd_rn(q, ex) : neg_inf;
+      const float mx = redux_max_f32(u);
+      const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+      // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
+      // unwrap panics) is detected after the walk (ball_min == 0); the walk itself stays in bounds.
+      ball_min = min(ball_min, ball);
+      const uint32_t a = bfind_u32(ball | 1u);
+      const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
+      // node_path.push(current_head_id) (:270 / F3) together with the action taken; every lane
+      // stores the same word to the same address (cheaper than electing a lane)
+      t.path[plen] = (cur_slot << 3) | a;
+      plen++;
+      if (ch_meta < kMaxBlockId) {  // an expanded child: descend (:269-274 + F2)
+        cur_slot = cur_meta * 8u + a;
+        cur_meta = ch_meta;
+        par_n = __shfl_sync(kFull, nn, a);
+        if (GENERIC) depth++;
+        continue;
+      }
+      if (ch_meta != kMetaPlaceholder) {  // a link or a finished game
+        if (GENERIC) depth++;
+        if (ch_meta == kMetaLink) {
+          cur_slot = __shfl_sync(kFull, w.x, a);
+          cur_meta = __shfl_sync(kFull, w.y, a);
+          par_n = __shfl_sync(kFull, nn, a);
+          if (cur_meta < kMaxBlockId) continue;
+        } else {
+          cur_slot = cur_meta * 8u + a;
+          cur_meta = ch_meta;
+        }
+        at_terminal(cur_meta);
+        break;
+      }
+      // ---- the chosen child is a placeholder: upgrade it (:279-356) ----
       __syncwarp();
       const uint32_t my_slot = cur_meta * 8u + a;
       const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
       const uint64_t key2 = state_key(S2);
+      // the home bucket's load is issued first; terminal test / evaluation overlap its latency
+      const uint4 e_home = tt_load_home(t, p.bucket_mask, key2, lane);
+      const int code = game_ended_code(S2, p.quirks);
+      const uint32_t vm = valid_mask(S2.cur | S2.opp);
+      float pi = 0.0f, val = 0.0f;
+      const bool inline_eval = !code && ev_kind < AZB_EVAL_NNET;
+      if (inline_eval) {
+        evaluate_inline(ev_kind, S2, lane, pi, val);
+        pi = mask_normalise(pi, vm, lane);
+      }
       uint32_t o_slot, o_meta, ins;
-      if (tt_find(t, p.bucket_mask, key2, lane, o_slot, o_meta, ins)) {
+      if (tt_find(t, p.bucket_mask, key2, e_home, lane, o_slot, o_meta, ins)) {
         // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
         // owner without incrementing depth (async_mcts.rs:293-299)
         if (lane == static_cast<int>(a)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
@@ -444,12 +476,13 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
         cur_slot = o_slot;
         cur_meta = o_meta;
         par_n = ld_n(t, o_slot);
-        continue;
+        if (cur_meta < kMaxBlockId) continue;
+        at_terminal(cur_meta);
+        break;
       }
       if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return true; }
       if (ball_min == 0u) { t.error = kErrInternal; return true; }
       // upgrade -> Some(true) (node.rs:290-322)
-      const int code = game_ended_code(S2, p.quirks);
       if (code) {  // repair F5: terminal leaf, the net is skipped
         const uint32_t new_meta = kMetaTerminal | static_cast<uint32_t>(code);
         v = terminal_e(static_cast<uint32_t>(code));
@@ -465,33 +498,29 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
       pd.kind = kPendExpand;
       pd.my_slot = my_slot;
       pd.new_meta = t.n_blocks++;
-      pd.vm = valid_mask(S2.cur | S2.opp);
+      pd.vm = vm;
       pd.plen = plen;
       pd.ins = ins;
       pd.levels = plen;
       pd.key = key2;
-      if (ev_kind >= AZB_EVAL_NNET) {
+      if (!inline_eval) {
         leaf = S2;
         return false;
       }
-      float pi, val;
-      evaluate_inline(ev_kind, S2, lane, pi, val);
       finish_expand(t, p, pd, pi, val, lane);
       return true;
     }
-    if (ch_meta == kMetaLink) {
-      cur_slot = __shfl_sync(kFull, w.x, a);
-      cur_meta = __shfl_sync(kFull, w.y, a);
-    } else {
-      cur_slot = cur_meta * 8u + a;
-      cur_meta = ch_meta;
-    }
-    par_n = __shfl_sync(kFull, nn, a);
-    depth++;
   }
   if (ball_min == 0u) { t.error = kErrInternal; return true; }
   backup_path(t, p, plen, cur_slot, v, plen + end_level, lane);
   return true;
+}
+
+__device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
+                                        uint32_t root_slot, uint32_t root_meta, int lane,
+                                        Pending& pd, BB& leaf) {
+  if (t.slow || p.max_depth < 43u) return one_sim_impl<true>(t, p, ev_kind, root, root_slot, root_meta, lane, pd, leaf);
+  return one_sim_impl<false>(t, p, ev_kind, root, root_slot, root_meta, lane, pd, leaf);
 }
 
 // search (:191-217) with num_threads = 1 and a fused evaluator: nsims simulations from `root`.

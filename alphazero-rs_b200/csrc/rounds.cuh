@@ -213,7 +213,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
     const float val = leaf.v[row];
     if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
-    else finish_expand(t, p, pd, pi, val, lane);
+    else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false);
     sims_done++;
     phase = kPhaseSearch;
   }

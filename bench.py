@@ -11,7 +11,7 @@ batch of games (Coach::execute_episode x 4096, coach.rs:104-157,241-272).
   value  = simulations of all ranks / device time of the self-play kernel (CUDA events on the
            launching stream, max over ranks) — nothing but the config lives on the host;
   e2e    = the same through the C ABI as a caller uses it: azb_coach_self_play followed by
-           azb_coach_export_samples into pinned-size host buffers (config upload, kernel,
+           azb_coach_export_samples into page-locked host buffers (config upload, kernel,
            sample expansion, device->host copy of the SOA samples), wall clock, max over ranks.
 
 `--impl reference` times the CPU oracle (oracle/, the line-by-line restatement of the
@@ -112,7 +112,7 @@ def run_reference(args):
     ge.build_oracle()
     import oracle_api as orc
     cores = os.cpu_count() or 1
-    games_per_step = max(cores, 2 * cores if cores <= 64 else cores)
+    games_per_step = 16 * cores  # ~0.5 M simulations per core per step
     for _ in range(args.warmup):
         orc.bench_selfplay(cores, cores, num_sims=NUM_SIMS, seed=SEED, reserve=131072)
     sims = plies = 0
@@ -184,8 +184,9 @@ def main():
     coach = azb.Coach(num_sims=args.sims, seed=SEED, quirks=azb.PROFILE_SANE, evaluator=azb.EVAL_UNIFORM,
                       temp_threshold=15, cpuct=1, max_depth=1000, mcts_reserve_size=1000000, device=local_rank)
     G = args.games
-    cap = G * 84
-    out = (np.zeros((cap, 2, 6, 7), np.float32), np.zeros((cap, 7), np.float32), np.zeros(cap, np.float32))
+    cap = G * 84  # 42 plies x 2 symmetries: the most samples a game can produce
+    pinned = [azb.PinnedArray((cap, 2, 6, 7)), azb.PinnedArray((cap, 7)), azb.PinnedArray((cap,))]
+    out = tuple(p.array for p in pinned)
 
     def step(k):
         """One pass of the hot path through the public API, host buffers out."""

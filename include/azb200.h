@@ -45,6 +45,11 @@ const char* azb_last_error(void);
 /* Number of visible CUDA devices (0 when there is none; never fails). */
 int azb_device_count(void);
 
+/* Page-locked host buffers for the bulk outputs (samples): device->host copies into them run at
+ * full PCIe rate.  Ordinary malloc'ed memory works everywhere too, just slower. */
+int azb_host_alloc(size_t bytes, void** out);
+int azb_host_free(void* p);
+
 /* ---------------------------------------------------------------------------------------
  * Game = ConnectFour.  trait Game, src/game.rs:10-28; the only implementation is
  * examples/connect_four_lib/connect_four_game.rs.  State POD mirrors its struct (:18-23)
@@ -145,6 +150,9 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id,
                         azb_selfplay_stats* stats);
 int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint32_t* plies,
                      float* final_r, int8_t* final_player);
+/* Diagnostic (persistent schedule, env AZB200_PLY_TIMES=1): ns[n_games][64] = %globaltimer at the end
+ * of each ply of each game, 0 where no ply was played. */
+int azb_coach_ply_times(azb_coach* c, uint64_t* ns);
 /* Number of training samples the last self-play call produced (2 per ply: coach.rs:130-135). */
 int azb_coach_num_samples(azb_coach* c, uint64_t* n);
 /* SOATrainingSamples (src/nnet.rs:33): boards[n][2][6][7], pis[n][7], vs[n], ordered by game,
