@@ -196,7 +196,8 @@ struct azb_nnet {
         }
       AZB_CUDA(d_wtiles.ensure(tiles.size() * 2));
       AZB_CUDA(cudaMemcpy(d_wtiles.p, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
-      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     }
     return AZB_OK;
   }
@@ -224,7 +225,51 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prm, net->L, d_states, d_count, max_batch, x);
   const uint32_t tiles = (max_batch * kCells + kTcTileM - 1) / kTcTileM;
-  const unsigned grid = std::min<uint32_t>(tiles, 148u);
+  // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
+  // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can
+  // keep in flight through its shared-memory stages (Little's law at ~2 us L2 latency), not by L2
+  // traffic, and the multicast slices occupy the same stages; kept for the next layout (A reuse).
+  static const bool no_cluster = std::getenv("AZB200_TC_CLUSTER") == nullptr;
+  // how many clusters are co-resident (GPC sizes need not be multiples of the cluster size)
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(148u / kTcCluster * kTcCluster);
+    qc.blockDim = dim3(kTcThreads);
+    qc.dynamicSmemBytes = kTcSmemBytes;
+    cudaLaunchAttribute qa{};
+    qa.id = cudaLaunchAttributeClusterDimension;
+    qa.val.clusterDim.x = kTcCluster;
+    qa.val.clusterDim.y = 1;
+    qa.val.clusterDim.z = 1;
+    qc.attrs = &qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc<kTcCluster>, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  const bool clustered = !no_cluster && max_clusters > 0 && tiles >= 2u * kTcCluster;
+  const unsigned grid = clustered ? std::min<uint32_t>((tiles + kTcCluster - 1) / kTcCluster, static_cast<uint32_t>(max_clusters)) * kTcCluster
+                                  : std::min<uint32_t>(tiles, 148u);
+  auto launch_conv = [&](const ConvTcArgs& a) -> cudaError_t {
+    if (!clustered) {
+      k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+      return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kTcCluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_conv3x3_tc<kTcCluster>, a);
+  };
   for (int blk = 0; blk < net->L.R; ++blk) {
     ConvTcArgs a{};
     a.count = d_count;
@@ -232,11 +277,11 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     a.in = x; a.residual = nullptr; a.out = y;
     a.w_tiles = net->d_wtiles.as<uint8_t>() + static_cast<size_t>(2 * blk) * kTcKBlocks * kTcTileBytes;
     a.bias = prm + net->L.tower_b + (2 * blk) * kNetC;
-    k_conv3x3_tc<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    AZB_CUDA(launch_conv(a));
     a.in = y; a.residual = x; a.out = z;
     a.w_tiles += static_cast<size_t>(kTcKBlocks) * kTcTileBytes;
     a.bias += kNetC;
-    k_conv3x3_tc<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    AZB_CUDA(launch_conv(a));
     std::swap(x, z);
   }
   k_heads_bf16<<<std::min<uint32_t>(max_batch, 148u * 8u), 128, 0, st>>>(prm, net->L, x, d_count, max_batch, d_pi, d_v);

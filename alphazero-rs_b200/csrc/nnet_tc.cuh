@@ -40,6 +40,7 @@ constexpr int kTcLookahead = AZB_TC_LOOKAHEAD;            // cp.async groups a p
 constexpr int kTcKBlocks = 18;              // 9 taps x 2 halves of 64 input channels
 constexpr uint32_t kTcTileBytes = 128 * 64 * 2;  // one A or B stage: 128 rows x 128 bytes
 constexpr int kTcThreads = 320;
+constexpr int kTcCluster = 4;               // CTAs sharing each weight tile by multicast
 constexpr uint32_t kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -72,6 +73,19 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// The same copy delivered to the same shared-memory offset of every CTA in cta_mask; each destination
+// CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -99,6 +113,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -122,6 +141,10 @@ struct ConvTcArgs {
   uint32_t max_batch;
 };
 
+// CL = CTAs per cluster.  With CL > 1 the CTAs of a cluster walk their M tiles in lock-step and share
+// every weight tile: CTA r fetches the r-th 1/CL of it and multicasts that slice to all of them, and a
+// pipeline stage is released only when every CTA of the cluster has consumed it (multicast commit).
+template <int CL>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
@@ -138,12 +161,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
   const uint32_t rows = n_pos * kCells;
   const uint32_t n_tiles = (rows + kTcTileM - 1) / kTcTileM;
+  // tile schedule: group = cluster index, rank = CTA within the cluster; every CTA of a cluster runs
+  // the same number of iterations (tiles past the end are all-zero rows whose output is dropped)
+  const uint32_t rank = blockIdx.x % CL, group = blockIdx.x / CL, n_groups = gridDim.x / CL;
+  const uint32_t iters = (n_tiles + n_groups * CL - 1) / (n_groups * CL);
+  const uint16_t cl_mask = static_cast<uint16_t>((1u << CL) - 1u);
+  auto tile_of = [&](uint32_t i) { return (i * n_groups + group) * CL + rank; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(bar_full_a(s), 128);
       mbar_init(bar_full_b(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full(a), 1);
@@ -157,6 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before anyone multicasts into them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -167,7 +197,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
     const int t = threadIdx.x;
     const uint32_t j = t & 7u;
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t i = 0; i < iters; ++i) {
+      const uint32_t tile = tile_of(i);
+      if (CL == 1 && tile >= n_tiles) break;
       uint32_t rc[8];  // per owned row: (r << 8) | c, or 0xFFFF when the row is past the end
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -208,8 +240,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   } else if (warp < 8) {
     // ===== epilogue: TMEM -> registers -> bias / residual / ReLU -> bf16 -> HBM =====
     const int q = warp - 4;
-    uint32_t ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+    for (uint32_t ti = 0; ti < iters; ++ti) {
+      const uint32_t tile = tile_of(ti);
+      if (CL == 1 && tile >= n_tiles) break;
       const uint32_t a = ti & 1u;
       mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
       tc_fence_after();
@@ -250,8 +283,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
     }
   } else if (warp == 8) {
     // ===== MMA issuer: one elected thread =====
-    uint32_t it = 0, ti = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+    uint32_t it = 0;
+    for (uint32_t ti = 0; ti < iters; ++ti) {
+      if (CL == 1 && tile_of(ti) >= n_tiles) break;
       const uint32_t a = ti & 1u;
       mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -267,7 +301,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
 #pragma unroll
           for (int k = 0; k < kTcBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
             umma_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128, (kb | k) ? 1u : 0u);
-          umma_commit(bar_empty(s));  // frees the stage when these MMAs have read it
+          // frees the stage (in every CTA of the cluster) when these MMAs have read it
+          if (CL > 1) umma_commit_multicast(bar_empty(s), cl_mask);
+          else umma_commit(bar_empty(s));
           if (kb == kTcKBlocks - 1) umma_commit(bar_acc_full(a));
         }
         __syncwarp();
@@ -276,13 +312,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   } else {
     // ===== weight loader: bulk TMA of pre-swizzled 16-KB B tiles =====
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    constexpr uint32_t kSlice = kTcTileBytes / CL;
+    for (uint32_t i = 0; i < iters; ++i) {
+      if (CL == 1 && tile_of(i) >= n_tiles) break;
       for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
         const int s = it % kTcStages;
         mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
         if (lane == 0) {
-          mbar_arrive_expect_tx(bar_full_b(s), kTcTileBytes);
-          tma_bulk_g2s(sB + s * kTcTileBytes, g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes, kTcTileBytes, bar_full_b(s));
+          mbar_arrive_expect_tx(bar_full_b(s), kTcTileBytes);  // the whole tile: CL slices arrive
+          const uint8_t* src = g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kSlice;
+          const uint32_t dst = sB + s * kTcTileBytes + rank * kSlice;
+          if (CL > 1) tma_bulk_g2s_multicast(dst, src, kSlice, bar_full_b(s), cl_mask);
+          else tma_bulk_g2s(dst, src, kSlice, bar_full_b(s));
         }
         __syncwarp();
       }
@@ -291,6 +332,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
