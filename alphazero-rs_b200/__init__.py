@@ -16,6 +16,8 @@ import os
 
 import numpy as np
 
+from . import sharding  # noqa: F401  (multi-GPU game sharding helpers)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AZB200_LIB", os.path.join(_HERE, "libazb200.so"))  # override: kernel-variant sweeps
 

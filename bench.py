@@ -173,12 +173,7 @@ def main():
             torch.cuda.synchronize()
 
     def reduce(x, op):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
-        return float(t.item())
+        return azb.sharding.reduce_scalar(dist, x, op, device="cuda" if dist is not None else None)
 
     import numpy as np
     coach = azb.Coach(num_sims=args.sims, seed=SEED, quirks=azb.PROFILE_SANE, evaluator=azb.EVAL_UNIFORM,
@@ -190,7 +185,7 @@ def main():
 
     def step(k):
         """One pass of the hot path through the public API, host buffers out."""
-        first = (k * world + rank) * G  # global game ids: disjoint per rank and per step
+        first, _ = azb.sharding.shard(k, rank, world, G)  # global game ids: disjoint per rank and per step
         t0 = time.perf_counter()
         st = coach.self_play(G, first)
         _, _, vs = coach.export_samples(out)
