@@ -165,7 +165,8 @@ struct azb_nnet {
   NetLayout L;
   std::vector<float> h_params;
   DevBuf d_params;
-  DevBuf d_wtiles;                     // bf16 path: [2R][18] pre-swizzled 16-KB weight tiles
+  DevBuf d_wtiles;                     // bf16 path: kTcWeightCopies x [2R][18] pre-swizzled 16-KB weight tiles
+  size_t wtile_copy_bytes = 0;
   DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
   DevBuf d_feat, d_states, d_pi, d_v;  // azb_nnet_predict staging
   static uint16_t bf16_rne(float f) {
@@ -194,8 +195,12 @@ struct azb_nnet {
               t[byte / 2] = bf16_rne(w[static_cast<size_t>(half * 64 + k) * kNetC + n]);
             }
         }
-      AZB_CUDA(d_wtiles.ensure(tiles.size() * 2));
-      AZB_CUDA(cudaMemcpy(d_wtiles.p, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
+      // kTcWeightCopies replicas at different addresses: every CTA streams the same tile sequence at
+      // about the same time; spreading the CTAs over replicas spreads that traffic over the L2 slices
+      wtile_copy_bytes = tiles.size() * 2;
+      AZB_CUDA(d_wtiles.ensure(wtile_copy_bytes * kTcWeightCopies));
+      for (int c = 0; c < kTcWeightCopies; ++c)
+        AZB_CUDA(cudaMemcpy(d_wtiles.as<uint8_t>() + c * wtile_copy_bytes, tiles.data(), wtile_copy_bytes, cudaMemcpyHostToDevice));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     }
@@ -224,7 +229,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const float* prm = net->d_params.as<float>();
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prm, net->L, d_states, d_count, max_batch, x);
-  const uint32_t tiles = (max_batch * kCells + kTcTileM - 1) / kTcTileM;
+  const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
   // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can
   // keep in flight through its shared-memory stages (Little's law at ~2 us L2 latency), not by L2
@@ -276,6 +281,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     a.max_batch = max_batch;
     a.in = x; a.residual = nullptr; a.out = y;
     a.w_tiles = net->d_wtiles.as<uint8_t>() + static_cast<size_t>(2 * blk) * kTcKBlocks * kTcTileBytes;
+    a.w_copy_stride = net->wtile_copy_bytes;
     a.bias = prm + net->L.tower_b + (2 * blk) * kNetC;
     AZB_CUDA(launch_conv(a));
     a.in = y; a.residual = x; a.out = z;

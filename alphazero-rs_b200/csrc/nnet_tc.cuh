@@ -27,21 +27,27 @@ namespace azb {
 constexpr int kTcTileM = 128;
 constexpr int kTcBlockK = 64;
 #ifndef AZB_TC_STAGES
-#define AZB_TC_STAGES 6
-#endif
-#ifndef AZB_TC_LOOKAHEAD
-#define AZB_TC_LOOKAHEAD 4
+#define AZB_TC_STAGES 4
 #endif
 #ifndef AZB_TC_CPASYNC
 #define AZB_TC_CPASYNC "cp.async.cg.shared.global"
 #endif
 constexpr int kTcStages = AZB_TC_STAGES;
-constexpr int kTcLookahead = AZB_TC_LOOKAHEAD;            // cp.async groups a producer thread keeps in flight (< stages)
 constexpr int kTcKBlocks = 18;              // 9 taps x 2 halves of 64 input channels
-constexpr uint32_t kTcTileBytes = 128 * 64 * 2;  // one A or B stage: 128 rows x 128 bytes
+constexpr uint32_t kTcTileBytes = 128 * 64 * 2;  // one 128-row operand tile of a k-block: 128 rows x 128 bytes
+#ifndef AZB_TC_SUB
+#define AZB_TC_SUB 2
+#endif
+constexpr int kTcSub = AZB_TC_SUB;                        // 128-row A sub-tiles per CTA tile: they share every B tile
+constexpr int kTcCtaRows = kTcTileM * kTcSub;
+constexpr uint32_t kTcStageBytes = (kTcSub + 1) * kTcTileBytes;  // A sub-tiles + B
 constexpr int kTcThreads = 320;
+#ifndef AZB_TC_WCOPIES
+#define AZB_TC_WCOPIES 8
+#endif
+constexpr int kTcWeightCopies = AZB_TC_WCOPIES;
 constexpr int kTcCluster = 4;               // CTAs sharing each weight tile by multicast
-constexpr uint32_t kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -135,7 +141,8 @@ struct ConvTcArgs {
   const __nv_bfloat16* in;        // [rows][128]
   const __nv_bfloat16* residual;  // [rows][128] or nullptr
   __nv_bfloat16* out;             // [rows][128]
-  const uint8_t* w_tiles;         // [18][16384] pre-swizzled B tiles of this layer
+  const uint8_t* w_tiles;         // [18][16384] pre-swizzled B tiles of this layer (replica 0)
+  size_t w_copy_stride;           // byte distance between the kTcWeightCopies replicas
   const float* bias;              // [128]
   const uint32_t* count;          // positions this round (device), or nullptr
   uint32_t max_batch;
@@ -148,8 +155,10 @@ template <int CL>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
-  const uint32_t sA = base, sB = base + kTcStages * kTcTileBytes;
-  const uint32_t bars = sB + kTcStages * kTcTileBytes;
+  // stage s: [A sub-tile 0][A sub-tile 1][B]
+  auto stage_a = [&](int s, int sub) { return base + s * kTcStageBytes + sub * kTcTileBytes; };
+  auto stage_b = [&](int s) { return base + s * kTcStageBytes + kTcSub * kTcTileBytes; };
+  const uint32_t bars = base + kTcStages * kTcStageBytes;
   auto bar_full_a = [&](int s) { return bars + 8u * s; };
   auto bar_full_b = [&](int s) { return bars + 64u + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 128u + 8u * s; };
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
   const uint32_t rows = n_pos * kCells;
-  const uint32_t n_tiles = (rows + kTcTileM - 1) / kTcTileM;
+  const uint32_t n_tiles = (rows + kTcCtaRows - 1) / kTcCtaRows;
   // tile schedule: group = cluster index, rank = CTA within the cluster; every CTA of a cluster runs
   // the same number of iterations (tiles past the end are all-zero rows whose output is dropped)
   const uint32_t rank = blockIdx.x % CL, group = blockIdx.x / CL, n_groups = gridDim.x / CL;
@@ -180,8 +189,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {  // TMEM: 2 accumulator stages x 128 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+  if (warp == 9) {  // TMEM: 2 accumulator stages x 2 sub-tiles x 128 fp32 columns = all 512
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -200,10 +209,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
     for (uint32_t i = 0; i < iters; ++i) {
       const uint32_t tile = tile_of(i);
       if (CL == 1 && tile >= n_tiles) break;
-      uint32_t rc[8];  // per owned row: (r << 8) | c, or 0xFFFF when the row is past the end
+      uint32_t rc[8 * kTcSub];  // per owned row: (r << 8) | c, or 0xFFFF when the row is past the end
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t m = tile * kTcTileM + (t >> 3) + 16u * i;
+      for (int i = 0; i < 8 * kTcSub; ++i) {
+        const uint32_t m = tile * kTcCtaRows + (t >> 3) + 16u * i;
         const uint32_t cell = m % kCells;
         rc[i] = m < rows ? ((cell / 7u) << 8) | (cell % 7u) : 0xFFFFu;
       }
@@ -211,32 +220,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
         const int s = it % kTcStages;
         mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
         const int tap = kb >> 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const uint32_t stage = sA + s * kTcTileBytes;
+        const uint32_t stage = stage_a(s, 0);
         const __nv_bfloat16* colbase = g.in + (kb & 1) * kTcBlockK + j * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t row = (t >> 3) + 16u * i;
+        for (int i = 0; i < 8 * kTcSub; ++i) {
+          const uint32_t row = (t >> 3) + 16u * i;  // 0..255; sub-tile = row / 128
           const int rr = static_cast<int>(rc[i] >> 8) + dy, cc = static_cast<int>(rc[i] & 0xFFu) + dx;
           const bool ok = rc[i] != 0xFFFFu && rr >= 0 && rr < 6 && cc >= 0 && cc < 7;
-          const size_t srow = static_cast<size_t>(tile * kTcTileM + row) + dy * 7 + dx;
+          const size_t srow = static_cast<size_t>(tile * kTcCtaRows + row) + dy * 7 + dx;
           const __nv_bfloat16* src = ok ? colbase + srow * kNetC : g.in;
-          // swizzle-128B: chunk j of row lands at chunk (j ^ row%8); src-size 0 zero-fills
+          // swizzle-128B: chunk j of row lands at chunk (j ^ row%8); src-size 0 zero-fills.
+          // (row >> 3) * 1024 walks straight from sub-tile 0 into sub-tile 1 (16 KB each)
           const uint32_t dst = stage + (row >> 3) * 1024u + (row & 7u) * 128u + ((j ^ (row & 7u)) << 4);
           asm volatile(AZB_TC_CPASYNC " [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (it >= static_cast<uint32_t>(kTcLookahead)) {  // the group issued kTcLookahead iterations ago has landed
-          asm volatile("cp.async.wait_group %0;" ::"n"(kTcLookahead) : "memory");
-          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-          mbar_arrive(bar_full_a((it - kTcLookahead) % kTcStages));
-        }
+        // The barrier gets this thread's arrival when the copies above have landed: no polling, so the
+        // producers run ahead as far as the free stages allow (the consumer issues the proxy fence).
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full_a(s)) : "memory");
       }
     }
-    // drain: the last kTcLookahead groups
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fence_proxy_async();
-    for (uint32_t k = (it > static_cast<uint32_t>(kTcLookahead) ? it - kTcLookahead : 0u); k < it; ++k)
-      mbar_arrive(bar_full_a(k % kTcStages));
   } else if (warp < 8) {
     // ===== epilogue: TMEM -> registers -> bias / residual / ReLU -> bf16 -> HBM =====
     const int q = warp - 4;
@@ -246,10 +248,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
       const uint32_t a = ti & 1u;
       mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
       tc_fence_after();
-      const uint32_t m = tile * kTcTileM + q * 32 + lane;
+      for (int sub = 0; sub < kTcSub; ++sub) {
+      const uint32_t m = tile * kTcCtaRows + sub * kTcTileM + q * 32 + lane;
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t acc[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + ch * 32u, acc);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 256u + sub * 128u + ch * 32u, acc);
         if (m < rows) {
           const float* bias = g.bias + ch * 32;
           uint32_t packed[16];
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
           for (int j = 0; j < 4; ++j) op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(bar_acc_empty(a));
     }
@@ -294,13 +298,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
         const uint32_t ph = (it / kTcStages) & 1u;
         mbar_wait(bar_full_a(s), ph);
         mbar_wait(bar_full_b(s), ph);
+        fence_proxy_async();  // cp.async (generic proxy) writes of A -> the tensor core's async-proxy reads
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t ad = umma_desc_sw128(sA + s * kTcTileBytes);
-          const uint64_t bd = umma_desc_sw128(sB + s * kTcTileBytes);
+          const uint64_t bd = umma_desc_sw128(stage_b(s));
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
-            umma_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128, (kb | k) ? 1u : 0u);
+          for (int sub = 0; sub < kTcSub; ++sub) {
+            const uint64_t ad = umma_desc_sw128(stage_a(s, sub));
+#pragma unroll
+            for (int k = 0; k < kTcBlockK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+              umma_bf16(tmem_base + a * 256u + sub * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128, (kb | k) ? 1u : 0u);
+          }
           // frees the stage (in every CTA of the cluster) when these MMAs have read it
           if (CL > 1) umma_commit_multicast(bar_empty(s), cl_mask);
           else umma_commit(bar_empty(s));
@@ -320,8 +328,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
         mbar_wait(bar_empty(s), ((it / kTcStages) & 1u) ^ 1u);
         if (lane == 0) {
           mbar_arrive_expect_tx(bar_full_b(s), kTcTileBytes);  // the whole tile: CL slices arrive
-          const uint8_t* src = g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kSlice;
-          const uint32_t dst = sB + s * kTcTileBytes + rank * kSlice;
+          const uint8_t* src = g.w_tiles + (group % kTcWeightCopies) * g.w_copy_stride +
+                               static_cast<size_t>(kb) * kTcTileBytes + rank * kSlice;
+          const uint32_t dst = stage_b(s) + rank * kSlice;
           if (CL > 1) tma_bulk_g2s_multicast(dst, src, kSlice, bar_full_b(s), cl_mask);
           else tma_bulk_g2s(dst, src, kSlice, bar_full_b(s));
         }
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 // Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, 8 channels).
