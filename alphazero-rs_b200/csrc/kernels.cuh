@@ -17,13 +17,15 @@ struct Pools {
 };
 
 __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchParams& p, uint32_t tree) {
-  __shared__ uint32_t s_path[kWarpsPerCta][kPathCap];
+  __shared__ PathEnt s_path[kWarpsPerCta][kPathCap];
   WarpTree t;
   t.blocks = pools.blocks + static_cast<size_t>(tree) * p.cap_blocks * 8u;
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
   t.path = s_path[(threadIdx.x >> 5) % kWarpsPerCta];
   t.n_blocks = t.n_owners = t.error = t.slow = 0u;
+  t.pred_len = 0u;
   t.stat = 0u;
+  t.uni_prior = uniform_prior_table(threadIdx.x & 31);
   return t;
 }
 
@@ -235,6 +237,7 @@ __global__ void k_selftest_arith(unsigned long long* mismatches) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0, bad_q = 0;
+  if (tid == 0 && __uint_as_float(0x3E124925u) != __fdiv_rn(1.0f, 7.0f)) bad_div++;  // evaluate_inline's RN(1/7)
   for (uint32_t b = 1u + tid; b <= 65536u; b += nthreads) {
     const float fb = static_cast<float>(b);
     if (rcp_int(fb) != __frcp_rn(fb)) bad_rcp++;

@@ -56,15 +56,28 @@ struct TreeRec {
   uint32_t stat[8];
 };
 
+// One level of the current simulation's path (shared memory).  After the simulation's backup the
+// entries double as the PREDICTION for the next simulation of the same tree: consecutive
+// simulations share most of their path (measured: 5.5 of 7.6 levels), so the next simulation
+// evaluates up to four predicted levels at once, one per 8-lane group (one_sim_impl).
+struct __align__(16) PathEnt {
+  uint32_t sa;   // (slot << 3) | action: the node of this level (its owner slot) and the edge taken (7 = none yet)
+  uint32_t blk;  // the node's child block
+  uint32_t n;    // the node's N after the last backup that passed through it
+  uint32_t pad;
+};
+
 // Per-warp view of one tree.  Every member is warp-uniform except `stat` (lane k = stat k).
 struct WarpTree {
   uint4* blocks;   // slot id indexes this directly (16-byte slots, 8 per block)
   uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}
-  uint32_t* path;  // shared memory, kPathCap entries: (slot << 3) | action
+  PathEnt* path;   // shared memory, kPathCap entries
+  uint32_t pred_len;  // levels [0, pred_len) of `path` describe nodes the previous simulation walked
   uint32_t n_blocks, n_owners, error;
   uint32_t slow;  // != 0: use __fdiv_rn in the level loop (a prior outside the range the FMA division
                   // is proven for, or visit counts that may wrap the 16-bit N field, quirk Q6)
   uint32_t stat;
+  float uni_prior;  // lane k: the UNIFORM evaluator's normalised prior with k legal actions (uniform_prior_table)
 };
 
 // Visit counts stay below this => (1 + n) & 0xFFFF is never 0 in the level loop.
@@ -191,7 +204,7 @@ __device__ __forceinline__ void tt_insert(const WarpTree& t, uint32_t ins, uint6
 // Lane a (< 7) returns pi[a]; `v` is warp-uniform.  `kind` is warp-uniform.
 __device__ __forceinline__ void evaluate_inline(int kind, BB s, int lane, float& pi, float& v) {
   if (kind == AZB_EVAL_UNIFORM) {  // examples/connect_four.rs:34-38
-    pi = __fdiv_rn(1.0f, 7.0f);
+    pi = __uint_as_float(0x3E124925u);  // RN(1/7), checked by azb_selftest_arith
     v = 1.0f;
   } else {  // SURVEY App. B.6 hash evaluator
     uint64_t h = splitmix64(splitmix64(s.cur) + s.opp);
@@ -215,6 +228,46 @@ __device__ __forceinline__ float mask_normalise(float pi, uint32_t vm, int lane)
   return __fdiv_rn(pi, s2);
 }
 
+// evaluate_inline + mask_normalise.  For the UNIFORM evaluator the result depends only on how many
+// actions are legal (the sequential sum adds k copies of RN(1/7) and exact zeros), so it is read
+// from the per-warp table built by uniform_prior_table() with the very same operations.
+__device__ __forceinline__ float uniform_prior_table(int lane) {
+  const float c = __fdiv_rn(1.0f, 7.0f);
+  float s = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 7; ++a) s = __fadd_rn(s, a < lane ? c : 0.0f);  // lane k: k legal actions
+  return lane >= 1 && lane <= 7 ? __fdiv_rn(c, s) : 0.0f;
+}
+__device__ __forceinline__ void evaluate_masked(const WarpTree& t, int kind, BB s, uint32_t vm, int lane,
+                                                float& pi, float& v) {
+  if (kind == AZB_EVAL_UNIFORM) {
+    const float pr = __shfl_sync(kFull, t.uni_prior, __popc(vm & 0x7Fu));
+    pi = (lane < 7 && ((vm >> lane) & 1u)) ? pr : 0.0f;
+    v = 1.0f;
+  } else {
+    evaluate_inline(kind, s, lane, pi, v);
+    pi = mask_normalise(pi, vm, lane);
+  }
+}
+
+// game_ended_code() with the eight (direction, side) line tests spread over lanes: lane k & 7 tests
+// direction k >> 1 (scan order H, V, D1, D2) for side k & 1 (0 = cur).  Warp-uniform result.
+__device__ __forceinline__ int game_ended_code_warp(BB s, uint32_t quirks, int lane) {
+  const bool lit = quirks & AZB_Q1_WIN_RANGE_LITERAL;
+  const uint32_t dir = (static_cast<uint32_t>(lane) >> 1) & 3u;
+  const uint64_t b = (lane & 1) ? s.opp : s.cur;
+  const int sh = dir == 0u ? 1 : (dir == 1u ? 7 : (dir == 2u ? 8 : 6));
+  const uint64_t start = dir == 0u ? (lit ? kStartH_lit : kStartH_fix)
+                                   : (dir == 1u ? (lit ? kStartV_lit : kStartV_fix) : (dir == 2u ? kStartD1 : kStartD2));
+  const uint64_t ls = line_starts(b, sh, start);
+  const uint32_t bal = __ballot_sync(kFull, ls != 0ull) & 0xFFu;
+  if (bal == 0u) return ((s.cur | s.opp) == kBoard42) ? 3 : 0;
+  const int d2 = (__ffs(static_cast<int>(bal)) - 1) & ~1;  // the first direction in scan order with a line
+  const uint64_t c = __shfl_sync(kFull, ls, d2), o = __shfl_sync(kFull, ls, d2 + 1);
+  const uint64_t m = c | o;
+  return (c & (m & (0 - m))) ? 1 : 2;
+}
+
 // A fresh child block: every legal action is a placeholder with W = bias, N = 0, q = 0.
 __device__ __forceinline__ void write_child_block(const WarpTree& t, uint32_t blk, uint32_t vm,
                                                   float prior, uint32_t flags, int lane) {
@@ -236,6 +289,7 @@ __device__ __forceinline__ bool make_root(WarpTree& t, const SearchParams& p, BB
                                           uint32_t& root_slot, uint32_t& root_meta) {
   const uint64_t key = state_key(s);
   uint32_t o_slot, o_meta, ins;
+  t.pred_len = 0u;  // a new root: the previous path predicts nothing
   if (tt_find(t, p.bucket_mask, key, lane, o_slot, o_meta, ins)) {
     root_slot = o_slot;
     root_meta = o_meta;
@@ -270,7 +324,7 @@ __device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t p
   for (uint32_t base = 0; base < plen; base += 32u) {
     const uint32_t i = base + lane;
     const bool on = i < plen;
-    const uint32_t col = on ? (t.path[i] & 7u) : 8u;
+    const uint32_t col = on ? (t.path[i].sa & 7u) : 8u;
     uint32_t same = 0u;  // lanes of this chunk that play the same column (7 independent ballots)
 #pragma unroll
     for (uint32_t c = 0; c < 7u; ++c) {
@@ -295,7 +349,7 @@ __device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t p
 
 // unvisit of one path node, folded with the visit that preceded it (node.rs:77-92), and refresh
 // of the cached q.
-__device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
+__device__ __forceinline__ uint32_t backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
   uint64_t c = ld_counter(t, slot) + kVisit;
   c = counter_unvisit(c, v, quirks);
   *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q_fast(c)));
@@ -305,6 +359,7 @@ __device__ __forceinline__ void backup_node(const WarpTree& t, uint32_t slot, fl
   uint32_t* word = reinterpret_cast<uint32_t*>(t.blocks + (slot | 7u)) + ((slot & 7u) >> 1);
   const uint32_t sh = (slot & 1u) * 16u;
   *word = (*word & ~(0xFFFFu << sh)) | (counter_n(c) << sh);
+  return counter_n(c);
 }
 
 // ---- search_iteration (async_mcts.rs:219-371) --------------------------------
@@ -332,13 +387,12 @@ __device__ __forceinline__ void backup_path(WarpTree& t, const SearchParams& p, 
   for (uint32_t base = 0; base <= plen; base += 32u) {
     const uint32_t l = base + lane;
     if (l <= plen) {
-      const uint32_t slot = l < plen ? (t.path[l] >> 3) : leaf_slot;
+      const uint32_t slot = l < plen ? (t.path[l].sa >> 3) : leaf_slot;
       const bool neg = alternate && ((plen - l) & 1u);
-      backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+      t.path[l].n = backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
     }
   }
-  if (lane == kStatSims) t.stat++;
-  if (lane == kStatLevels) t.stat += levels;
+  t.stat += static_cast<uint32_t>(lane == kStatSims) + (lane == kStatLevels ? levels : 0u);
   __syncwarp();
 }
 
@@ -352,21 +406,29 @@ __device__ __forceinline__ void finish_root_eval(WarpTree& t, const SearchParams
   if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
   if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
   if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
-  if (lane == kStatEvals) t.stat++;
+  t.stat += static_cast<uint32_t>(lane == kStatEvals);
   backup_path(t, p, 0u, root_slot, -val, 1u, lane);
 }
 
 // upgrade -> Some(true), second half (node.rs:290-322, async_mcts.rs:317-353): mask + normalise
 // the policy, publish the new node, back the value up.
 __device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p, const Pending& pd,
-                                              float pi, float val, int lane, bool normalised = true) {
+                                              float pi, float val, int lane, bool normalised = true,
+                                              bool predict = false) {
   if (!normalised) pi = mask_normalise(pi, pd.vm, lane);
+  // predict: the path of this simulation, with the new node as its last level, is the prediction
+  // for the next one (only when path[0..plen) carries block ids, i.e. not after a resume)
+  t.pred_len = 0u;
+  if (predict) {
+    if (lane == 0) *reinterpret_cast<uint2*>(t.path + pd.plen) = make_uint2((pd.my_slot << 3) | 7u, pd.new_meta);
+    t.pred_len = pd.plen + 1u;
+  }
   if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
   write_child_block(t, pd.new_meta, pd.vm, pi, kFlagHasPolicy, lane);
   if (lane == 0) reinterpret_cast<uint32_t*>(t.blocks + pd.my_slot)[3] = pd.new_meta;
   tt_insert(t, pd.ins, pd.key, pd.my_slot, pd.new_meta, lane);
   t.n_owners++;
-  if (lane == kStatEvals || lane == kStatExpansions) t.stat++;
+  t.stat += static_cast<uint32_t>(lane == kStatEvals || lane == kStatExpansions);
   backup_path(t, p, pd.plen, pd.my_slot, -val, pd.levels, lane);  // :353 returns -v
 }
 
@@ -375,77 +437,142 @@ __device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root
   return meta_is_block(root_meta) && !(block_flags(t, root_meta) & kFlagHasPolicy);
 }
 
+// best_child's per-edge work (node.rs:343-370) for the node whose child block is `blk` and whose N
+// before this simulation's visit is `npar`: lane (8g + a) returns edge a's slot words `w`, visit
+// count `nn` and u = q + (cpuct*P*sqrt(N_parent + 1e-6))/(1 + n) (-inf when the lane takes no part).
+template <bool GENERIC>
+__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, uint32_t npar,
+                                           bool use, uint32_t la, uint4& w, uint32_t& nn, float& u, bool& ok) {
+  const uint4* bp = t.blocks + static_cast<size_t>(blk) * 8u;
+  w = bp[la];
+  nn = reinterpret_cast<const uint16_t*>(bp + 7)[la];
+  // parent N is read after this simulation's visit()
+  const float sq = sqrt_count(__fadd_rn(static_cast<float>((npar + 1u) & 0xFFFFu), kEps));
+  ok = use && la < 7u && w.w != kMetaInvalid;
+  float q = __uint_as_float(w.y);
+  if (__any_sync(kFull, ok && w.w == kMetaLink)) {  // rare; kept off the common instruction stream
+    if (ok && w.w == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
+      q = ld_q(t, w.x);
+      nn = ld_n(t, w.x);
+    }
+  }
+  const float t3 = __fmul_rn(__fmul_rn(cpuct_f, __uint_as_float(w.z)), sq);
+  const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
+  const float ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
+  u = ok ? __fadd_rn(q, ex) : __uint_as_float(0xFF800000u);
+}
+
 // One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
 // network evaluation: then `pd` describes the pending expansion and `leaf` is the position to
 // evaluate.  ev_kind < AZB_EVAL_NNET evaluates inline and never suspends.
 // GENERIC = false is the hot variant: no max_depth check (depth counts moves into existing nodes, at
-// most 42 on this board, so the check is dead unless max_depth < 43) and the slow-path-free division;
-// GENERIC = true keeps the depth check and uses __fdiv_rn (trees whose `slow` flag is set).
+// most 42 on this board, so the check is dead unless max_depth < 43), the slow-path-free division,
+// and a SPECULATIVE PREFIX: consecutive simulations of a tree share most of their path, so the walk
+// first re-checks the previous simulation's path (t.pred_len levels of t.path) four levels at a time,
+// one per 8-lane group (group g: level base + g; lane 8g + a: edge a).  What a node selects depends
+// only on that node's own block, never on how the walk got there, so a level's check is exact
+// whenever every level above it still selects the predicted edge; a level "holds" when no other edge
+// beats the predicted one under max_by's last-maximum rule (one shuffle + one ballot for four
+// levels, no arg-max).  The first level that does not hold is resolved with the real arg-max and the
+// walk goes on from there one level per iteration.  Results are bit-identical with the
+// one-level-at-a-time walk (the GENERIC variant, and the oracle).
+// GENERIC = true keeps the depth check, uses __fdiv_rn and never speculates (trees whose `slow`
+// flag is set).
 template <bool GENERIC>
 __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
                                              uint32_t root_slot, uint32_t root_meta, int lane,
                                              Pending& pd, BB& leaf) {
   const float neg_inf = __uint_as_float(0xFF800000u);
+  const uint32_t grp8 = lane & 24u, la = lane & 7u;  // first lane of my 8-lane group, my edge
+  const uint32_t pred_len = GENERIC ? 0u : t.pred_len;
+  t.pred_len = 0u;  // set again by the exits that leave a usable path behind
   uint32_t cur_slot = root_slot, cur_meta = root_meta;
-  uint32_t par_n = ld_n(t, root_slot);  // N of the current node before this simulation's visit
+  uint32_t par_n = 0u;  // N of the current node before this simulation's visit
   uint32_t depth = 0, plen = 0;
-  uint32_t ball_min = 0xFFFFFFFFu;  // stays non-zero unless some level had no selectable child
-  uint32_t end_level = 1;           // levels walked = plen + end_level
+  uint32_t empty_seen = 0u;  // != 0: some walked level had no selectable child
+  uint32_t end_level = 1;    // levels walked = plen + end_level
   float v = 0.0f;
   // a node whose game has ended: value e (:246-249 + F6); the max_depth exit comes first (:241-244)
   auto at_terminal = [&](uint32_t meta) {
     if (GENERIC && depth > p.max_depth) return;  // v stays eval_heuristic() == 0
     v = terminal_e(meta & 3u);
-    if (lane == kStatTerminal) t.stat++;
+    t.stat += static_cast<uint32_t>(lane == kStatTerminal);
   };
   if (cur_meta >= kMaxBlockId) {
     at_terminal(cur_meta);
   } else {
+    bool spec = !GENERIC && pred_len > 1u;
+    if (!spec) par_n = ld_n(t, root_slot);
     for (;;) {
       if (GENERIC && depth > p.max_depth) break;  // :241-244 (+F6): v = eval_heuristic() == 0
-      // best_child (node.rs:343-370); parent N is read after this simulation's visit()
-      const uint4* bp = t.blocks + static_cast<size_t>(cur_meta) * 8u;
-      const uint4 w = bp[lane & 7];
-      uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[lane & 7];
-      const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
-      const uint32_t meta = w.w;
-      const bool ok = lane < 7 && meta != kMetaInvalid;
-      float q = __uint_as_float(w.y);
-      if (ok && meta == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
-        q = ld_q(t, w.x);
-        nn = ld_n(t, w.x);
+      uint4 w;
+      uint32_t nn, a, sl, ch_meta, blk, sa;
+      float u;
+      bool ok;
+      if (spec) {
+        // ---- speculative prefix: which predicted levels still select the predicted edge? ----
+        uint32_t base = 0u, stop;
+        uint4 e;
+        for (;;) {
+          const uint32_t l = base + (grp8 >> 3);
+          const bool have = l < pred_len;
+          e = *reinterpret_cast<const uint4*>(t.path + (have ? l : 0u));  // {sa, blk, n, -}
+          eval_edges<GENERIC>(t, p.cpuct_f, e.y, e.z, have, la, w, nn, u, ok);
+          const uint32_t pa = e.x & 7u;  // the predicted edge (7 on the previous leaf: nothing holds)
+          const float upred = __shfl_sync(kFull, u, pa, 8);
+          const bool beaten = ok && (u > upred || (la > pa && u == upred));  // last maximum wins (node.rs:366)
+          // the last predicted level always stops the prefix: it is resolved with the real arg-max
+          // below (after a terminal / link exit its edge may hold again; the previous leaf has none)
+          stop = __ballot_sync(kFull, beaten || l + 1u >= pred_len);
+          if (stop) break;
+          base += 4u;
+        }
+        const uint32_t gs8 = (static_cast<uint32_t>(__ffs(static_cast<int>(stop))) - 1u) & 24u;
+        plen = base + (gs8 >> 3);  // the levels before it took the predicted edges; their entries stay
+        const bool mine = ok && grp8 == gs8;
+        const float mx = redux_max_f32(mine ? u : neg_inf);
+        const uint32_t ball = __ballot_sync(kFull, mine && u == mx);
+        empty_seen |= (ball == 0u);
+        sl = bfind_u32(ball | (1u << gs8));
+        a = sl & 7u;
+        ch_meta = __shfl_sync(kFull, w.w, sl);
+        blk = __shfl_sync(kFull, e.y, gs8);
+        sa = __shfl_sync(kFull, e.x, gs8);
+        spec = false;
+      } else {
+        // ---- best_child of the current node; max_by keeps the LAST maximum (node.rs:366).  An
+        // empty / all-NaN candidate set (node.rs:367 unwrap panics) is detected after the walk
+        // (empty_seen); the walk itself stays in bounds. ----
+        blk = cur_meta;
+        sa = cur_slot << 3;
+        eval_edges<GENERIC>(t, p.cpuct_f, blk, par_n, grp8 == 0u, la, w, nn, u, ok);
+        const float mx = redux_max_f32(u);
+        const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+        empty_seen |= (ball == 0u);
+        a = bfind_u32(ball | 1u);
+        sl = a;
+        ch_meta = __shfl_sync(kFull, w.w, sl);
       }
-      const float t3 = __fmul_rn(__fmul_rn(p.cpuct_f, __uint_as_float(w.z)), sq);
-      const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
-      const float ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
-      const float u = ok ? __fadd_rn(q, ex) : neg_inf;
-      const float mx = redux_max_f32(u);
-      const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
-      // max_by keeps the LAST maximum (node.rs:366).  An empty / all-NaN candidate set (node.rs:367
-      // unwrap panics) is detected after the walk (ball_min == 0); the walk itself stays in bounds.
-      ball_min = min(ball_min, ball);
-      const uint32_t a = bfind_u32(ball | 1u);
-      const uint32_t ch_meta = __shfl_sync(kFull, meta, a);
-      // node_path.push(current_head_id) (:270 / F3) together with the action taken; every lane
-      // stores the same word to the same address (cheaper than electing a lane)
-      t.path[plen] = (cur_slot << 3) | a;
+      // node_path.push(current_head_id) (:270 / F3) together with the action taken.  Every lane
+      // stores the same words to the same address (cheaper than electing a lane)
+      *reinterpret_cast<uint2*>(t.path + plen) = make_uint2((sa & ~7u) | a, blk);
       plen++;
       if (ch_meta < kMaxBlockId) {  // an expanded child: descend (:269-274 + F2)
-        cur_slot = cur_meta * 8u + a;
+        cur_slot = blk * 8u + a;
         cur_meta = ch_meta;
-        par_n = __shfl_sync(kFull, nn, a);
+        par_n = __shfl_sync(kFull, nn, sl);
         if (GENERIC) depth++;
         continue;
       }
       if (ch_meta != kMetaPlaceholder) {  // a link or a finished game
         if (GENERIC) depth++;
         if (ch_meta == kMetaLink) {
-          cur_slot = __shfl_sync(kFull, w.x, a);
-          cur_meta = __shfl_sync(kFull, w.y, a);
-          par_n = __shfl_sync(kFull, nn, a);
+          cur_slot = __shfl_sync(kFull, w.x, sl);
+          cur_meta = __shfl_sync(kFull, w.y, sl);
+          par_n = __shfl_sync(kFull, nn, sl);
           if (cur_meta < kMaxBlockId) continue;
         } else {
-          cur_slot = cur_meta * 8u + a;
+          cur_slot = blk * 8u + a;
           cur_meta = ch_meta;
         }
         at_terminal(cur_meta);
@@ -453,25 +580,22 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       }
       // ---- the chosen child is a placeholder: upgrade it (:279-356) ----
       __syncwarp();
-      const uint32_t my_slot = cur_meta * 8u + a;
+      const uint32_t my_slot = blk * 8u + a;
       const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
       const uint64_t key2 = state_key(S2);
       // the home bucket's load is issued first; terminal test / evaluation overlap its latency
       const uint4 e_home = tt_load_home(t, p.bucket_mask, key2, lane);
-      const int code = game_ended_code(S2, p.quirks);
+      const int code = game_ended_code_warp(S2, p.quirks, lane);
       const uint32_t vm = valid_mask(S2.cur | S2.opp);
       float pi = 0.0f, val = 0.0f;
       const bool inline_eval = !code && ev_kind < AZB_EVAL_NNET;
-      if (inline_eval) {
-        evaluate_inline(ev_kind, S2, lane, pi, val);
-        pi = mask_normalise(pi, vm, lane);
-      }
+      if (inline_eval) evaluate_masked(t, ev_kind, S2, vm, lane, pi, val);
       uint32_t o_slot, o_meta, ins;
       if (tt_find(t, p.bucket_mask, key2, e_home, lane, o_slot, o_meta, ins)) {
         // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
         // owner without incrementing depth (async_mcts.rs:293-299)
-        if (lane == static_cast<int>(a)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
-        if (lane == kStatDupLinks) t.stat++;
+        if (lane == static_cast<int>(sl)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
+        t.stat += static_cast<uint32_t>(lane == kStatDupLinks);
         __syncwarp();
         cur_slot = o_slot;
         cur_meta = o_meta;
@@ -481,15 +605,15 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         break;
       }
       if (ins == 0xFFFFFFFFu) { t.error = kErrTable; return true; }
-      if (ball_min == 0u) { t.error = kErrInternal; return true; }
+      if (empty_seen) { t.error = kErrInternal; return true; }
       // upgrade -> Some(true) (node.rs:290-322)
       if (code) {  // repair F5: terminal leaf, the net is skipped
         const uint32_t new_meta = kMetaTerminal | static_cast<uint32_t>(code);
         v = terminal_e(static_cast<uint32_t>(code));
-        if (lane == static_cast<int>(a)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+        if (lane == static_cast<int>(sl)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
         tt_insert(t, ins, key2, my_slot, new_meta, lane);
         t.n_owners++;
-        if (lane == kStatTerminal || lane == kStatExpansions) t.stat++;
+        t.stat += static_cast<uint32_t>(lane == kStatTerminal || lane == kStatExpansions);
         cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
         end_level = 0;
         break;
@@ -507,12 +631,13 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         leaf = S2;
         return false;
       }
-      finish_expand(t, p, pd, pi, val, lane);
+      finish_expand(t, p, pd, pi, val, lane, /*normalised=*/true, /*predict=*/!GENERIC);
       return true;
     }
   }
-  if (ball_min == 0u) { t.error = kErrInternal; return true; }
+  if (empty_seen) { t.error = kErrInternal; return true; }
   backup_path(t, p, plen, cur_slot, v, plen + end_level, lane);
+  if (!GENERIC) t.pred_len = plen;  // the walked nodes (not the terminal / depth-limit leaf)
   return true;
 }
 

@@ -207,7 +207,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
 
   if (phase == kPhasePending) {  // the network's answer for the suspended simulation is in
     Pending pd = rec->pd;
-    for (uint32_t i = lane; i < pd.plen; i += 32u) t.path[i] = rec->path[i];
+    for (uint32_t i = lane; i < pd.plen; i += 32u) t.path[i].sa = rec->path[i];
     __syncwarp();
     const size_t row = static_cast<size_t>(side) * rp.n_slots + rec->leaf_idx;
     const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
@@ -297,7 +297,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
         rec->leaf_idx = idx;
       }
       __syncwarp();
-      for (uint32_t i = lane; i < pd.plen; i += 32u) rec->path[i] = t.path[i];
+      for (uint32_t i = lane; i < pd.plen; i += 32u) rec->path[i] = t.path[i].sa;
       phase = kPhasePending;
       break;
     }
