@@ -47,8 +47,9 @@ AZB_HD uint32_t valid_mask(uint64_t occupied) {  // get_valid_moves, :104-109
 
 // The cell a stone dropped in column a lands on (:95-99): one above the column's top stone.
 AZB_HD uint64_t landing_bit(uint64_t occupied, int a) {
-  uint64_t mc = occupied & (kCol0 << a);
-  return mc ? ((mc & (0 - mc)) >> 7) : (1ull << (35 + a));
+  // all seven landing cells at once: empty cells that sit on the bottom row or right above a stone
+  const uint64_t landing = ((occupied >> 7) | (kTopRow << 35)) & ~occupied;
+  return landing & (kCol0 << a);
 }
 
 // get_next_state(+1, a) followed by get_canonical_form(-1) (async_mcts.rs:284-287 with F4/F10):

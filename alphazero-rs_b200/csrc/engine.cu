@@ -140,11 +140,23 @@ int capacity_error(uint32_t code) {
   }
 }
 
+// The search lives on L1 hits of the hot tree top: keep the unified L1/shared array as L1 and ask for
+// just enough shared memory for the CTAs the launch bounds allow (static smem + 1 KB reserved each).
+template <typename K>
+static cudaError_t search_carveout(K kernel) {
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  const size_t want = 7 * (fa.sharedSizeBytes + 1024);
+  const int pct = static_cast<int>((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 static int resident_trees(int device, uint32_t* out) {
   int per_sm = 0, sms = 0;
-  // the search lives on L1 hits of the hot tree top: keep the unified L1/shared array as L1
-  AZB_CUDA(cudaFuncSetAttribute(k_selfplay, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                8 /* percent: 7 CTAs x (768 B + 1 KB reserved) fit in the 16 KB configuration */));
+  AZB_CUDA(search_carveout(k_selfplay));
+  AZB_CUDA(search_carveout(k_round));
+  AZB_CUDA(search_carveout(k_mcts_search));
   AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay, kWarpsPerCta * 32, 0));
   AZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   *out = static_cast<uint32_t>(per_sm * sms * kWarpsPerCta);
@@ -789,6 +801,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   s.samples = s.plies * 2;
   s.device_ms = ms;
   s.launches = c->launches;
+  s.trees_resident = n_trees;
   c->n_games = G;
   c->n_samples = s.samples;
   if (stats) *stats = s;

@@ -18,10 +18,15 @@ struct Pools {
 
 __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchParams& p, uint32_t tree) {
   __shared__ PathEnt s_path[kWarpsPerCta][kPathCap];
+  __shared__ uint4 s_win[kWarpsPerCta][8];
   WarpTree t;
+  const int wi = (threadIdx.x >> 5) % kWarpsPerCta;
+  if ((threadIdx.x & 31) < 8) s_win[wi][threadIdx.x & 31] = win_table(p.quirks, threadIdx.x & 31);
+  __syncwarp();
+  t.win = s_win[wi];
   t.blocks = pools.blocks + static_cast<size_t>(tree) * p.cap_blocks * 8u;
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
-  t.path = s_path[(threadIdx.x >> 5) % kWarpsPerCta];
+  t.path = s_path[wi];
   t.n_blocks = t.n_owners = t.error = t.slow = 0u;
   t.pred_len = 0u;
   t.stat = 0u;

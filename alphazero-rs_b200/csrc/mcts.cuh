@@ -64,7 +64,8 @@ struct __align__(16) PathEnt {
   uint32_t sa;   // (slot << 3) | action: the node of this level (its owner slot) and the edge taken (7 = none yet)
   uint32_t blk;  // the node's child block
   uint32_t n;    // the node's N after the last backup that passed through it
-  uint32_t pad;
+  uint32_t sq;   // f32 bits of sqrt(n + 1 + 1e-6): best_child's parent term for the next visit
+  uint64_t cur, opp;  // the node's position, canonical for its side to move
 };
 
 // Per-warp view of one tree.  Every member is warp-uniform except `stat` (lane k = stat k).
@@ -72,6 +73,7 @@ struct WarpTree {
   uint4* blocks;   // slot id indexes this directly (16-byte slots, 8 per block)
   uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}
   PathEnt* path;   // shared memory, kPathCap entries
+  const uint4* win;  // shared memory, 8 entries: win_table()
   uint32_t pred_len;  // levels [0, pred_len) of `path` describe nodes the previous simulation walked
   uint32_t n_blocks, n_owners, error;
   uint32_t slow;  // != 0: use __fdiv_rn in the level loop (a prior outside the range the FMA division
@@ -236,7 +238,9 @@ __device__ __forceinline__ float uniform_prior_table(int lane) {
   float s = 0.0f;
 #pragma unroll
   for (int a = 0; a < 7; ++a) s = __fadd_rn(s, a < lane ? c : 0.0f);  // lane k: k legal actions
-  return lane >= 1 && lane <= 7 ? __fdiv_rn(c, s) : 0.0f;
+  float r = lane >= 1 && lane <= 7 ? __fdiv_rn(c, s) : 0.0f;
+  asm volatile("" : "+f"(r));  // opaque: keep it in its register instead of recomputing it at every use
+  return r;
 }
 __device__ __forceinline__ void evaluate_masked(const WarpTree& t, int kind, BB s, uint32_t vm, int lane,
                                                 float& pi, float& v) {
@@ -251,15 +255,20 @@ __device__ __forceinline__ void evaluate_masked(const WarpTree& t, int kind, BB 
 }
 
 // game_ended_code() with the eight (direction, side) line tests spread over lanes: lane k & 7 tests
-// direction k >> 1 (scan order H, V, D1, D2) for side k & 1 (0 = cur).  Warp-uniform result.
-__device__ __forceinline__ int game_ended_code_warp(BB s, uint32_t quirks, int lane) {
+// direction k >> 1 (scan order H, V, D1, D2) for side k & 1 (0 = cur).  The per-lane constants
+// {window starts, shift} sit in shared memory (t.win, filled by win_table()).  Warp-uniform result.
+__device__ __forceinline__ uint4 win_table(uint32_t quirks, int k) {
   const bool lit = quirks & AZB_Q1_WIN_RANGE_LITERAL;
-  const uint32_t dir = (static_cast<uint32_t>(lane) >> 1) & 3u;
-  const uint64_t b = (lane & 1) ? s.opp : s.cur;
-  const int sh = dir == 0u ? 1 : (dir == 1u ? 7 : (dir == 2u ? 8 : 6));
+  const uint32_t dir = (static_cast<uint32_t>(k) >> 1) & 3u;
+  const uint32_t sh = dir == 0u ? 1u : (dir == 1u ? 7u : (dir == 2u ? 8u : 6u));
   const uint64_t start = dir == 0u ? (lit ? kStartH_lit : kStartH_fix)
                                    : (dir == 1u ? (lit ? kStartV_lit : kStartV_fix) : (dir == 2u ? kStartD1 : kStartD2));
-  const uint64_t ls = line_starts(b, sh, start);
+  return make_uint4(static_cast<uint32_t>(start), static_cast<uint32_t>(start >> 32), sh, 0u);
+}
+__device__ __forceinline__ int game_ended_code_warp(const WarpTree& t, BB s, int lane) {
+  const uint4 k = t.win[lane & 7];
+  const uint64_t b = (lane & 1) ? s.opp : s.cur;
+  const uint64_t ls = line_starts(b, static_cast<int>(k.z), (static_cast<uint64_t>(k.y) << 32) | k.x);
   const uint32_t bal = __ballot_sync(kFull, ls != 0ull) & 0xFFu;
   if (bal == 0u) return ((s.cur | s.opp) == kBoard42) ? 3 : 0;
   const int d2 = (__ffs(static_cast<int>(bal)) - 1) & ~1;  // the first direction in scan order with a line
@@ -315,38 +324,6 @@ __device__ __forceinline__ bool make_root(WarpTree& t, const SearchParams& p, BB
   return true;
 }
 
-// The position reached from `root` by the path actions path[0..plen) (each entry's low 3 bits),
-// in canonical form for the side to move there.  Lane i places move i: its row follows from
-// the root column height plus the number of earlier path moves in the same column.
-__device__ __forceinline__ BB replay_path(const WarpTree& t, BB root, uint32_t plen, int lane) {
-  uint64_t even = 0ull, odd = 0ull;  // stones added by the root's side to move / by the other side
-  const uint64_t occ = root.cur | root.opp;
-  for (uint32_t base = 0; base < plen; base += 32u) {
-    const uint32_t i = base + lane;
-    const bool on = i < plen;
-    const uint32_t col = on ? (t.path[i].sa & 7u) : 8u;
-    uint32_t same = 0u;  // lanes of this chunk that play the same column (7 independent ballots)
-#pragma unroll
-    for (uint32_t c = 0; c < 7u; ++c) {
-      const uint32_t bal = __ballot_sync(kFull, col == c);
-      if (col == c) same = bal;
-    }
-    uint64_t bit = 0ull;
-    if (on) {
-      const uint64_t filled = occ | even | odd;
-      const uint32_t h = __popcll(filled & (kCol0 << col)) + __popc(same & ((1u << lane) - 1u));
-      bit = 1ull << ((5u - h) * 7u + col);
-    }
-    const uint64_t e = (i & 1u) ? 0ull : bit, o = (i & 1u) ? bit : 0ull;
-    even |= (static_cast<uint64_t>(__reduce_or_sync(kFull, static_cast<uint32_t>(e >> 32))) << 32) |
-            __reduce_or_sync(kFull, static_cast<uint32_t>(e));
-    odd |= (static_cast<uint64_t>(__reduce_or_sync(kFull, static_cast<uint32_t>(o >> 32))) << 32) |
-           __reduce_or_sync(kFull, static_cast<uint32_t>(o));
-  }
-  const BB abs{root.cur | even, root.opp | odd};
-  return (plen & 1u) ? BB{abs.opp, abs.cur} : abs;
-}
-
 // unvisit of one path node, folded with the visit that preceded it (node.rs:77-92), and refresh
 // of the cached q.
 __device__ __forceinline__ uint32_t backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
@@ -389,7 +366,9 @@ __device__ __forceinline__ void backup_path(WarpTree& t, const SearchParams& p, 
     if (l <= plen) {
       const uint32_t slot = l < plen ? (t.path[l].sa >> 3) : leaf_slot;
       const bool neg = alternate && ((plen - l) & 1u);
-      t.path[l].n = backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+      const uint32_t n_new = backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+      const float sq = sqrt_count(__fadd_rn(static_cast<float>((n_new + 1u) & 0xFFFFu), kEps));
+      *reinterpret_cast<uint2*>(&t.path[l].n) = make_uint2(n_new, __float_as_uint(sq));
     }
   }
   t.stat += static_cast<uint32_t>(lane == kStatSims) + (lane == kStatLevels ? levels : 0u);
@@ -439,15 +418,14 @@ __device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root
 
 // best_child's per-edge work (node.rs:343-370) for the node whose child block is `blk` and whose N
 // before this simulation's visit is `npar`: lane (8g + a) returns edge a's slot words `w`, visit
-// count `nn` and u = q + (cpuct*P*sqrt(N_parent + 1e-6))/(1 + n) (-inf when the lane takes no part).
+// count `nn` and u = q + (cpuct*P*sq)/(1 + n) (-inf when the lane takes no part), sq = sqrt(N_parent +
+// 1e-6) with the parent's N read after this simulation's visit().
 template <bool GENERIC>
-__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, uint32_t npar,
+__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, float sq,
                                            bool use, uint32_t la, uint4& w, uint32_t& nn, float& u, bool& ok) {
   const uint4* bp = t.blocks + static_cast<size_t>(blk) * 8u;
   w = bp[la];
   nn = reinterpret_cast<const uint16_t*>(bp + 7)[la];
-  // parent N is read after this simulation's visit()
-  const float sq = sqrt_count(__fadd_rn(static_cast<float>((npar + 1u) & 0xFFFFu), kEps));
   ok = use && la < 7u && w.w != kMetaInvalid;
   float q = __uint_as_float(w.y);
   if (__any_sync(kFull, ok && w.w == kMetaLink)) {  // rare; kept off the common instruction stream
@@ -502,6 +480,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
     at_terminal(cur_meta);
   } else {
     bool spec = !GENERIC && pred_len > 1u;
+    BB pos = root;  // position of the level being resolved (spec: reloaded from its path entry)
     if (!spec) par_n = ld_n(t, root_slot);
     for (;;) {
       if (GENERIC && depth > p.max_depth) break;  // :241-244 (+F6): v = eval_heuristic() == 0
@@ -516,8 +495,8 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         for (;;) {
           const uint32_t l = base + (grp8 >> 3);
           const bool have = l < pred_len;
-          e = *reinterpret_cast<const uint4*>(t.path + (have ? l : 0u));  // {sa, blk, n, -}
-          eval_edges<GENERIC>(t, p.cpuct_f, e.y, e.z, have, la, w, nn, u, ok);
+          e = *reinterpret_cast<const uint4*>(t.path + (have ? l : 0u));  // {sa, blk, n, sqrt}
+          eval_edges<GENERIC>(t, p.cpuct_f, e.y, __uint_as_float(e.w), have, la, w, nn, u, ok);
           const uint32_t pa = e.x & 7u;  // the predicted edge (7 on the previous leaf: nothing holds)
           const float upred = __shfl_sync(kFull, u, pa, 8);
           const bool beaten = ok && (u > upred || (la > pa && u == upred));  // last maximum wins (node.rs:366)
@@ -538,6 +517,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         ch_meta = __shfl_sync(kFull, w.w, sl);
         blk = __shfl_sync(kFull, e.y, gs8);
         sa = __shfl_sync(kFull, e.x, gs8);
+        if (plen) pos = BB{t.path[plen].cur, t.path[plen].opp};
         spec = false;
       } else {
         // ---- best_child of the current node; max_by keeps the LAST maximum (node.rs:366).  An
@@ -545,7 +525,8 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         // (empty_seen); the walk itself stays in bounds. ----
         blk = cur_meta;
         sa = cur_slot << 3;
-        eval_edges<GENERIC>(t, p.cpuct_f, blk, par_n, grp8 == 0u, la, w, nn, u, ok);
+        const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
+        eval_edges<GENERIC>(t, p.cpuct_f, blk, sq, grp8 == 0u, la, w, nn, u, ok);
         const float mx = redux_max_f32(u);
         const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
         empty_seen |= (ball == 0u);
@@ -557,6 +538,12 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       // stores the same words to the same address (cheaper than electing a lane)
       *reinterpret_cast<uint2*>(t.path + plen) = make_uint2((sa & ~7u) | a, blk);
       plen++;
+      // get_next_state + get_canonical_form (:284-287 with F4, F10) for the edge taken: the child's
+      // position, kept with its path level (a link leads to the same position's owner)
+      pos = play_canonical(pos, static_cast<int>(a));
+      *reinterpret_cast<uint4*>(&t.path[plen].cur) =
+          make_uint4(static_cast<uint32_t>(pos.cur), static_cast<uint32_t>(pos.cur >> 32),
+                     static_cast<uint32_t>(pos.opp), static_cast<uint32_t>(pos.opp >> 32));
       if (ch_meta < kMaxBlockId) {  // an expanded child: descend (:269-274 + F2)
         cur_slot = blk * 8u + a;
         cur_meta = ch_meta;
@@ -579,13 +566,12 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         break;
       }
       // ---- the chosen child is a placeholder: upgrade it (:279-356) ----
-      __syncwarp();
       const uint32_t my_slot = blk * 8u + a;
-      const BB S2 = replay_path(t, root, plen, lane);  // :284-287 with F4, F10
+      const BB S2 = pos;
       const uint64_t key2 = state_key(S2);
       // the home bucket's load is issued first; terminal test / evaluation overlap its latency
       const uint4 e_home = tt_load_home(t, p.bucket_mask, key2, lane);
-      const int code = game_ended_code_warp(S2, p.quirks, lane);
+      const int code = game_ended_code_warp(t, S2, lane);
       const uint32_t vm = valid_mask(S2.cur | S2.opp);
       float pi = 0.0f, val = 0.0f;
       const bool inline_eval = !code && ev_kind < AZB_EVAL_NNET;

@@ -54,41 +54,56 @@ def algorithmic_bytes_per_sim(levels_per_sim, expansions_per_sim, evals_ext_per_
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed window by a thread of this process through
+    NVML (pynvml): a polling nvidia-smi side process was measured to stall the CUDA calls of the step
+    it overlaps (tens of milliseconds of e2e time per step), in-process NVML reads do not."""
+    PERIOD_S = 0.05
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.rows, self.h, self.on, self.thread = index, [], None, False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # no NVML: report that, never fail the bench
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while self.on:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(self.PERIOD_S)
+
+    def window_open(self):
+        if self.h is None:
+            return
+        self.on = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def window_close(self):
+        self.on = False
+        if self.thread:
+            self.thread.join()
+
+    def stop(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "")]}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(n for n, bit in names.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_baseline_run(orc, seconds_target, threads):
@@ -138,7 +153,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="azb200", choices=["azb200", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (default: config 2)")
@@ -192,12 +207,12 @@ def main():
         t1 = time.perf_counter()
         return st, t1 - t0, len(vs)
 
+    sampler = ClockSampler(local_rank)
     for k in range(args.warmup):
         step(k)
-    sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.window_open()
     dev_ms = wall = 0.0
     tot = {}
     n_samples = 0
@@ -209,6 +224,7 @@ def main():
                 tot[key] = tot.get(key, 0) + v
         tot["blocks_used_max"] = max(tot.get("blocks_used_max", 0), st["blocks_used_max"])
     barrier()
+    sampler.window_close()
     clocks = sampler.stop() if rank == 0 else None
 
     dev_ms_max = reduce(dev_ms, "MAX")

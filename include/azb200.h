@@ -139,6 +139,7 @@ typedef struct azb_selfplay_stats {
   uint64_t blocks_used_max, owners_max; /* pool high-water marks over trees */
   double device_ms;                     /* CUDA-event time of the self-play kernels */
   uint64_t launches;                    /* kernels launched by the call */
+  uint64_t trees_resident;              /* games (trees) in flight at once */
 } azb_selfplay_stats;
 
 /* Coach::execute_episode over n_games concurrent games — coach.rs:104-157 and the episode

@@ -10,5 +10,5 @@ schedule = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 ppl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 coach = azb.Coach(num_sims=sims, seed=0xA1FA0, evaluator=ev, schedule=schedule, plies_per_launch=ppl)
 st = coach.self_play(games, 0)
-print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "terminal_hits", "dup_links", "device_ms", "launches")},
+print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "terminal_hits", "dup_links", "device_ms", "launches", "trees_resident")},
       "sims/s=%.3e" % (st["sims"] / st["device_ms"] * 1e3))
