@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -35,6 +36,20 @@ int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                  \
       return fail(AZB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
   } while (0)
+
+// AZB200_TIMING=1: host-side section times of the public calls on stderr (diagnostic)
+struct HostTimer {
+  bool on = std::getenv("AZB200_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  const char* what;
+  explicit HostTimer(const char* w) : what(w) {}
+  void lap(const char* section) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[azb200 %s] %-24s %8.3f ms\n", what, section, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -713,17 +728,25 @@ int azb_coach_destroy(azb_coach* c) {
 int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, azb_selfplay_stats* stats) {
   if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
   if (n_games == 0 || n_games > (1u << 26)) return fail(AZB_ERR_INVALID, "n_games out of range");
+  HostTimer tm("self_play");
   AZB_CUDA(cudaSetDevice(c->cfg.device));
   const SearchParams p = make_params(c->cfg, kMaxPlies);
   // how many trees live in HBM at once: all games, capped by co-resident warps, memory and config
   uint32_t resident = 0;
   int rc = resident_trees(c->cfg.device, &resident);
   if (rc) return rc;
-  size_t free_b = 0, total_b = 0;
-  AZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t by_mem = (static_cast<uint64_t>(free_b) + c->pool.blocks.bytes + c->pool.tables.bytes) * 8 / 10 / tree_bytes(p);
-  uint64_t n_trees = std::min<uint64_t>({n_games, resident, by_mem});
+  tm.lap("carveout+occupancy");
+  uint64_t n_trees = std::min<uint64_t>(n_games, resident);
   if (c->cfg.max_concurrent_games) n_trees = std::min<uint64_t>(n_trees, c->cfg.max_concurrent_games);
+  // cudaMemGetInfo was measured to take up to 70 ms now and then: ask only when the pool has to change
+  const bool pool_fits = c->pool_ready && c->pool.n_trees == n_trees && std::memcmp(&c->pool.p, &p, sizeof(p)) == 0;
+  if (!pool_fits) {
+    size_t free_b = 0, total_b = 0;
+    AZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t by_mem = (static_cast<uint64_t>(free_b) + c->pool.blocks.bytes + c->pool.tables.bytes) * 8 / 10 / tree_bytes(p);
+    n_trees = std::min<uint64_t>(n_trees, by_mem);
+  }
+  tm.lap("cudaMemGetInfo");
   if (n_trees == 0) return fail(AZB_ERR_CAPACITY, "not enough device memory for one tree");
   if (!c->pool_ready || c->pool.n_trees != n_trees || std::memcmp(&c->pool.p, &p, sizeof(p)) != 0) {
     rc = c->pool.alloc(p, static_cast<uint32_t>(n_trees));
@@ -734,6 +757,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   rc = c->gs.alloc(G, true);
   if (rc) return rc;
   GameBufs g = c->gs.g;
+  tm.lap("pool + game buffers");
   c->n_games = 0;
   c->n_samples = 0;
   if (c->cfg.evaluator >= AZB_EVAL_NNET && !c->net)
@@ -773,7 +797,9 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     if (rc) return rc;
   }
   AZB_CUDA(cudaEventRecord(e1));
+  tm.lap("launch");
   AZB_CUDA(cudaEventSynchronize(e1));
+  tm.lap("kernel wait");
   float ms = 0.0f;
   AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
@@ -784,6 +810,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   AZB_CUDA(cudaMemcpy(c->h_plies.data(), c->gs.plies.p, G * 4, cudaMemcpyDeviceToHost));
   AZB_CUDA(cudaMemcpy(h_err.data(), c->gs.error.p, G * 4, cudaMemcpyDeviceToHost));
   AZB_CUDA(cudaMemcpy(h_stats.data(), c->gs.stats.p, G * 32, cudaMemcpyDeviceToHost));
+  tm.lap("stats D2H");
   azb_selfplay_stats s{};
   for (uint64_t i = 0; i < G; ++i) {
     if (h_err[i]) return capacity_error(h_err[i]);
@@ -849,9 +876,12 @@ int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs,
   }
   AZB_CUDA(c->offsets.ensure(G * 8));
   AZB_CUDA(cudaMemcpy(c->offsets.p, off.data(), G * 8, cudaMemcpyHostToDevice));
-  AZB_CUDA(c->out_boards.ensure(N * 84 * 4));
-  AZB_CUDA(c->out_pis.ensure(N * 7 * 4));
-  AZB_CUDA(c->out_vs.ensure(N * 4));
+  // sized for the most samples G games can produce (42 plies x 2 symmetries), so that a step with a
+  // few more samples than the last one never pays a cudaFree + cudaMalloc
+  const uint64_t cap_n = std::max<uint64_t>(N, G * kMaxPlies * 2);
+  AZB_CUDA(c->out_boards.ensure(cap_n * 84 * 4));
+  AZB_CUDA(c->out_pis.ensure(cap_n * 7 * 4));
+  AZB_CUDA(c->out_vs.ensure(cap_n * 4));
   k_export_samples<<<static_cast<unsigned>(G), 128>>>(c->gs.g, c->offsets.as<uint64_t>(), c->cfg.quirks,
                                                       c->out_boards.as<float>(), c->out_pis.as<float>(),
                                                       c->out_vs.as<float>(), N);

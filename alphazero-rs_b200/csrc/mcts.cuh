@@ -325,18 +325,41 @@ __device__ __forceinline__ bool make_root(WarpTree& t, const SearchParams& p, BB
 }
 
 // unvisit of one path node, folded with the visit that preceded it (node.rs:77-92), and refresh
-// of the cached q.
-__device__ __forceinline__ uint32_t backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
-  uint64_t c = ld_counter(t, slot) + kVisit;
+// of the cached q — split into the loads + arithmetic (prepare) and the stores (commit), so that an
+// expansion can do the first half while its transposition probe is still in flight.
+struct BackupRegs {
+  uint32_t w_new, q_bits, nword, n_new;
+};
+__device__ __forceinline__ uint32_t* n_word_ptr(const WarpTree& t, uint32_t slot) {
+  return reinterpret_cast<uint32_t*>(t.blocks + (slot | 7u)) + ((slot & 7u) >> 1);
+}
+__device__ __forceinline__ BackupRegs backup_prepare(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
+  const uint32_t sh = (slot & 1u) * 16u;
+  const uint32_t old = *n_word_ptr(t, slot);
+#ifdef AZB_BACKUP_SEPARATE_N
+  uint64_t c = counter_pack(ld_w(t, slot), ld_n(t, slot)) + kVisit;
+#else
+  uint64_t c = counter_pack(ld_w(t, slot), old >> sh) + kVisit;
+#endif
   c = counter_unvisit(c, v, quirks);
-  *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(static_cast<uint32_t>(c >> 32), __float_as_uint(counter_q_fast(c)));
+  BackupRegs r;
+  r.w_new = static_cast<uint32_t>(c >> 32);
+  r.q_bits = __float_as_uint(counter_q_fast(c));
+  r.n_new = counter_n(c);
+  r.nword = (old & ~(0xFFFFu << sh)) | (r.n_new << sh);
+  return r;
+}
+__device__ __forceinline__ void backup_commit(const WarpTree& t, uint32_t slot, const BackupRegs& r) {
+  *reinterpret_cast<uint2*>(t.blocks + slot) = make_uint2(r.w_new, r.q_bits);
   // n[] is updated with a 32-bit read-modify-write: sub-word global stores knock the whole line
   // out of L1 (measured: profiles/r1_v2_selfplay_ncu.md), and the next simulation re-reads it.
   // No other lane touches this block's header during a backup (path nodes sit in distinct blocks).
-  uint32_t* word = reinterpret_cast<uint32_t*>(t.blocks + (slot | 7u)) + ((slot & 7u) >> 1);
-  const uint32_t sh = (slot & 1u) * 16u;
-  *word = (*word & ~(0xFFFFu << sh)) | (counter_n(c) << sh);
-  return counter_n(c);
+  *n_word_ptr(t, slot) = r.nword;
+}
+__device__ __forceinline__ uint32_t backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
+  const BackupRegs r = backup_prepare(t, slot, v, quirks);
+  backup_commit(t, slot, r);
+  return r.n_new;
 }
 
 // ---- search_iteration (async_mcts.rs:219-371) --------------------------------
@@ -462,7 +485,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
                                              Pending& pd, BB& leaf) {
   const float neg_inf = __uint_as_float(0xFF800000u);
   const uint32_t grp8 = lane & 24u, la = lane & 7u;  // first lane of my 8-lane group, my edge
-  const uint32_t pred_len = GENERIC ? 0u : t.pred_len;
+  const uint32_t pred_len = t.pred_len;  // (GENERIC: never read)
   t.pred_len = 0u;  // set again by the exits that leave a usable path behind
   uint32_t cur_slot = root_slot, cur_meta = root_meta;
   uint32_t par_n = 0u;  // N of the current node before this simulation's visit
@@ -479,7 +502,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
   if (cur_meta >= kMaxBlockId) {
     at_terminal(cur_meta);
   } else {
-    bool spec = !GENERIC && pred_len > 1u;
+    bool spec = !GENERIC && pred_len > 1u;  // GENERIC callers keep t.pred_len == 0
     BB pos = root;  // position of the level being resolved (spec: reloaded from its path entry)
     if (!spec) par_n = ld_n(t, root_slot);
     for (;;) {
@@ -488,7 +511,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       uint32_t nn, a, sl, ch_meta, blk, sa;
       float u;
       bool ok;
-      if (spec) {
+      if (!GENERIC && spec) {
         // ---- speculative prefix: which predicted levels still select the predicted edge? ----
         uint32_t base = 0u, stop;
         uint4 e;

@@ -216,9 +216,11 @@ def main():
     dev_ms = wall = 0.0
     tot = {}
     n_samples = 0
+    per_step = []
     for k in range(args.steps):
         st, w, ns = step(args.warmup + k)
         dev_ms += st["device_ms"]; wall += w; n_samples += ns
+        per_step.append((round(st["device_ms"], 2), round(1e3 * w, 2)))
         for key, v in st.items():
             if key not in ("device_ms", "blocks_used_max", "owners_max"):
                 tot[key] = tot.get(key, 0) + v
@@ -265,7 +267,8 @@ def main():
                      "traffic": traffic, "peak_source": peak_src, "kernel": "k_selfplay<UNIFORM>",
                      "launch_ms": dev_ms / args.steps},
         "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * wall_max / args.steps},
+                "ms_per_step": 1e3 * wall_max / args.steps,
+                "per_step_ms_device_and_wall": per_step},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
     }
