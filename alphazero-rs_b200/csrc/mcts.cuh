@@ -443,12 +443,14 @@ __device__ __forceinline__ bool root_needs_eval(const WarpTree& t, uint32_t root
 // before this simulation's visit is `npar`: lane (8g + a) returns edge a's slot words `w`, visit
 // count `nn` and u = q + (cpuct*P*sq)/(1 + n) (-inf when the lane takes no part), sq = sqrt(N_parent +
 // 1e-6) with the parent's N read after this simulation's visit().
-template <bool GENERIC>
-__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, float sq,
-                                           bool use, uint32_t la, uint4& w, uint32_t& nn, float& u, bool& ok) {
+__device__ __forceinline__ void load_edges(const WarpTree& t, uint32_t blk, uint32_t la, uint4& w, uint32_t& nn) {
   const uint4* bp = t.blocks + static_cast<size_t>(blk) * 8u;
   w = bp[la];
   nn = reinterpret_cast<const uint16_t*>(bp + 7)[la];
+}
+template <bool GENERIC>
+__device__ __forceinline__ void score_edges(const WarpTree& t, float cpuct_f, float sq, bool use, uint32_t la,
+                                            const uint4& w, uint32_t& nn, float& u, bool& ok) {
   ok = use && la < 7u && w.w != kMetaInvalid;
   float q = __uint_as_float(w.y);
   if (__any_sync(kFull, ok && w.w == kMetaLink)) {  // rare; kept off the common instruction stream
@@ -461,6 +463,12 @@ __device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uin
   const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
   const float ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
   u = ok ? __fadd_rn(q, ex) : __uint_as_float(0xFF800000u);
+}
+template <bool GENERIC>
+__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, float sq,
+                                           bool use, uint32_t la, uint4& w, uint32_t& nn, float& u, bool& ok) {
+  load_edges(t, blk, la, w, nn);
+  score_edges<GENERIC>(t, cpuct_f, sq, use, la, w, nn, u, ok);
 }
 
 // One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
