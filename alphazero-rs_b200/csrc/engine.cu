@@ -195,6 +195,9 @@ struct azb_nnet {
   DevBuf d_wtiles;                     // bf16 path: kTcWeightCopies x [2R][18] pre-swizzled 16-KB weight tiles
   size_t wtile_copy_bytes = 0;
   DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
+  CUtensorMap act_map[3];              // the same buffers as 4-D tensors [pos][6][7][128] for TMA im2col loads
+  void* act_map_ptr[3] = {nullptr, nullptr, nullptr};
+  size_t act_map_bytes[3] = {0, 0, 0};
   DevBuf d_feat, d_states, d_pi, d_v;  // azb_nnet_predict staging
   static uint16_t bf16_rne(float f) {
     uint32_t u;
@@ -230,12 +233,39 @@ struct azb_nnet {
         AZB_CUDA(cudaMemcpy(d_wtiles.as<uint8_t>() + c * wtile_copy_bytes, tiles.data(), wtile_copy_bytes, cudaMemcpyHostToDevice));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
     }
     return AZB_OK;
   }
 };
 
 namespace {
+// TMA descriptor of an activation buffer for im2col loads: NHWC tensor {C=128, W=7, H=6, N}, 3x3 window
+// with padding 1 (pixel box corners -1 / -1), 64 channels x 128 pixels per copy, SWIZZLE_128B.
+int encode_act_map(CUtensorMap* map, void* ptr, size_t bytes) {
+  typedef CUresult (*EncodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeIm2col encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    AZB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeIm2col is not available in this driver");
+    encode = reinterpret_cast<EncodeIm2col>(fn);
+  }
+  const cuuint64_t n_pos = bytes / (static_cast<size_t>(kCells) * kNetC * 2);
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kNetC), 7, 6, n_pos};
+  const cuuint64_t strides[3] = {kNetC * 2, 7 * kNetC * 2, static_cast<cuuint64_t>(kCells) * kNetC * 2};  // bytes: W, H, N
+  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};  // {W, H}: padding 1, 3x3 window (CUTLASS fprop: -pad, pad - (R-1))
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, lower, upper, kTcBlockK, kTcTileM, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeIm2col failed");
+  return AZB_OK;
+}
+
 // One dense forward pass over the first *d_count (or max_batch) positions.
 int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
                  float* d_v, cudaStream_t st) {
@@ -250,6 +280,13 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   // bf16 tensor-core path: stem -> 2R x conv3x3 (tcgen05) -> heads
   const size_t act_bytes = static_cast<size_t>(max_batch) * kCells * kNetC * 2;
   for (auto& b : net->d_act) AZB_CUDA(b.ensure(act_bytes));
+  for (int i = 0; i < 3; ++i)
+    if (net->act_map_ptr[i] != net->d_act[i].p || net->act_map_bytes[i] != net->d_act[i].bytes) {
+      const int rc = encode_act_map(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
+      if (rc) return rc;
+      net->act_map_ptr[i] = net->d_act[i].p;
+      net->act_map_bytes[i] = net->d_act[i].bytes;
+    }
   __nv_bfloat16* x = net->d_act[0].as<__nv_bfloat16>();
   __nv_bfloat16* y = net->d_act[1].as<__nv_bfloat16>();
   __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
@@ -283,7 +320,29 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const bool clustered = !no_cluster && max_clusters > 0 && tiles >= 2u * kTcCluster;
   const unsigned grid = clustered ? std::min<uint32_t>((tiles + kTcCluster - 1) / kTcCluster, static_cast<uint32_t>(max_clusters)) * kTcCluster
                                   : std::min<uint32_t>(tiles, 148u);
+  // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
+  // single-CTA kernel with streamed weight tiles.
+  static const bool use_pair = !(std::getenv("AZB200_TC_PAIR") && std::getenv("AZB200_TC_PAIR")[0] == '0');
+  const uint32_t pair_tiles = (max_batch * kCells + kT2PairRows - 1) / kT2PairRows;
+  static int max_pairs = -1;  // co-resident CTA pairs (one CTA per SM; a GPC with an odd SM count leaves one out)
+  if (max_pairs < 0) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(148u);
+    qc.blockDim = dim3(kTcThreads);
+    qc.dynamicSmemBytes = kT2SmemBytes;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc2, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_pairs = n;
+    if (std::getenv("AZB200_TIMING")) std::fprintf(stderr, "[azb200 nnet] co-resident CTA pairs: %d\n", n);
+  }
   auto launch_conv = [&](const ConvTcArgs& a) -> cudaError_t {
+    if (use_pair && max_pairs > 0) {
+      int mi = 0;
+      while (mi < 2 && net->d_act[mi].p != a.in) ++mi;
+      k_conv3x3_tc2<<<2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)), kTcThreads, kT2SmemBytes, st>>>(
+          a, net->act_map[mi]);
+      return cudaGetLastError();
+    }
     if (!clustered) {
       k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
       return cudaGetLastError();
@@ -302,8 +361,14 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_conv3x3_tc<kTcCluster>, a);
   };
+  static unsigned long long* d_dbg = nullptr;  // AZB200_TC_DEBUG=1: role timers of the first conv launch
+  if (!d_dbg && std::getenv("AZB200_TC_DEBUG")) {
+    AZB_CUDA(cudaMalloc(&d_dbg, 32 * 8));
+    AZB_CUDA(cudaMemset(d_dbg, 0, 32 * 8));
+  }
   for (int blk = 0; blk < net->L.R; ++blk) {
     ConvTcArgs a{};
+    a.dbg = blk == 0 ? d_dbg : nullptr;
     a.count = d_count;
     a.max_batch = max_batch;
     a.in = x; a.residual = nullptr; a.out = y;
@@ -312,6 +377,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     a.bias = prm + net->L.tower_b + (2 * blk) * kNetC;
     AZB_CUDA(launch_conv(a));
     a.in = y; a.residual = x; a.out = z;
+    a.dbg = nullptr;
     a.w_tiles += static_cast<size_t>(kTcKBlocks) * kTcTileBytes;
     a.bias += kNetC;
     AZB_CUDA(launch_conv(a));
@@ -319,6 +385,19 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   }
   k_heads_bf16<<<std::min<uint32_t>(max_batch, 148u * 8u), 128, 0, st>>>(prm, net->L, x, d_count, max_batch, d_pi, d_v);
   AZB_CUDA(cudaGetLastError());
+  if (d_dbg) {
+    unsigned long long h[32];
+    AZB_CUDA(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    static int printed = 0;
+    if (printed++ == 4) {
+      const char* names[16] = {"producer wait empty", "producer TMA issue", "epilogue wait acc_full", "epilogue work", "mma wait full",
+                               "mma wait acc_empty", "mma fences", "mma issue (4 MMAs)", "mma commit", "mma wait weights",
+                               "relay fence+arrive", "kernel cycles", "tile iterations", "", "", ""};
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 13; ++k)
+          if (h[r * 16 + k]) std::fprintf(stderr, "[azb200 tc2 rank %d] %-24s %llu\n", r, names[k], h[r * 16 + k]);
+    }
+  }
   return AZB_OK;
 }
 

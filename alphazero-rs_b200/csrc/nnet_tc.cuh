@@ -15,6 +15,7 @@
 //   9 weight loader + TMEM allocator.  Three pipelines: smem full/empty (4 stages), TMEM full/empty.
 // * Epilogue fused: + bias (folded BN), + residual, ReLU, fp32 -> bf16, straight to HBM.
 #pragma once
+#include <cuda.h>  // CUtensorMap (the encoder itself is fetched at run time with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -146,6 +147,7 @@ struct ConvTcArgs {
   const float* bias;              // [128]
   const uint32_t* count;          // positions this round (device), or nullptr
   uint32_t max_batch;
+  unsigned long long* dbg;        // diagnostic (AZB200_TC_DEBUG=1): per-role cycle counters of CTA pair 0, or nullptr
 };
 
 // CL = CTAs per cluster.  With CL > 1 the CTAs of a cluster walk their M tiles in lock-step and share
@@ -343,6 +345,259 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ================================================================================================
+// CTA-pair version: tcgen05.mma.cta_group::2 (M256 N128 K16), the layer's weights RESIDENT in shared
+// memory, and the A operand gathered by TMA in IM2COL mode.
+//
+// Why: the single-CTA kernel above is bound by what each SM pulls through its load/store unit and its
+// shared-memory port per k-block (A gathered with 16-byte cp.async at <= ~32 B/clk/SM, a streamed 16-KB
+// weight tile, 64 KB read by the SS-mode MMAs).  Here a CTA pair (the two SMs of a TPC, cluster of 2)
+// computes a 256-row tile together:
+//  * each CTA holds HALF of the layer's weights (64 of the 128 output channels, all 18 k-blocks =
+//    144 KB), loaded ONCE per launch with bulk TMA; the pair's tensor cores exchange the halves, so per
+//    MMA an SM reads 4 KB (A) + 2 KB (B) of shared memory instead of 8 KB, and no weight tile is ever
+//    streamed again;
+//  * the activations are a 4-D tensor [position][6][7][128] to the TMA unit; ONE
+//    cp.async.bulk.tensor.4d.im2col per k-block and CTA delivers the 128 consecutive (position, cell)
+//    rows of the CTA's sub-tile, shifted by the tap (dy, dx), zero-filled outside the 6x7 board, 64
+//    channels wide, already in the SWIZZLE_128B layout the UMMA descriptor expects — no gather warps,
+//    no address arithmetic, no generic-proxy writes (so no proxy fence), and both CTAs' copies
+//    complete on the LEADER's mbarrier (.cta_group::2), so the pair needs no relay either;
+//  * accumulators: 2 x 128 TMEM columns in each CTA's own TMEM (its 128 rows).
+// Roles (both CTAs unless noted): warps 0-7 epilogue (accumulator-empty arrivals go to the leader);
+// warp 8 lane 0 of the leader (cluster rank 0) issues every MMA of the pair and the multicast commits;
+// warp 9: TMEM allocation (cta_group::2: the same warp in both CTAs), then lane 0 preloads the weights
+// and is the TMA producer.
+// ================================================================================================
+#ifndef AZB_T2_STAGES
+#define AZB_T2_STAGES 5
+#endif
+constexpr int kT2Stages = AZB_T2_STAGES;
+constexpr uint32_t kT2WTile = 64 * 128;                    // one k-block of the CTA's 64 output channels
+constexpr uint32_t kT2WBytes = kTcKBlocks * kT2WTile;      // 147456
+constexpr uint32_t kT2SmemBytes = kT2WBytes + kT2Stages * kTcTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kT2PairRows = 2 * kTcTileM;
+constexpr uint32_t kIdescBf16M256N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+  return remote;
+}
+// arrive on the barrier at the same offset in CTA `cta`.  Default semantics (release at CTA scope), as
+// CUTLASS's umma_arrive_2x1SM_sm0: a cluster-scope release was measured at ~900 cycles per arrival.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(local_bar, cta)) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// 128 consecutive base pixels starting at (w, h, n) of the bounding box, tap offset (off_w, off_h),
+// channels [c, c + 64): 16 KB into `dst`; completes on `mbar_cluster` (may live in the pair's leader).
+__device__ __forceinline__ void tma_im2col_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t mbar_cluster, int c, int w, int h,
+                                                int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
+  auto w_tile = [&](int kb) { return base + kb * kT2WTile; };
+  auto stage_a = [&](int s) { return base + kT2WBytes + s * kTcTileBytes; };
+  const uint32_t bars = base + kT2WBytes + kT2Stages * kTcTileBytes;
+  auto bar_full = [&](int s) { return bars + 8u * s; };              // leader: 1 arrival (its expect_tx) + 2 x 16 KB of TMA bytes
+  auto bar_empty = [&](int s) { return bars + 80u + 8u * s; };       // 1 arrival: the pair's MMAs have read the stage
+  auto bar_acc_full = [&](int a) { return bars + 120u + 8u * a; };   // 1 arrival: the tile's MMAs are done
+  auto bar_acc_empty = [&](int a) { return bars + 136u + 8u * a; };  // leader: 512 arrivals (both CTAs' 8 epilogue warps)
+  const uint32_t bar_w_full = bars + 152u;
+  const uint32_t bar_w_peer = bars + 160u;                           // leader: the peer's weights are resident
+  const uint32_t tmem_slot = bars + 168u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
+  const uint32_t rows = n_pos * kCells;
+  const uint32_t n_tiles = (rows + kT2PairRows - 1) / kT2PairRows;  // pair tiles of 256 rows
+  const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;  // same in both CTAs of a pair
+  auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kT2PairRows + rank * kTcTileM; };
+  const bool dbg_on = g.dbg != nullptr && blockIdx.x < 2;
+  unsigned long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
+  long long dbg_c = 0;
+#define AZB_DBG_T0() do { if (dbg_on) dbg_c = clock64(); } while (0)
+#define AZB_DBG_ADD(k) do { if (dbg_on) { const long long n_ = clock64(); dbg_t[k] += n_ - dbg_c; dbg_c = n_; } } while (0)
+  const long long dbg_start = dbg_on ? clock64() : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kT2Stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full(a), 1);
+      mbar_init(bar_acc_empty(a), 512);
+    }
+    mbar_init(bar_w_full, 1);
+    mbar_init(bar_w_peer, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
+  }
+  if (warp == 9) {  // 2 accumulator stages x 128 fp32 columns, in both CTAs' TMEM
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely / multicasts into them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 8) {
+    // ===== epilogue, 8 warps: own TMEM lanes (the CTA's 128 rows) -> bias / residual / ReLU -> bf16 -> HBM.
+    // A warp reads the TMEM lane quarter warp % 4; warps 0-3 take output channels 0-63, warps 4-7 64-127 =====
+    const int q = warp & 3, half = warp >> 2;
+    for (uint32_t ti = 0; ti < iters; ++ti) {
+      const uint32_t a = ti & 1u;
+      AZB_DBG_T0();
+      mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
+      AZB_DBG_ADD(0);
+      tc_fence_after();
+      const uint32_t m = row0_of(ti) + q * 32 + lane;
+      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + ch * 32u, acc);
+        if (m < rows) {
+          const float* bias = g.bias + ch * 32;
+          uint32_t packed[16];
+          uint4 res[4];
+          if (g.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + ch * 32);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) res[jj] = rp[jj];
+          }
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            float x0 = __uint_as_float(acc[2 * jj]) + bias[2 * jj];
+            float x1 = __uint_as_float(acc[2 * jj + 1]) + bias[2 * jj + 1];
+            if (g.residual) {
+              const uint32_t rw = reinterpret_cast<const uint32_t*>(res)[jj];
+              x0 += __uint_as_float(rw << 16);
+              x1 += __uint_as_float(rw & 0xFFFF0000u);
+            }
+            x0 = fmaxf(x0, 0.0f);
+            x1 = fmaxf(x1, 0.0f);
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
+            packed[jj] = *reinterpret_cast<const uint32_t*>(&p2);
+          }
+          uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + ch * 32);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) op[jj] = make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(bar_acc_empty(a), 0u);  // the leader issues the MMAs that overwrite accumulator a
+      AZB_DBG_ADD(1);
+    }
+    if (dbg_on && threadIdx.x == 128) { g.dbg[rank * 16 + 2] = dbg_t[0]; g.dbg[rank * 16 + 3] = dbg_t[1]; }
+  } else if (warp == 8) {
+    if (lane == 0 && iters > 0) {
+      AZB_DBG_T0();
+      mbar_wait(bar_w_full, 0u);  // my half of the weights is resident
+      if (rank == 1) {
+        mbar_arrive_cluster(bar_w_peer, 0u);
+      } else {
+        // ===== MMA issuer of the pair: ONE thread, nothing but waits, MMAs and commits =====
+        mbar_wait(bar_w_peer, 0u);
+        AZB_DBG_ADD(5);
+        uint32_t it = 0;
+        for (uint32_t ti = 0; ti < iters; ++ti) {
+          const uint32_t a = ti & 1u;
+          AZB_DBG_T0();
+          mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+          AZB_DBG_ADD(1);
+          for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
+            const int s = it % kT2Stages;
+            AZB_DBG_T0();
+            mbar_wait(bar_full(s), (it / kT2Stages) & 1u);
+            AZB_DBG_ADD(0);
+            tc_fence_after();
+            AZB_DBG_ADD(2);
+            const uint64_t ad = umma_desc_sw128(stage_a(s)), bd = umma_desc_sw128(w_tile(kb));
+#pragma unroll
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              umma2_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
+            AZB_DBG_ADD(3);
+            umma2_commit_multicast(bar_empty(s), 3u);  // frees the stage in both CTAs
+            if (kb == kTcKBlocks - 1) umma2_commit_multicast(bar_acc_full(a), 3u);
+            AZB_DBG_ADD(4);
+          }
+        }
+        if (dbg_on) for (int k = 0; k < 6; ++k) g.dbg[4 + k] = dbg_t[k];
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0 && iters > 0) {
+      // ===== weight preload: this CTA's 64 output channels of all 18 k-blocks, once per launch =====
+      mbar_arrive_expect_tx(bar_w_full, kT2WBytes);
+      for (int kb = 0; kb < kTcKBlocks; ++kb)
+        tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w_full);
+      // ===== A producer: one im2col TMA per k-block for this CTA's 128 rows =====
+      uint32_t it = 0;
+      for (uint32_t i = 0; i < iters; ++i) {
+        const uint32_t row0 = row0_of(i);
+        const int n = static_cast<int>(row0 / kCells), cell = static_cast<int>(row0 % kCells);
+        const int h = cell / 7 - 1, w = cell % 7 - 1;  // base pixel in bounding-box coordinates (lower corner -1)
+        for (int kb = 0; kb < kTcKBlocks; ++kb, ++it) {
+          const int s = it % kT2Stages;
+          AZB_DBG_T0();
+          mbar_wait(bar_empty(s), ((it / kT2Stages) & 1u) ^ 1u);
+          AZB_DBG_ADD(0);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2u * kTcTileBytes);  // both CTAs' copies land on this barrier
+          const int tap = kb >> 1;
+          tma_im2col_pair(stage_a(s), &tmap_in, map_to_cta(bar_full(s), 0u), (kb & 1) * kTcBlockK, w, h, n,
+                          static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
+          AZB_DBG_ADD(1);
+        }
+      }
+      if (dbg_on) { g.dbg[rank * 16 + 0] = dbg_t[0]; g.dbg[rank * 16 + 1] = dbg_t[1]; }
+    }
+    __syncwarp();
+  }
+
+  if (dbg_on && threadIdx.x == 0) { g.dbg[rank * 16 + 11] = clock64() - dbg_start; g.dbg[rank * 16 + 12] = iters; }
+#undef AZB_DBG_T0
+#undef AZB_DBG_ADD
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair's MMAs / remote arrivals may still be in flight
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 // Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, 8 channels).
