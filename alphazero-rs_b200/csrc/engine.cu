@@ -195,6 +195,7 @@ struct azb_nnet {
   DevBuf d_wtiles;                     // bf16 path: kTcWeightCopies x [2R][18] pre-swizzled 16-KB weight tiles
   size_t wtile_copy_bytes = 0;
   DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
+  HeadConvW head_w{};                  // bf16 path: 1x1 head convolutions as a kernel parameter (constant bank)
   CUtensorMap act_map[3];              // the same buffers as 4-D tensors [pos][6][7][128] for TMA im2col loads
   void* act_map_ptr[3] = {nullptr, nullptr, nullptr};
   size_t act_map_bytes[3] = {0, 0, 0};
@@ -234,6 +235,15 @@ struct azb_nnet {
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+      for (int ci = 0; ci < kNetC; ++ci) {
+        head_w.w[ci][0] = h_params[L.pol_w + ci * 2 + 0];
+        head_w.w[ci][1] = h_params[L.pol_w + ci * 2 + 1];
+        head_w.w[ci][2] = h_params[L.val_w + ci];
+      }
+      head_w.b[0] = h_params[L.pol_b + 0];
+      head_w.b[1] = h_params[L.pol_b + 1];
+      head_w.b[2] = h_params[L.val_b];
     }
     return AZB_OK;
   }
@@ -292,7 +302,8 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
   const float* prm = net->d_params.as<float>();
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
-  k_stem_bf16<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(prm, net->L, d_states, d_count, max_batch, x);
+  k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148u * 2u)), 256, kStemSmemBytes, st>>>(
+      prm, net->L, d_states, d_count, max_batch, x);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
   // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can
@@ -383,7 +394,8 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     AZB_CUDA(launch_conv(a));
     std::swap(x, z);
   }
-  k_heads_bf16<<<std::min<uint32_t>(max_batch, 148u * 8u), 128, 0, st>>>(prm, net->L, x, d_count, max_batch, d_pi, d_v);
+  k_heads_bf16<<<std::min<uint32_t>((max_batch + kHeadPos - 1) / kHeadPos, 148u * 8u), 256, 0, st>>>(prm, net->L, net->head_w, x, d_count,
+                                                                                                      max_batch, d_pi, d_v);
   AZB_CUDA(cudaGetLastError());
   if (d_dbg) {
     unsigned long long h[32];

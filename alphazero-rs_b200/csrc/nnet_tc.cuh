@@ -600,62 +600,137 @@ k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
-// Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  One thread per (row, 8 channels).
-__global__ void k_stem_bf16(const float* __restrict__ prm, NetLayout L, const uint4* __restrict__ states,
-                            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
+// Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  The two input planes are
+// binary, so a window row (3 cells x 2 planes = 6 bits) selects one of 64 precomputed partial sums:
+// out = ReLU(bias + T[0][bits of row y-1] + T[1][bits of row y] + T[2][bits of row y+1]).  Each
+// persistent CTA builds the 3 x 64 x 128 fp32 table (96 KB of shared memory) from the 18 x 128 stem
+// weights once (entry = its set taps added in (dx, plane) order), then every thread produces 8
+// channels of one (position, cell) row per step: HBM-write bound (256 B per row).
+constexpr uint32_t kStemSmemBytes = 3 * 64 * kNetC * 4;
+__global__ void __launch_bounds__(256)
+k_stem_bf16(const float* __restrict__ prm, NetLayout L, const uint4* __restrict__ states,
+            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float stem_tab[];  // [3][64][128]
+  for (uint32_t e = threadIdx.x; e < 3u * 64u * kNetC; e += blockDim.x) {
+    const uint32_t c = e % kNetC, bits = (e / kNetC) % 64u, dyi = e / (kNetC * 64u);
+    float acc = 0.0f;
+    for (uint32_t dxi = 0; dxi < 3u; ++dxi)
+      for (uint32_t pl = 0; pl < 2u; ++pl)
+        if ((bits >> (dxi + 3u * pl)) & 1u) acc += prm[L.stem_w + ((dyi * 3u + dxi) * 2u + pl) * kNetC + c];
+    stem_tab[e] = acc;
+  }
+  __syncthreads();
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(n_pos) * kCells * (kNetC / 8);
-  if (idx >= total) return;
-  const uint32_t cg = idx % (kNetC / 8);
-  const uint32_t m = idx / (kNetC / 8), pos = m / kCells, cell = m % kCells;
-  const int r = cell / 7, c = cell % 7;
-  const uint4 st = states[pos];
-  const uint64_t cur = (static_cast<uint64_t>(st.y) << 32) | st.x, opp = (static_cast<uint64_t>(st.w) << 32) | st.z;
-  float acc[8];
-  {
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t cg = idx % (kNetC / 8);
+    const uint32_t m = static_cast<uint32_t>(idx / (kNetC / 8)), pos = m / kCells, cell = m % kCells;
+    const int r = cell / 7, c = cell % 7;
+    const uint4 st = states[pos];
+    const uint64_t cur = (static_cast<uint64_t>(st.y) << 32) | st.x, opp = (static_cast<uint64_t>(st.w) << 32) | st.z;
     const float4 b0 = *reinterpret_cast<const float4*>(prm + L.stem_b + cg * 8);
     const float4 b1 = *reinterpret_cast<const float4*>(prm + L.stem_b + cg * 8 + 4);
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-  }
-  for (int tap = 0; tap < 9; ++tap) {  // accumulation order: tap-major, plane-minor (as the fp32 path)
-    const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
-    if (rr < 0 || rr >= 6 || cc < 0 || cc >= 7) continue;
-    const int b = rr * 7 + cc;
-    for (int pl = 0; pl < 2; ++pl) {
-      if (!(((pl ? opp : cur) >> b) & 1ull)) continue;
-      const float* w = prm + L.stem_w + (tap * 2 + pl) * kNetC + cg * 8;
-      const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
-      acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w; acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
-    }
-  }
-  uint32_t pk[4];
+    float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[2 * k], 0.0f), fmaxf(acc[2 * k + 1], 0.0f));
-    pk[k] = *reinterpret_cast<const uint32_t*>(&p2);
+    for (int dyi = 0; dyi < 3; ++dyi) {
+      const int rr = r + dyi - 1;
+      if (rr < 0 || rr >= 6) continue;  // a window row off the board contributes nothing
+      // bits c-1, c, c+1 of the board row (zero beyond the edges) for both planes: index = cur3 + 8 * opp3
+      const uint32_t cur3 = ((static_cast<uint32_t>(cur >> (rr * 7)) & 0x7Fu) << 1 >> c) & 7u;
+      const uint32_t opp3 = ((static_cast<uint32_t>(opp >> (rr * 7)) & 0x7Fu) << 1 >> c) & 7u;
+      const float* t = stem_tab + (static_cast<uint32_t>(dyi) * 64u + cur3 + 8u * opp3) * kNetC + cg * 8;
+      const float4 t0 = *reinterpret_cast<const float4*>(t), t1 = *reinterpret_cast<const float4*>(t + 4);
+      acc[0] += t0.x; acc[1] += t0.y; acc[2] += t0.z; acc[3] += t0.w; acc[4] += t1.x; acc[5] += t1.y; acc[6] += t1.z; acc[7] += t1.w;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[2 * k], 0.0f), fmaxf(acc[2 * k + 1], 0.0f));
+      pk[k] = *reinterpret_cast<const uint32_t*>(&p2);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-// Heads from the bf16 tower output: one CTA (128 threads) per position.  Rows are padded to 129
-// floats so that threads working on different cells hit different banks.
-__global__ void __launch_bounds__(128)
-k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __nv_bfloat16* __restrict__ act,
-             const uint32_t* __restrict__ count, uint32_t max_batch, float* __restrict__ pi_out, float* __restrict__ v_out) {
-  __shared__ float a0[kCells][kNetC + 1];
-  __shared__ float scratch[256];
+// Heads from the bf16 tower output.  A CTA of 256 threads takes 6 positions per step: thread = one
+// (position, cell) row computes the three 1x1-convolution outputs of its cell (policy planes 0/1 and
+// the value plane) straight from its 256 bytes of bf16 activations, the 3 x 128 weights coming from
+// the kernel-parameter constant bank; the small FC layers, softmax and tanh follow from shared memory.
+// Every output is accumulated in exactly the order of heads_from_smem (the fp32 path's head), so both
+// paths produce the same head arithmetic on the same tower values.
+struct HeadConvW {
+  float w[kNetC][3];  // [in channel][policy plane 0, policy plane 1, value plane]
+  float b[3];
+};
+constexpr int kHeadPos = 6;  // positions per CTA step: 6 x 42 = 252 rows on 256 threads
+__global__ void __launch_bounds__(256)
+k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __grid_constant__ HeadConvW hw,
+             const __nv_bfloat16* __restrict__ act, const uint32_t* __restrict__ count, uint32_t max_batch,
+             float* __restrict__ pi_out, float* __restrict__ v_out) {
+  __shared__ float pol[kHeadPos][84];   // plane*42 + cell
+  __shared__ float val[kHeadPos][42];
+  __shared__ float h1[kHeadPos][64];
+  __shared__ float logit[kHeadPos][8];
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
-  for (uint32_t pos = blockIdx.x; pos < n_pos; pos += gridDim.x) {
+  const int tid = threadIdx.x;
+  for (uint32_t p0 = blockIdx.x * kHeadPos; p0 < n_pos; p0 += gridDim.x * kHeadPos) {
     __syncthreads();
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(act + static_cast<size_t>(pos) * kCells * kNetC);
-    for (int i = threadIdx.x; i < kCells * kNetC / 2; i += 128) {
-      const uint32_t wd = src[i];
-      a0[(2 * i) / kNetC][(2 * i) % kNetC] = __uint_as_float(wd << 16);
-      a0[(2 * i) / kNetC][(2 * i) % kNetC + 1] = __uint_as_float(wd & 0xFFFF0000u);
+    const int lp = tid / kCells, cell = tid % kCells;
+    if (tid < kHeadPos * kCells && p0 + lp < n_pos) {
+      const uint4* src = reinterpret_cast<const uint4*>(act + (static_cast<size_t>(p0 + lp) * kCells + cell) * kNetC);
+      float s0 = hw.b[0], s1 = hw.b[1], s2 = hw.b[2];
+#pragma unroll
+      for (int v8 = 0; v8 < kNetC / 8; ++v8) {
+        const uint4 x = src[v8];
+        const uint32_t wd[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = __uint_as_float(wd[k] << 16), hi = __uint_as_float(wd[k] & 0xFFFF0000u);
+          const int ci = v8 * 8 + 2 * k;
+          s0 = fmaf(lo, hw.w[ci][0], s0); s1 = fmaf(lo, hw.w[ci][1], s1); s2 = fmaf(lo, hw.w[ci][2], s2);
+          s0 = fmaf(hi, hw.w[ci + 1][0], s0); s1 = fmaf(hi, hw.w[ci + 1][1], s1); s2 = fmaf(hi, hw.w[ci + 1][2], s2);
+        }
+      }
+      pol[lp][cell] = fmaxf(s0, 0.0f);
+      pol[lp][42 + cell] = fmaxf(s1, 0.0f);
+      val[lp][cell] = fmaxf(s2, 0.0f);
     }
     __syncthreads();
-    heads_from_smem<kNetC + 1>(prm, L, a0, scratch, pi_out + static_cast<size_t>(pos) * 8u, v_out + pos);
+    // FC(84 -> 7) of the policy head: 6 x 7 outputs; FC(42 -> 64) of the value head: 6 x 64 outputs
+    for (int o = tid; o < kHeadPos * (7 + 64); o += 256) {
+      const int q = o / (7 + 64), j = o % (7 + 64);
+      if (p0 + q >= n_pos) continue;
+      if (j < 7) {
+        float s = prm[L.pol_fc_b + j];
+        for (int i = 0; i < 84; ++i) s = fmaf(pol[q][i], prm[L.pol_fc_w + i * 7 + j], s);
+        logit[q][j] = s;
+      } else {
+        const int jj = j - 7;
+        float s = prm[L.val_fc1_b + jj];
+        for (int i = 0; i < 42; ++i) s = fmaf(val[q][i], prm[L.val_fc1_w + i * 64 + jj], s);
+        h1[q][jj] = fmaxf(s, 0.0f);
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * kHeadPos) {
+      const int q = tid >> 1;
+      if (p0 + q < n_pos) {
+        if (tid & 1) {
+          float s = prm[L.val_fc2_b];
+          for (int j = 0; j < 64; ++j) s = fmaf(h1[q][j], prm[L.val_fc2_w + j], s);
+          v_out[p0 + q] = tanhf(s);
+        } else {
+          float m = logit[q][0];
+          for (int a = 1; a < 7; ++a) m = fmaxf(m, logit[q][a]);
+          float e[7], sum = 0.0f;
+          for (int a = 0; a < 7; ++a) { e[a] = expf(logit[q][a] - m); sum += e[a]; }
+          float* po = pi_out + static_cast<size_t>(p0 + q) * 8u;
+          for (int a = 0; a < 7; ++a) po[a] = e[a] / sum;
+          po[7] = 0.0f;
+        }
+      }
+    }
   }
 }
 
