@@ -195,6 +195,7 @@ struct azb_nnet {
   DevBuf d_wtiles;                     // bf16 path: kTcWeightCopies x [2R][18] pre-swizzled 16-KB weight tiles
   size_t wtile_copy_bytes = 0;
   DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
+  DevBuf d_stem_tab;                   // bf16 path: the stem's 3 x 64 x 128 partial-sum table (k_stem_bf16)
   HeadConvW head_w{};                  // bf16 path: 1x1 head convolutions as a kernel parameter (constant bank)
   CUtensorMap act_map[3];              // the same buffers as 4-D tensors [pos][6][7][128] for TMA im2col loads
   void* act_map_ptr[3] = {nullptr, nullptr, nullptr};
@@ -236,6 +237,12 @@ struct azb_nnet {
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+      {
+        std::vector<float> tab(3 * 64 * kNetC);
+        stem_table_build(h_params.data(), L, tab.data());
+        AZB_CUDA(d_stem_tab.ensure(kStemSmemBytes));
+        AZB_CUDA(cudaMemcpy(d_stem_tab.p, tab.data(), kStemSmemBytes, cudaMemcpyHostToDevice));
+      }
       for (int ci = 0; ci < kNetC; ++ci) {
         head_w.w[ci][0] = h_params[L.pol_w + ci * 2 + 0];
         head_w.w[ci][1] = h_params[L.pol_w + ci * 2 + 1];
@@ -303,7 +310,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const float* prm = net->d_params.as<float>();
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148u * 2u)), 256, kStemSmemBytes, st>>>(
-      prm, net->L, d_states, d_count, max_batch, x);
+      prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
   // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can

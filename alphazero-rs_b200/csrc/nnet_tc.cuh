@@ -603,22 +603,27 @@ k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
 // Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  The two input planes are
 // binary, so a window row (3 cells x 2 planes = 6 bits) selects one of 64 precomputed partial sums:
 // out = ReLU(bias + T[0][bits of row y-1] + T[1][bits of row y] + T[2][bits of row y+1]).  Each
-// persistent CTA builds the 3 x 64 x 128 fp32 table (96 KB of shared memory) from the 18 x 128 stem
-// weights once (entry = its set taps added in (dx, plane) order), then every thread produces 8
-// channels of one (position, cell) row per step: HBM-write bound (256 B per row).
+// persistent CTA copies the 3 x 64 x 128 fp32 table (96 KB, built from the 18 x 128 stem weights when
+// the parameters are uploaded) into shared memory, then every thread produces 8 channels of one
+// (position, cell) row per step: HBM-write bound (256 B per row).
 constexpr uint32_t kStemSmemBytes = 3 * 64 * kNetC * 4;
-__global__ void __launch_bounds__(256)
-k_stem_bf16(const float* __restrict__ prm, NetLayout L, const uint4* __restrict__ states,
-            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float stem_tab[];  // [3][64][128]
-  for (uint32_t e = threadIdx.x; e < 3u * 64u * kNetC; e += blockDim.x) {
+// Host side of the table (azb_nnet::upload): entry [dyi][cur3 + 8*opp3][c] = its set taps added in (dx, plane) order.
+inline void stem_table_build(const float* prm, const NetLayout& L, float* tab /* [3][64][128] */) {
+  for (uint32_t e = 0; e < 3u * 64u * kNetC; ++e) {
     const uint32_t c = e % kNetC, bits = (e / kNetC) % 64u, dyi = e / (kNetC * 64u);
     float acc = 0.0f;
     for (uint32_t dxi = 0; dxi < 3u; ++dxi)
       for (uint32_t pl = 0; pl < 2u; ++pl)
         if ((bits >> (dxi + 3u * pl)) & 1u) acc += prm[L.stem_w + ((dyi * 3u + dxi) * 2u + pl) * kNetC + c];
-    stem_tab[e] = acc;
+    tab[e] = acc;
   }
+}
+__global__ void __launch_bounds__(256)
+k_stem_bf16(const float* __restrict__ prm, NetLayout L, const float* __restrict__ tab, const uint4* __restrict__ states,
+            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float stem_tab[];  // [3][64][128], copied from the table built at upload
+  for (uint32_t e = threadIdx.x; e < 3u * 64u * kNetC / 4u; e += blockDim.x)
+    reinterpret_cast<float4*>(stem_tab)[e] = reinterpret_cast<const float4*>(tab)[e];
   __syncthreads();
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
   const size_t total = static_cast<size_t>(n_pos) * kCells * (kNetC / 8);
