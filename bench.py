@@ -272,6 +272,27 @@ def main():
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
     }
+    if world == 1:
+        # secondary evidence (not the headline): the leaf evaluator's dense forward pass, the only
+        # tensor-core work of the path (BASELINE config 3), timed with CUDA events inside the library
+        try:
+            batch, blocks = 8192, 6
+            net = azb.NNet(seed=7, blocks=blocks, precision=azb.NNET_BF16_TC, device=local_rank)
+            ms = net.benchmark(batch, 20)
+            flop = 2 * 42 * 18 * 128 + 2 * blocks * 2 * 42 * 1152 * 128 + 21504 + 1176 + 10752 + 5376 + 128
+            tf = batch * flop / ms / 1e9
+            try:
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                tpeak, tsrc = float(pk["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+            except Exception:
+                tpeak, tsrc = 2250.0, "fallback (nominal dense bf16)"
+            line["nnet_forward"] = {"workload": "config3 leaf evaluator: ResNet-6x128 bf16 forward, batch 8192 resident positions",
+                                    "ms_per_pass": ms, "positions_per_sec": batch / ms * 1e3,
+                                    "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                                                 "frac": tf / tpeak, "peak_source": tsrc,
+                                                 "kernel": "k_conv3x3_tc2 (tcgen05 cta_group::2, TMA im2col)"}}
+        except Exception as e:  # never fail the headline line on the secondary measurement
+            line["nnet_forward"] = {"error": repr(e)}
     if not args.no_cpu_baseline:
         ge.build_oracle()
         import oracle_api as orc

@@ -195,3 +195,30 @@ def test_arena_two_networks(azb, oracle):
     assert sum(counts) == 8 and st["evals"] > 0
     counts2, res2, _ = azb.arena_play_games(8, azb.EVAL_NNET, azb.EVAL_NNET, a, b, k_open=2, num_sims=20, seed=5)
     assert res.tolist() == res2.tolist()
+
+
+def test_pair_kernel_equals_single_cta_kernel(azb, oracle, tmp_path):
+    """k_conv3x3_tc2 (CTA pair, cta_group::2, TMA im2col, resident weights) and k_conv3x3_tc<1> (one CTA,
+    cp.async gather, streamed weights) accumulate every output in the same K order in fp32: the two
+    implementations of the tower must agree bit for bit (the kernel is chosen once per process, so the
+    single-CTA run happens in a child process with AZB200_TC_PAIR=0)."""
+    import os, subprocess, sys
+    feats = random_features(oracle, 25)
+    np.save(tmp_path / "feats.npy", feats)
+    net = azb.NNet(seed=11, blocks=3, precision=azb.NNET_BF16_TC)
+    pi, v = net.predict(feats)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import importlib, sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "azb = importlib.import_module('alphazero-rs_b200')\n"
+        f"feats = np.load({str(tmp_path / 'feats.npy')!r})\n"
+        "net = azb.NNet(seed=11, blocks=3, precision=azb.NNET_BF16_TC)\n"
+        "pi, v = net.predict(feats)\n"
+        f"np.save({str(tmp_path / 'pi.npy')!r}, pi); np.save({str(tmp_path / 'v.npy')!r}, v)\n"
+    )
+    env = dict(os.environ, AZB200_TC_PAIR="0")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    pi1, v1 = np.load(tmp_path / "pi.npy"), np.load(tmp_path / "v.npy")
+    assert np.array_equal(pi.view(np.uint32), pi1.view(np.uint32))
+    assert np.array_equal(v.view(np.uint32), v1.view(np.uint32))
