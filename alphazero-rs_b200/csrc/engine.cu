@@ -341,6 +341,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
   // single-CTA kernel with streamed weight tiles.
   static const bool use_pair = !(std::getenv("AZB200_TC_PAIR") && std::getenv("AZB200_TC_PAIR")[0] == '0');
+  static const bool use_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
   const uint32_t pair_tiles = (max_batch * kCells + kT2PairRows - 1) / kT2PairRows;
   static int max_pairs = -1;  // co-resident CTA pairs (one CTA per SM; a GPC with an odd SM count leaves one out)
   if (max_pairs < 0) {
@@ -357,9 +358,17 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     if (use_pair && max_pairs > 0) {
       int mi = 0;
       while (mi < 2 && net->d_act[mi].p != a.in) ++mi;
-      k_conv3x3_tc2<<<2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)), kTcThreads, kT2SmemBytes, st>>>(
-          a, net->act_map[mi]);
-      return cudaGetLastError();
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)));
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = kT2SmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute pdl{};  // overlap this layer's prologue + weight preload with the previous kernel's tail
+      pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pdl.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &pdl;
+      cfg.numAttrs = use_pdl ? 1 : 0;
+      return cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, a, net->act_map[mi]);
     }
     if (!clustered) {
       k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
@@ -401,8 +410,19 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     AZB_CUDA(launch_conv(a));
     std::swap(x, z);
   }
-  k_heads_bf16<<<std::min<uint32_t>((max_batch + kHeadPos - 1) / kHeadPos, 148u * 8u), 256, 0, st>>>(prm, net->L, net->head_w, x, d_count,
-                                                                                                      max_batch, d_pi, d_v);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min<uint32_t>((max_batch + kHeadPos - 1) / kHeadPos, 148u * 8u));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute pdl{};
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &pdl;
+    cfg.numAttrs = (use_pdl && use_pair && max_pairs > 0) ? 1 : 0;
+    const __nv_bfloat16* xin = x;
+    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_heads_bf16, prm, net->L, net->head_w, xin, d_count, max_batch, d_pi, d_v));
+  }
   AZB_CUDA(cudaGetLastError());
   if (d_dbg) {
     unsigned long long h[32];

@@ -477,8 +477,13 @@ k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as SMs free up (they set
+  // up barriers / TMEM and preload THEIR weights, which depend on nothing); everything that touches the
+  // activations first waits for the previous layer to have completed (griddepcontrol.wait below).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ===== epilogue, 8 warps: own TMEM lanes (the CTA's 128 rows) -> bias / residual / ReLU -> bf16 -> HBM.
     // A warp reads the TMEM lane quarter warp % 4; warps 0-3 take output channels 0-63, warps 4-7 64-127 =====
     const int q = warp & 3, half = warp >> 2;
@@ -569,6 +574,7 @@ k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       for (int kb = 0; kb < kTcKBlocks; ++kb)
         tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w_full);
       // ===== A producer: one im2col TMA per k-block for this CTA's 128 rows =====
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
       uint32_t it = 0;
       for (uint32_t i = 0; i < iters; ++i) {
         const uint32_t row0 = row0_of(i);
@@ -677,6 +683,7 @@ k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __grid_constant__
   __shared__ float val[kHeadPos][42];
   __shared__ float h1[kHeadPos][64];
   __shared__ float logit[kHeadPos][8];
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (launched with programmatic stream serialization)
   const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
   const int tid = threadIdx.x;
   for (uint32_t p0 = blockIdx.x * kHeadPos; p0 < n_pos; p0 += gridDim.x * kHeadPos) {
