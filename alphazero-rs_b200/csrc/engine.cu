@@ -295,7 +295,8 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     return AZB_OK;
   }
   // bf16 tensor-core path: stem -> 2R x conv3x3 (tcgen05) -> heads
-  const size_t act_bytes = static_cast<size_t>(max_batch) * kCells * kNetC * 2;
+  // + 8 positions of slack: the last 128-row TMA copy of a ragged batch runs a few rows past the batch
+  const size_t act_bytes = (static_cast<size_t>(max_batch) + 8) * kCells * kNetC * 2;
   for (auto& b : net->d_act) AZB_CUDA(b.ensure(act_bytes));
   for (int i = 0; i < 3; ++i)
     if (net->act_map_ptr[i] != net->d_act[i].p || net->act_map_bytes[i] != net->d_act[i].bytes) {
@@ -347,7 +348,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   if (max_pairs < 0) {
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(148u);
-    qc.blockDim = dim3(kTcThreads);
+    qc.blockDim = dim3(kT2Threads);
     qc.dynamicSmemBytes = kT2SmemBytes;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc2, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
@@ -360,7 +361,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
       while (mi < 2 && net->d_act[mi].p != a.in) ++mi;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)));
-      cfg.blockDim = dim3(kTcThreads);
+      cfg.blockDim = dim3(kT2Threads);
       cfg.dynamicSmemBytes = kT2SmemBytes;
       cfg.stream = st;
       cudaLaunchAttribute pdl{};  // overlap this layer's prologue + weight preload with the previous kernel's tail
