@@ -236,6 +236,7 @@ struct azb_nnet {
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
       {
         std::vector<float> tab(3 * 64 * kNetC);
@@ -283,6 +284,41 @@ int encode_act_map(CUtensorMap* map, void* ptr, size_t bytes) {
   return AZB_OK;
 }
 
+// TMA descriptor of a PADDED activation buffer [rows][128] for k_conv3x3_tc3: plain 2-D tiles of 64 channels x
+// 160 rows (a 128-row tile and its halo), SWIZZLE_128B, out-of-range rows zero-filled.
+int encode_act_map_rows(CUtensorMap* map, void* ptr, size_t bytes) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    AZB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kNetC), bytes / (kNetC * 2)};
+  const cuuint64_t strides[1] = {kNetC * 2};
+  const cuuint32_t box[2] = {kTcBlockK, static_cast<cuuint32_t>(kT3StageRows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return AZB_OK;
+}
+
+// Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout),
+// 2 = k_conv3x3_tc2 (CTA pair, TMA im2col per tap, dense layout), default 3 = k_conv3x3_tc3 (CTA pair, the
+// tile fetched once and reused by all taps, padded layout).
+int tc_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("AZB200_TC_PAIR");
+    return e && e[0] == '0' ? 0 : (e && e[0] == '2' ? 2 : 3);
+  }();
+  return mode;
+}
+
 // One dense forward pass over the first *d_count (or max_batch) positions.
 int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
                  float* d_v, cudaStream_t st) {
@@ -295,12 +331,17 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     return AZB_OK;
   }
   // bf16 tensor-core path: stem -> 2R x conv3x3 (tcgen05) -> heads
-  // + 8 positions of slack: the last 128-row TMA copy of a ragged batch runs a few rows past the batch
-  const size_t act_bytes = (static_cast<size_t>(max_batch) + 8) * kCells * kNetC * 2;
+  const int mode = tc_mode();
+  const ActLayout lay = mode == 3 ? kActPadded : kActDense;
+  // + slack: the last 128-row TMA copy of a ragged batch runs a few rows past the batch
+  const size_t act_bytes = (static_cast<size_t>(max_batch) + 8) * lay.pos_rows * kNetC * 2;
   for (auto& b : net->d_act) AZB_CUDA(b.ensure(act_bytes));
   for (int i = 0; i < 3; ++i)
     if (net->act_map_ptr[i] != net->d_act[i].p || net->act_map_bytes[i] != net->d_act[i].bytes) {
-      const int rc = encode_act_map(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
+      // a fresh buffer: the padded layout's zero rows / columns are zeroed here once and never written again
+      AZB_CUDA(cudaMemsetAsync(net->d_act[i].p, 0, net->d_act[i].bytes, st));
+      const int rc = mode == 3 ? encode_act_map_rows(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes)
+                               : encode_act_map(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
       if (rc) return rc;
       net->act_map_ptr[i] = net->d_act[i].p;
       net->act_map_bytes[i] = net->d_act[i].bytes;
@@ -311,7 +352,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const float* prm = net->d_params.as<float>();
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148u * 2u)), 256, kStemSmemBytes, st>>>(
-      prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x);
+      prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x, lay);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
   // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can
@@ -341,9 +382,9 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
                                   : std::min<uint32_t>(tiles, 148u);
   // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
   // single-CTA kernel with streamed weight tiles.
-  static const bool use_pair = !(std::getenv("AZB200_TC_PAIR") && std::getenv("AZB200_TC_PAIR")[0] == '0');
+  const bool use_pair = mode != 0;
   static const bool use_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
-  const uint32_t pair_tiles = (max_batch * kCells + kT2PairRows - 1) / kT2PairRows;
+  const uint32_t pair_tiles = (max_batch * lay.pos_rows + kT2PairRows - 1) / kT2PairRows;
   static int max_pairs = -1;  // co-resident CTA pairs (one CTA per SM; a GPC with an odd SM count leaves one out)
   if (max_pairs < 0) {
     cudaLaunchConfig_t qc{};
@@ -361,15 +402,16 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
       while (mi < 2 && net->d_act[mi].p != a.in) ++mi;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)));
-      cfg.blockDim = dim3(kT2Threads);
-      cfg.dynamicSmemBytes = kT2SmemBytes;
+      cfg.blockDim = dim3(mode == 3 ? kTcThreads : kT2Threads);
+      cfg.dynamicSmemBytes = mode == 3 ? kT3SmemBytes : kT2SmemBytes;
       cfg.stream = st;
       cudaLaunchAttribute pdl{};  // overlap this layer's prologue + weight preload with the previous kernel's tail
       pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
       pdl.val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = &pdl;
       cfg.numAttrs = use_pdl ? 1 : 0;
-      return cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, a, net->act_map[mi]);
+      return mode == 3 ? cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, a, net->act_map[mi])
+                       : cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, a, net->act_map[mi]);
     }
     if (!clustered) {
       k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
@@ -422,7 +464,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     cfg.attrs = &pdl;
     cfg.numAttrs = (use_pdl && use_pair && max_pairs > 0) ? 1 : 0;
     const __nv_bfloat16* xin = x;
-    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_heads_bf16, prm, net->L, net->head_w, xin, d_count, max_batch, d_pi, d_v));
+    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_heads_bf16, prm, net->L, net->head_w, xin, d_count, max_batch, d_pi, d_v, lay));
   }
   AZB_CUDA(cudaGetLastError());
   if (d_dbg) {

@@ -640,6 +640,232 @@ k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u * kT2Accs) : "memory");
 }
 
+// Where a (position, board row y, column x) lives in an activation buffer [row][128 channels]:
+//   dense  : row = pos * 42 + y * 7 + x                      (k_conv3x3_tc<1>, k_conv3x3_tc2)
+//   padded : row = pos * 56 + y * 8 + x, column 7 and board row 6 of every position are ZERO rows that
+//            nobody ever writes: a tap (dy, dx) of the 3x3 window is then the plain row shift dy * 8 + dx,
+//            zero padding included (k_conv3x3_tc3).
+struct ActLayout {
+  uint32_t pos_rows, pitch;  // 42, 7 or 56, 8
+  __host__ __device__ size_t row(uint32_t pos, int y, int x) const { return static_cast<size_t>(pos) * pos_rows + y * pitch + x; }
+};
+constexpr ActLayout kActDense{42u, 7u};
+constexpr ActLayout kActPadded{56u, 8u};
+
+// ================================================================================================
+// CTA-pair version 3: the A operand is fetched ONCE per tile and reused by all nine taps.
+//
+// k_conv3x3_tc2 asks the TMA unit for a shifted copy of the tile per tap and channel half (18 x 16 KB per
+// 128 rows), and the unit's im2col rate (~5 cycles per 128-byte pixel row) ends up feeding the tensor
+// core at ~40 % of what it could consume.  Here the activations live in the PADDED layout (ActLayout:
+// 56 rows per position, board rows of 8 with a zero column, a zero row after every position), in which
+// the tap (dy, dx) of output row R is input row R + dy * 8 + dx, zero padding included.  So a CTA
+// loads rows [R0 - 16, R0 + 144) of its 128-row tile once per channel half (2 x 20 KB, plain 2-D TMA,
+// SWIZZLE_128B, out-of-range rows zero-filled) and the 18 k-blocks of the tile are 18 views of the same
+// stage: the UMMA descriptor's start address moves by (16 + dy * 8 + dx) rows, with the descriptor's
+// base-offset field giving the swizzle phase of a start that is not 1024-byte aligned.  Per tile the
+// issuing thread waits once, issues 72 MMAs and commits twice; 25 % of the rows of a tile are padding
+// rows (computed, never stored).  Weights resident as in tc2 (144 KB per CTA); 2 stages of 40 KB
+// (the next tile is fetched while the current one is computed); accumulators 2 x 128 TMEM columns.
+// ================================================================================================
+constexpr int kT3HaloRows = 16;                                   // rows fetched before the tile (>= 9, multiple of 8)
+constexpr int kT3StageRows = kTcTileM + 2 * kT3HaloRows;          // 160
+constexpr uint32_t kT3HalfBytes = kT3StageRows * 128;             // 20480: one channel half of a stage
+constexpr uint32_t kT3StageBytes = 2 * kT3HalfBytes;              // 40960
+constexpr int kT3Stages = 2;
+constexpr uint32_t kT3SmemBytes = kT2WBytes + kT3Stages * kT3StageBytes + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
+
+// UMMA descriptor of a 128-row K-major SWIZZLE_128B operand that starts at an arbitrary 128-byte row of a
+// 1024-byte aligned buffer: the base-offset field [49, 52) carries (start address >> 7) & 7.
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t smem_addr) {
+  // Measured on B200: the swizzle XOR is taken from the absolute shared-memory address bits, so a start that is
+  // not 1024-byte aligned needs NO base offset (with base offset = (addr >> 7) & 7 the taps with dx != 0 came
+  // out wrong; with 0 the result is bit-identical to the im2col kernel).
+  return umma_desc_sw128(smem_addr);
+}
+// two 32-column accumulator chunks at once, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, uint32_t (&r0)[32], uint32_t (&r1)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+        "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15]), "=r"(r0[16]),
+        "=r"(r0[17]), "=r"(r0[18]), "=r"(r0[19]), "=r"(r0[20]), "=r"(r0[21]), "=r"(r0[22]), "=r"(r0[23]), "=r"(r0[24]),
+        "=r"(r0[25]), "=r"(r0[26]), "=r"(r0[27]), "=r"(r0[28]), "=r"(r0[29]), "=r"(r0[30]), "=r"(r0[31])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+        "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15]), "=r"(r1[16]),
+        "=r"(r1[17]), "=r"(r1[18]), "=r"(r1[19]), "=r"(r1[20]), "=r"(r1[21]), "=r"(r1[22]), "=r"(r1[23]), "=r"(r1[24]),
+        "=r"(r1[25]), "=r"(r1[26]), "=r"(r1[27]), "=r"(r1[28]), "=r"(r1[29]), "=r"(r1[30]), "=r"(r1[31])
+      : "r"(taddr + 32u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_tile2d_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t mbar_cluster, int c, int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster), "r"(c), "r"(row)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto w_tile = [&](int kb) { return base + kb * kT2WTile; };
+  auto stage_a = [&](int s, int half) { return base + kT2WBytes + s * kT3StageBytes + half * kT3HalfBytes; };
+  const uint32_t bars = base + kT2WBytes + kT3Stages * kT3StageBytes;
+  auto bar_full = [&](int s) { return bars + 8u * s; };              // leader: 1 arrival (its expect_tx) + 2 x 40 KB of TMA bytes
+  auto bar_empty = [&](int s) { return bars + 16u + 8u * s; };       // 1 arrival: the pair's MMAs have read the stage
+  auto bar_acc_full = [&](int a) { return bars + 32u + 8u * a; };    // 1 arrival: the tile's MMAs are done
+  auto bar_acc_empty = [&](int a) { return bars + 48u + 8u * a; };   // leader: 512 arrivals (both CTAs' 8 epilogue warps)
+  const uint32_t bar_w_full = bars + 64u;
+  const uint32_t bar_w_peer = bars + 72u;
+  const uint32_t tmem_slot = bars + 80u;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));  // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
+  const uint32_t rows = n_pos * kActPadded.pos_rows;  // padded rows
+  const uint32_t n_tiles = (rows + kT2PairRows - 1) / kT2PairRows;
+  const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;
+  auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kT2PairRows + rank * kTcTileM; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kT3Stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full(a), 1);
+      mbar_init(bar_acc_empty(a), 512);
+    }
+    mbar_init(bar_w_full, 1);
+    mbar_init(bar_w_peer, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
+  }
+  if (threadIdx.x < kNetC) s_bias[threadIdx.x] = g.bias[threadIdx.x];  // (parameters: not written by the previous layer)
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp < 8) {
+    // ===== epilogue, 8 warps: TMEM lane quarter warp % 4, output channels 64 * (warp / 4) .. + 63 =====
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int q = warp & 3, half = warp >> 2;
+    for (uint32_t ti = 0; ti < iters; ++ti) {
+      const uint32_t a = ti & 1u;
+      const uint32_t m = row0_of(ti) + q * 32 + lane;        // padded row
+      const uint32_t rem = m % kActPadded.pos_rows;
+      const bool real = m < rows && (rem & 7u) != 7u && rem < 48u;  // not the zero column, not the zero row
+      // the residual (64 channels = 8 x 16 B of my row) is requested before the accumulator is waited for
+      uint4 res[8];
+      if (real && g.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + half * 64);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
+      }
+      mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
+      tc_fence_after();
+      uint32_t acc0[32], acc1[32];
+      tmem_ld32x2(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + half * 64u, acc0, acc1);
+      tc_fence_before();
+      mbar_arrive_cluster(bar_acc_empty(a), 0u);  // the accumulator is in registers: the next tile may overwrite it
+      if (real) {
+        uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + half * 64);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {  // 8 output channels per 16-byte store
+          const uint32_t* acc = c8 < 4 ? acc0 : acc1;
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c8 * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c8 * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const uint32_t rw[4] = {res[c8].x, res[c8].y, res[c8].z, res[c8].w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e]) + bb[2 * e];
+            float x1 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e + 1]) + bb[2 * e + 1];
+            if (g.residual) {
+              x0 += __uint_as_float(rw[e] << 16);
+              x1 += __uint_as_float(rw[e] & 0xFFFF0000u);
+            }
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+            pk[e] = *reinterpret_cast<const uint32_t*>(&p2);
+          }
+          op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && iters > 0) {
+      mbar_wait(bar_w_full, 0u);
+      if (rank == 1) {
+        mbar_arrive_cluster(bar_w_peer, 0u);
+      } else {
+        // ===== MMA issuer of the pair: per tile one wait, 18 k-blocks x 4 MMAs on shifted views of the stage, two commits =====
+        mbar_wait(bar_w_peer, 0u);
+        for (uint32_t ti = 0; ti < iters; ++ti) {
+          const uint32_t a = ti & 1u;
+          const int s = ti % kT3Stages;
+          mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+          mbar_wait(bar_full(s), (ti / kT3Stages) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int kb = 0; kb < kTcKBlocks; ++kb) {
+            const int tap = kb >> 1, shift = kT3HaloRows + (tap / 3 - 1) * 8 + (tap % 3 - 1);  // rows
+            const uint64_t ad = umma_desc_sw128_rows(stage_a(s, kb & 1) + shift * 128), bd = umma_desc_sw128(w_tile(kb));
+#pragma unroll
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              umma2_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
+          }
+          umma2_commit_multicast(bar_empty(s), 3u);     // the stage may be refilled (both CTAs)
+          umma2_commit_multicast(bar_acc_full(a), 3u);  // the accumulator is complete (both CTAs' epilogues)
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0 && iters > 0) {
+      // ===== weight preload (once per launch), then the A producer: two 2-D TMA copies per tile =====
+      mbar_arrive_expect_tx(bar_w_full, kT2WBytes);
+      for (int kb = 0; kb < kTcKBlocks; ++kb)
+        tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w_full);
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
+      for (uint32_t i = 0; i < iters; ++i) {
+        const int s = i % kT3Stages;
+        mbar_wait(bar_empty(s), ((i / kT3Stages) & 1u) ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2u * kT3StageBytes);  // both CTAs' copies land on this barrier
+        const int r0 = static_cast<int>(row0_of(i)) - kT3HaloRows;  // negative for the first tile: zero-filled
+        const uint32_t full = map_to_cta(bar_full(s), 0u);
+        tma_tile2d_pair(stage_a(s, 0), &tmap_in, full, 0, r0);
+        tma_tile2d_pair(stage_a(s, 1), &tmap_in, full, kTcBlockK, r0);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
 // Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  The two input planes are
 // binary, so a window row (3 cells x 2 planes = 6 bits) selects one of 64 precomputed partial sums:
 // out = ReLU(bias + T[0][bits of row y-1] + T[1][bits of row y] + T[2][bits of row y+1]).  Each
@@ -660,7 +886,7 @@ inline void stem_table_build(const float* prm, const NetLayout& L, float* tab /*
 }
 __global__ void __launch_bounds__(256)
 k_stem_bf16(const float* __restrict__ prm, NetLayout L, const float* __restrict__ tab, const uint4* __restrict__ states,
-            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out) {
+            const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out, ActLayout lay) {
   extern __shared__ float stem_tab[];  // [3][64][128], copied from the table built at upload
   for (uint32_t e = threadIdx.x; e < 3u * 64u * kNetC / 4u; e += blockDim.x)
     reinterpret_cast<float4*>(stem_tab)[e] = reinterpret_cast<const float4*>(tab)[e];
@@ -694,7 +920,7 @@ k_stem_bf16(const float* __restrict__ prm, NetLayout L, const float* __restrict_
       const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[2 * k], 0.0f), fmaxf(acc[2 * k + 1], 0.0f));
       pk[k] = *reinterpret_cast<const uint32_t*>(&p2);
     }
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(out + lay.row(pos, r, c) * kNetC + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -712,7 +938,7 @@ constexpr int kHeadPos = 6;  // positions per CTA step: 6 x 42 = 252 rows on 256
 __global__ void __launch_bounds__(256)
 k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __grid_constant__ HeadConvW hw,
              const __nv_bfloat16* __restrict__ act, const uint32_t* __restrict__ count, uint32_t max_batch,
-             float* __restrict__ pi_out, float* __restrict__ v_out) {
+             float* __restrict__ pi_out, float* __restrict__ v_out, ActLayout lay) {
   __shared__ float pol[kHeadPos][84];   // plane*42 + cell
   __shared__ float val[kHeadPos][42];
   __shared__ float h1[kHeadPos][64];
@@ -724,7 +950,7 @@ k_heads_bf16(const float* __restrict__ prm, NetLayout L, const __grid_constant__
     __syncthreads();
     const int lp = tid / kCells, cell = tid % kCells;
     if (tid < kHeadPos * kCells && p0 + lp < n_pos) {
-      const uint4* src = reinterpret_cast<const uint4*>(act + (static_cast<size_t>(p0 + lp) * kCells + cell) * kNetC);
+      const uint4* src = reinterpret_cast<const uint4*>(act + lay.row(p0 + lp, cell / 7, cell % 7) * kNetC);
       float s0 = hw.b[0], s1 = hw.b[1], s2 = hw.b[2];
 #pragma unroll
       for (int v8 = 0; v8 < kNetC / 8; ++v8) {
