@@ -351,7 +351,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
   const float* prm = net->d_params.as<float>();
   const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
-  k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148u * 2u)), 256, kStemSmemBytes, st>>>(
+  k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes, st>>>(
       prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x, lay);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.

@@ -737,6 +737,12 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   const uint32_t n_tiles = (rows + kT2PairRows - 1) / kT2PairRows;
   const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;
   auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kT2PairRows + rank * kTcTileM; };
+  const bool dbg_on = g.dbg != nullptr && blockIdx.x < 2;
+  unsigned long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
+  long long dbg_c = 0;
+#define AZB_DBG_T0() do { if (dbg_on) dbg_c = clock64(); } while (0)
+#define AZB_DBG_ADD(k) do { if (dbg_on) { const long long n_ = clock64(); dbg_t[k] += n_ - dbg_c; dbg_c = n_; } } while (0)
+  const long long dbg_start = dbg_on ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kT3Stages; ++s) {
@@ -781,7 +787,9 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
       }
+      AZB_DBG_T0();
       mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
+      AZB_DBG_ADD(0);
       tc_fence_after();
       uint32_t acc0[32], acc1[32];
       tmem_ld32x2(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + half * 64u, acc0, acc1);
@@ -811,7 +819,9 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
           op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
+      AZB_DBG_ADD(1);
     }
+    if (dbg_on && threadIdx.x == 128) { g.dbg[rank * 16 + 2] = dbg_t[0]; g.dbg[rank * 16 + 3] = dbg_t[1]; }
   } else if (warp == 8) {
     if (lane == 0 && iters > 0) {
       mbar_wait(bar_w_full, 0u);
@@ -823,8 +833,11 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
         for (uint32_t ti = 0; ti < iters; ++ti) {
           const uint32_t a = ti & 1u;
           const int s = ti % kT3Stages;
+          AZB_DBG_T0();
           mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+          AZB_DBG_ADD(1);
           mbar_wait(bar_full(s), (ti / kT3Stages) & 1u);
+          AZB_DBG_ADD(0);
           tc_fence_after();
 #pragma unroll 1
           for (int kb = 0; kb < kTcKBlocks; ++kb) {
@@ -834,9 +847,12 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
             for (int k = 0; k < kTcBlockK / 16; ++k)
               umma2_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
           }
+          AZB_DBG_ADD(3);
           umma2_commit_multicast(bar_empty(s), 3u);     // the stage may be refilled (both CTAs)
           umma2_commit_multicast(bar_acc_full(a), 3u);  // the accumulator is complete (both CTAs' epilogues)
+          AZB_DBG_ADD(4);
         }
+        if (dbg_on) for (int k = 0; k < 6; ++k) g.dbg[4 + k] = dbg_t[k];
       }
     }
     __syncwarp();
@@ -849,16 +865,23 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
       for (uint32_t i = 0; i < iters; ++i) {
         const int s = i % kT3Stages;
+        AZB_DBG_T0();
         mbar_wait(bar_empty(s), ((i / kT3Stages) & 1u) ^ 1u);
+        AZB_DBG_ADD(0);
         if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2u * kT3StageBytes);  // both CTAs' copies land on this barrier
         const int r0 = static_cast<int>(row0_of(i)) - kT3HaloRows;  // negative for the first tile: zero-filled
         const uint32_t full = map_to_cta(bar_full(s), 0u);
         tma_tile2d_pair(stage_a(s, 0), &tmap_in, full, 0, r0);
         tma_tile2d_pair(stage_a(s, 1), &tmap_in, full, kTcBlockK, r0);
+        AZB_DBG_ADD(1);
       }
+      if (dbg_on) { g.dbg[rank * 16 + 0] = dbg_t[0]; g.dbg[rank * 16 + 1] = dbg_t[1]; }
     }
     __syncwarp();
   }
+  if (dbg_on && threadIdx.x == 0) { g.dbg[rank * 16 + 11] = clock64() - dbg_start; g.dbg[rank * 16 + 12] = iters; }
+#undef AZB_DBG_T0
+#undef AZB_DBG_ADD
 
   tc_fence_before();
   __syncthreads();
@@ -884,7 +907,7 @@ inline void stem_table_build(const float* prm, const NetLayout& L, float* tab /*
     tab[e] = acc;
   }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_stem_bf16(const float* __restrict__ prm, NetLayout L, const float* __restrict__ tab, const uint4* __restrict__ states,
             const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out, ActLayout lay) {
   extern __shared__ float stem_tab[];  // [3][64][128], copied from the table built at upload

@@ -290,7 +290,7 @@ def main():
                                     "ms_per_pass": ms, "positions_per_sec": batch / ms * 1e3,
                                     "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                                  "frac": tf / tpeak, "peak_source": tsrc,
-                                                 "kernel": "k_conv3x3_tc2 (tcgen05 cta_group::2, TMA im2col)"}}
+                                                 "kernel": "k_conv3x3_tc3 (tcgen05 cta_group::2, resident weights, TMA tiles reused by all taps)"}}
         except Exception as e:  # never fail the headline line on the secondary measurement
             line["nnet_forward"] = {"error": repr(e)}
     if not args.no_cpu_baseline:
