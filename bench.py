@@ -111,7 +111,7 @@ def cpu_baseline_run(orc, seconds_target, threads):
     (the reference's rayon episode pool).  Bounded sample: whole games until ~seconds_target."""
     probe = orc.bench_selfplay(threads, threads, num_sims=NUM_SIMS, seed=SEED, reserve=131072, first_game_id=0)
     per_round = max(probe["seconds"], 1e-3)
-    rounds = max(1, min(64, int(seconds_target / per_round)))
+    rounds = max(1, min(1024, int(seconds_target / per_round)))
     n_games = threads * rounds
     r = orc.bench_selfplay(n_games, threads, num_sims=NUM_SIMS, seed=SEED, reserve=131072, first_game_id=0)
     r["n_games"] = n_games

@@ -99,3 +99,37 @@ def test_pool_overflow_is_an_error(azb, oracle):
 def test_fast_arithmetic_is_ieee_exact(azb):
     # the level loop's division / sqrt without slow-path calls vs __frcp_rn/__fsqrt_rn/__fdiv_rn
     assert azb.selftest_arith() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("quirks", [0, 15])
+@pytest.mark.parametrize("max_depth", [0, 2, 7])
+def test_depth_limit_uses_the_generic_walk(azb, oracle, quirks, max_depth):
+    """max_depth < 43 routes every simulation to the GENERIC variant of one_sim_impl (depth check at every
+    level, __fdiv_rn, no speculative prefix): async_mcts.rs:241-244 with repair F6."""
+    root = oracle.init_board(1)
+    m = azb.AsyncMcts(1, num_sims=300, quirks=quirks, evaluator=1, max_depth=max_depth, mcts_reserve_size=400000)
+    o = oracle.Mcts(num_sims=300, quirks=quirks, evaluator=1, max_depth=max_depth)
+    for temp in (1.0, 0.0):
+        ca, pa = m.get_action_prob(root, temp)
+        cb, pb = o.get_action_prob(root, temp)
+        assert ca[0].tolist() == cb.tolist()
+        assert np.array_equal(pa[0].view(np.uint32), pb.view(np.uint32))
+    assert m.stats()[0][:6].tolist() == o.stats()[:6].tolist()
+    compare_tree(m, o)
+
+
+def test_visit_counts_past_the_16_bit_wrap(azb, oracle):
+    """Quirk Q6: N is 16 bits and wraps into W (node.rs:17).  Trees whose visit counts may reach the wrap switch
+    from the hot variant (speculative prefix, FMA division) to the GENERIC one in the middle of their life: the
+    result must stay bit-identical with the oracle across the switch and across the wrap itself."""
+    root = oracle.init_board(1)
+    sims = 22000
+    m = azb.AsyncMcts(1, num_sims=sims, quirks=0, evaluator=0, mcts_reserve_size=1000000)
+    o = oracle.Mcts(num_sims=sims, quirks=0, evaluator=0, reserve=1000000)
+    for call in range(4):  # 88 000 simulations through the same root: its N wraps at 65 536
+        ca, pa = m.get_action_prob(root, 1.0)
+        cb, pb = o.get_action_prob(root, 1.0)
+        assert ca[0].tolist() == cb.tolist(), call
+        assert int(m.counter_of(root)[0]) == o.counter_of(root), call
+    assert m.stats()[0][:6].tolist() == o.stats()[:6].tolist()
+    compare_tree(m, o)
