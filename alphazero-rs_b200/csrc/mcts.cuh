@@ -242,6 +242,10 @@ __device__ __forceinline__ float uniform_prior_table(int lane) {
   asm volatile("" : "+f"(r));  // opaque: keep it in its register instead of recomputing it at every use
   return r;
 }
+// every table entry 1/k (k = 1..7) times cpuct stays in the range the FMA division is proven for
+__device__ __forceinline__ bool uniform_prior_is_safe(float cpuct_f) {
+  return !prior_needs_slow_div(cpuct_f, 1.0f) && !prior_needs_slow_div(cpuct_f, __fdiv_rn(1.0f, 7.0f));
+}
 __device__ __forceinline__ void evaluate_masked(const WarpTree& t, int kind, BB s, uint32_t vm, int lane,
                                                 float& pi, float& v) {
   if (kind == AZB_EVAL_UNIFORM) {
@@ -416,7 +420,7 @@ __device__ __forceinline__ void finish_root_eval(WarpTree& t, const SearchParams
 // the policy, publish the new node, back the value up.
 __device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p, const Pending& pd,
                                               float pi, float val, int lane, bool normalised = true,
-                                              bool predict = false) {
+                                              bool predict = false, bool safe_prior = false) {
   if (!normalised) pi = mask_normalise(pi, pd.vm, lane);
   // predict: the path of this simulation, with the new node as its last level, is the prediction
   // for the next one (only when path[0..plen) carries block ids, i.e. not after a resume)
@@ -425,7 +429,9 @@ __device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p
     if (lane == 0) *reinterpret_cast<uint2*>(t.path + pd.plen) = make_uint2((pd.my_slot << 3) | 7u, pd.new_meta);
     t.pred_len = pd.plen + 1u;
   }
-  if (__any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
+  // (safe_prior: the UNIFORM evaluator's priors are 1/k, k = 1..7: inside fdiv_by_int's proven range whenever
+  // cpuct itself is, which uniform_prior_is_safe() checks once)
+  if (!safe_prior && __any_sync(kFull, lane < 7 && prior_needs_slow_div(p.cpuct_f, pi))) t.slow = 1u;
   write_child_block(t, pd.new_meta, pd.vm, pi, kFlagHasPolicy, lane);
   if (lane == 0) reinterpret_cast<uint32_t*>(t.blocks + pd.my_slot)[3] = pd.new_meta;
   tt_insert(t, pd.ins, pd.key, pd.my_slot, pd.new_meta, lane);
@@ -648,7 +654,8 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
         leaf = S2;
         return false;
       }
-      finish_expand(t, p, pd, pi, val, lane, /*normalised=*/true, /*predict=*/!GENERIC);
+      finish_expand(t, p, pd, pi, val, lane, /*normalised=*/true, /*predict=*/!GENERIC,
+                    /*safe_prior=*/ev_kind == AZB_EVAL_UNIFORM && uniform_prior_is_safe(p.cpuct_f));
       return true;
     }
   }
