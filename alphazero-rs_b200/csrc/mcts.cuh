@@ -7,18 +7,20 @@
 // One warp owns one tree and runs one simulation at a time, so every f32 rounding and every
 // tie-break happens in the reference's order and results are bit-exact with the oracle.
 //
-// The search is instruction-issue bound (ncu: profiles/r1_v1_selfplay_ncu.md), so the level
-// loop is kept minimal:
-//   * per level the warp reads ONE 128-byte block (lane a = edge a: {w, q, prior, meta} + n[a]),
-//     resolves transposition links with two small extra loads, computes
+// The search is bound by the dependent instruction chain of one simulation (ncu: profiles/
+// r1_selfplay_ncu.md: a warp alone on its scheduler issues one instruction per ~5.4 cycles), so the
+// walk is built to execute as few instructions as possible:
+//   * speculative prefix (one_sim_impl): the previous simulation's path is re-checked four levels per
+//     pass, one level per 8-lane group, with one shuffle + one ballot instead of four arg-maxes;
+//   * per level a group reads ONE 128-byte block (lane 8g + a = edge a: {w, q, prior, meta} + n[a]),
+//     resolves transposition links under a warp vote, computes
 //     u = q + (cpuct*P*sqrt(N_parent))/(1+n) per lane (Q is cached, one division left, done
-//     with an FMA sequence proven correctly rounded), and takes the LAST maximum with
-//     redux.max.f32 + ballot + clz;
+//     with an FMA sequence proven correctly rounded); a real arg-max (LAST maximum: redux.max.f32 +
+//     ballot + bfind) is taken only at the first level that leaves the prediction and below it;
 //   * visit()/unvisit() of the reference are folded into one read-modify-write per path node
-//     at backup (lane l handles path entry l), which also refreshes the cached q;
-//   * the board is not tracked during descent: only (slot, action) goes to a shared-memory
-//     path, and the leaf position is rebuilt lane-parallel from the root position and the path
-//     actions when (and only when) a placeholder is expanded.
+//     at backup (lane l handles path entry l), which also refreshes the cached q, N and sqrt(N);
+//   * the path lives in shared memory with the position of every level, so an expansion has its
+//     position at hand; the win test is lane-parallel; the UNIFORM evaluator's priors are a table.
 #pragma once
 #include <cuda_runtime.h>
 
