@@ -308,6 +308,15 @@ int encode_act_map_rows(CUtensorMap* map, void* ptr, size_t bytes) {
   return AZB_OK;
 }
 
+// Network rounds: a slot that needs no evaluation for this many simulations yields (endgames that only hit
+// terminal nodes would otherwise hold the whole round back, every simulation of a round starting from cold
+// caches).  Measured on config 3 (8192 games x 400 sims): 1: 10.1 s, 2: 9.1, 3: 8.8, 4-6: 8.7, 8: 8.8, 16: 9.3,
+// 32: 9.8.  AZB200_ROUND_SIMS overrides for sweeps; results do not depend on it.
+uint32_t round_sim_budget(bool arena = false) {
+  static const uint32_t n = std::getenv("AZB200_ROUND_SIMS") ? static_cast<uint32_t>(std::max(1, std::atoi(std::getenv("AZB200_ROUND_SIMS")))) : 0u;
+  return n ? n : (arena ? 16u : 5u);  // (the arena share of config 4: 3.07 s with 16, 3.17 s with 5)
+}
+
 // Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout),
 // 2 = k_conv3x3_tc2 (CTA pair, TMA im2col per tap, dense layout), default 3 = k_conv3x3_tc3 (CTA pair, the
 // tile fetched once and reused by all taps, padded layout).
@@ -949,7 +958,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rp.mode = kModeSelfPlay;
     rp.ev_kind[0] = rp.ev_kind[1] = c->cfg.evaluator;
     rp.plies_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 0u : (c->cfg.plies_per_launch ? c->cfg.plies_per_launch : 2u);
-    rp.sims_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 16u : 0u;
+    rp.sims_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? round_sim_budget() : 0u;
     rp.n_slots = static_cast<uint32_t>(n_trees);
     rp.n_games = static_cast<uint32_t>(G);
     rp.first_game_id = first_game_id;
@@ -1234,7 +1243,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   rp.ev_kind[1] = eval_b;
   const bool any_net = eval_a >= AZB_EVAL_NNET || eval_b >= AZB_EVAL_NNET;
   rp.plies_per_launch = any_net ? 0u : (cfg->plies_per_launch ? cfg->plies_per_launch : 2u);
-  rp.sims_per_launch = any_net ? 16u : 0u;
+  rp.sims_per_launch = any_net ? round_sim_budget(true) : 0u;
   rp.n_slots = static_cast<uint32_t>(n_slots);
   rp.n_games = static_cast<uint32_t>(G);
   rp.half = static_cast<uint32_t>(half);
