@@ -911,11 +911,12 @@ __global__ void __launch_bounds__(1024)
 k_stem_bf16(const float* __restrict__ prm, NetLayout L, const float* __restrict__ tab, const uint4* __restrict__ states,
             const uint32_t* __restrict__ count, uint32_t max_batch, __nv_bfloat16* __restrict__ out, ActLayout lay) {
   extern __shared__ float stem_tab[];  // [3][64][128], copied from the table built at upload
+  const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
+  const size_t total = static_cast<size_t>(n_pos) * kCells * (kNetC / 8);
+  if (static_cast<size_t>(blockIdx.x) * blockDim.x >= total) return;  // (the grid is sized for max_batch) no work: no 96-KB copy
   for (uint32_t e = threadIdx.x; e < 3u * 64u * kNetC / 4u; e += blockDim.x)
     reinterpret_cast<float4*>(stem_tab)[e] = reinterpret_cast<const float4*>(tab)[e];
   __syncthreads();
-  const uint32_t n_pos = count ? min(*count, max_batch) : max_batch;
-  const size_t total = static_cast<size_t>(n_pos) * kCells * (kNetC / 8);
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const uint32_t cg = idx % (kNetC / 8);
