@@ -40,7 +40,7 @@ struct __align__(16) GameRec {
   uint32_t pad[3];
   Pending pd;
   TreeVars tv[2];
-  uint32_t path[kPathCap];
+  PathEnt path[kPathCap];  // the suspended simulation's path, whole entries: after the resume it is the next simulation's prediction
 };
 
 struct LeafBufs {
@@ -207,13 +207,13 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
 
   if (phase == kPhasePending) {  // the network's answer for the suspended simulation is in
     Pending pd = rec->pd;
-    for (uint32_t i = lane; i < pd.plen; i += 32u) t.path[i].sa = rec->path[i];
+    for (uint32_t i = lane; i <= pd.plen && i < kPathCap; i += 32u) t.path[i] = rec->path[i];
     __syncwarp();
     const size_t row = static_cast<size_t>(side) * rp.n_slots + rec->leaf_idx;
     const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
     const float val = leaf.v[row];
     if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
-    else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false);
+    else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false, /*predict=*/true);
     sims_done++;
     phase = kPhaseSearch;
   }
@@ -297,7 +297,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
         rec->leaf_idx = idx;
       }
       __syncwarp();
-      for (uint32_t i = lane; i < pd.plen; i += 32u) rec->path[i] = t.path[i].sa;
+      for (uint32_t i = lane; i <= pd.plen && i < kPathCap; i += 32u) rec->path[i] = t.path[i];
       phase = kPhasePending;
       break;
     }
