@@ -222,3 +222,21 @@ def test_pair_kernel_equals_single_cta_kernel(azb, oracle, tmp_path):
     pi1, v1 = np.load(tmp_path / "pi.npy"), np.load(tmp_path / "v.npy")
     assert np.array_equal(pi.view(np.uint32), pi1.view(np.uint32))
     assert np.array_equal(v.view(np.uint32), v1.view(np.uint32))
+
+
+def test_config3_parameters_sampled_games(azb, oracle):
+    """BASELINE config 3 parameters (400 sims/move, ResNet-6x128 bf16 on the tcgen05 tower, seed 0xA1FA0) on a
+    512-game batch — many M tiles per layer, rounds with thousands of pending leaves — and two of its games replayed
+    by the oracle with the same network as its predict callback: actions and per-ply root counts bit for bit."""
+    net = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
+    coach = azb.Coach(nnet=net, num_sims=400, seed=0xA1FA0, evaluator=azb.EVAL_NNET)
+    st = coach.self_play(512, 0)
+    tr = coach.traces()
+    assert st["games"] == 512 and st["sims"] == 400 * st["plies"]
+    for g in (3, 509):
+        o = oracle.execute_episode(num_sims=400, quirks=0, seed=0xA1FA0, episode_id=g, evaluator=oracle.EVAL_CALLBACK,
+                                   callback=net.predict)
+        n = o["plies"]
+        assert tr["plies"][g] == n
+        assert tr["actions"][g, :n].tolist() == o["actions"][:n].tolist()
+        assert np.array_equal(tr["counts"][g, :n], o["counts"][:n])
