@@ -143,6 +143,8 @@ def _load():
         "azb_nnet_set_params": [vp, vp, u64],
         "azb_coach_set_nnet": [vp, vp],
         "azb_nnet_benchmark": [vp, u64, u32, C.POINTER(C.c_double)],
+        "azb_nnet_conv_hook": [vp, C.c_int32, C.c_int32, vp, vp, vp, u64, vp],
+        "azb_nnet_wgrad_hook": [vp, vp, vp, u64, vp],
         "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
                                  C.POINTER(SelfPlayStats)],
     }
@@ -444,6 +446,25 @@ class NNet:
         v = np.zeros(n, np.float32)
         _check(lib.azb_nnet_predict(self._h, _ptr(boards), n, model_id, _ptr(pi), _ptr(v)))
         return pi, v
+
+    def conv_hook(self, layer, mode, x, residual=None, mask=None):
+        """Tower convolution `layer` on the tensor cores: mode 0 forward, mode 1 backward data (see azb200.h).
+        x / residual / mask: f32 [n, 42, 128] (cell-major, channel-minor); returns the same shape."""
+        x = np.ascontiguousarray(x, np.float32)
+        res = None if residual is None else np.ascontiguousarray(residual, np.float32)
+        msk = None if mask is None else np.ascontiguousarray(mask, np.float32)
+        out = np.zeros_like(x)
+        _check(lib.azb_nnet_conv_hook(self._h, layer, mode, _ptr(x), _ptr(res) if res is not None else None,
+                                      _ptr(msk) if msk is not None else None, len(x), _ptr(out)))
+        return out
+
+    def wgrad_hook(self, x, dz):
+        """dW[9, 128 ci, 128 co] of a tower convolution from its input x and the gradient dz of its pre-activation."""
+        x = np.ascontiguousarray(x, np.float32)
+        dz = np.ascontiguousarray(dz, np.float32)
+        dw = np.zeros((9, 128, 128), np.float32)
+        _check(lib.azb_nnet_wgrad_hook(self._h, _ptr(x), _ptr(dz), len(x), _ptr(dw)))
+        return dw
 
     def benchmark(self, batch, iters=10):
         """Device-only mean milliseconds per forward pass over `batch` resident positions."""

@@ -193,6 +193,7 @@ struct azb_nnet {
   std::vector<float> h_params;
   DevBuf d_params;
   DevBuf d_wtiles;                     // bf16 path: kTcWeightCopies x [2R][18] pre-swizzled 16-KB weight tiles
+  DevBuf d_wtiles_bwd;                 // the same tiles tap-mirrored and transposed (ci <-> co): backward data = forward kernel
   size_t wtile_copy_bytes = 0;
   DevBuf d_act[3];                     // bf16 path: activation ping-pong [max_batch*42][128]
   DevBuf d_stem_tab;                   // bf16 path: the stem's 3 x 64 x 128 partial-sum table (k_stem_bf16)
@@ -227,6 +228,22 @@ struct azb_nnet {
               t[byte / 2] = bf16_rne(w[static_cast<size_t>(half * 64 + k) * kNetC + n]);
             }
         }
+      {  // backward-data tiles: dX[r][ci] = sum_tap' sum_co dZ[r + s(tap')][co] W[8 - tap'][ci][co]: n = ci, k = co
+        std::vector<uint16_t> bt(n_tiles * (kTcTileBytes / 2));
+        for (int layer = 0; layer < 2 * L.R; ++layer)
+          for (int kb = 0; kb < kTcKBlocks; ++kb) {
+            uint16_t* t = bt.data() + (static_cast<size_t>(layer) * kTcKBlocks + kb) * (kTcTileBytes / 2);
+            const int tap = kb >> 1, half = kb & 1;
+            const float* w = h_params.data() + L.tower_w + (static_cast<size_t>(layer) * 9 + (8 - tap)) * kNetC * kNetC;
+            for (int n = 0; n < 128; ++n)
+              for (int k = 0; k < 64; ++k) {
+                const size_t byte = (n / 8) * 1024 + (n % 8) * 128 + (((k / 8) ^ (n % 8)) * 16) + (k % 8) * 2;
+                t[byte / 2] = bf16_rne(w[static_cast<size_t>(n) * kNetC + half * 64 + k]);
+              }
+          }
+        AZB_CUDA(d_wtiles_bwd.ensure(bt.size() * 2));
+        AZB_CUDA(cudaMemcpy(d_wtiles_bwd.p, bt.data(), bt.size() * 2, cudaMemcpyHostToDevice));
+      }
       // kTcWeightCopies replicas at different addresses: every CTA streams the same tile sequence at
       // about the same time; spreading the CTAs over replicas spreads that traffic over the L2 slices
       wtile_copy_bytes = tiles.size() * 2;
@@ -237,6 +254,7 @@ struct azb_nnet {
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
       {
         std::vector<float> tab(3 * 64 * kNetC);
@@ -1189,6 +1207,76 @@ int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_p
   *ms_per_pass = ms / iters;
   return AZB_OK;
 }
+namespace {
+// a padded bf16 device copy of an fp32 dense host tensor [n_pos][42][128] (zero rows included), or an empty buffer
+int upload_padded(const float* host, uint64_t n_pos, DevBuf& stage, DevBuf& out) {
+  const size_t dense = static_cast<size_t>(n_pos) * kCells * kNetC, padded_bytes = (static_cast<size_t>(n_pos) + 8) * kActPadded.pos_rows * kNetC * 2;
+  AZB_CUDA(out.ensure(padded_bytes));
+  AZB_CUDA(cudaMemset(out.p, 0, out.bytes));
+  if (!host) return AZB_OK;
+  AZB_CUDA(stage.ensure(dense * 4));
+  AZB_CUDA(cudaMemcpy(stage.p, host, dense * 4, cudaMemcpyHostToDevice));
+  k_dense_f32_to_padded_bf16<<<static_cast<unsigned>((dense + 255) / 256), 256>>>(stage.as<float>(), static_cast<uint32_t>(n_pos),
+                                                                                  out.as<__nv_bfloat16>());
+  AZB_CUDA(cudaGetLastError());
+  return AZB_OK;
+}
+}  // namespace
+
+int azb_nnet_conv_hook(azb_nnet* n, int32_t layer, int32_t mode, const float* x, const float* residual, const float* mask,
+                       uint64_t n_pos, float* out) {
+  if (!n || !x || !out || n_pos == 0 || n_pos > (1u << 20)) return fail(AZB_ERR_INVALID, "bad argument");
+  if (n->cfg.precision != AZB_NNET_BF16_TC || tc_mode() != 3) return fail(AZB_ERR_UNSUPPORTED, "needs the default tensor-core tower");
+  if (layer < 0 || layer >= 2 * n->L.R || mode < 0 || mode > 1) return fail(AZB_ERR_INVALID, "layer / mode out of range");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  DevBuf stage, dx, dres, dmask, dout;
+  int rc;
+  if ((rc = upload_padded(x, n_pos, stage, dx)) || (rc = upload_padded(nullptr, n_pos, stage, dout))) return rc;
+  if (residual && (rc = upload_padded(residual, n_pos, stage, dres))) return rc;
+  if (mask && (rc = upload_padded(mask, n_pos, stage, dmask))) return rc;
+  CUtensorMap map;
+  if ((rc = encode_act_map_rows(&map, dx.p, dx.bytes))) return rc;
+  ConvTcArgs a{};
+  a.in = dx.as<__nv_bfloat16>();
+  a.residual = residual ? dres.as<__nv_bfloat16>() : nullptr;
+  a.mask = mask ? dmask.as<__nv_bfloat16>() : nullptr;
+  a.out = dout.as<__nv_bfloat16>();
+  a.mode = mode;
+  a.w_tiles = (mode == 0 ? n->d_wtiles.as<uint8_t>() : n->d_wtiles_bwd.as<uint8_t>()) + static_cast<size_t>(layer) * kTcKBlocks * kTcTileBytes;
+  a.bias = n->d_params.as<float>() + n->L.tower_b + static_cast<size_t>(layer) * kNetC;
+  a.max_batch = static_cast<uint32_t>(n_pos);
+  const uint32_t pair_tiles = (a.max_batch * kActPadded.pos_rows + kT2PairRows - 1) / kT2PairRows;
+  k_conv3x3_tc3<<<2u * std::min<uint32_t>(pair_tiles, 64u), kTcThreads, kT3SmemBytes>>>(a, map);
+  AZB_CUDA(cudaGetLastError());
+  const size_t dense = static_cast<size_t>(n_pos) * kCells * kNetC;
+  AZB_CUDA(stage.ensure(dense * 4));
+  k_padded_bf16_to_dense_f32<<<static_cast<unsigned>((dense + 255) / 256), 256>>>(dout.as<__nv_bfloat16>(), a.max_batch, stage.as<float>());
+  AZB_CUDA(cudaGetLastError());
+  AZB_CUDA(cudaMemcpy(out, stage.p, dense * 4, cudaMemcpyDeviceToHost));
+  return AZB_OK;
+}
+
+int azb_nnet_wgrad_hook(azb_nnet* n, const float* x, const float* dz, uint64_t n_pos, float* dw) {
+  if (!n || !x || !dz || !dw || n_pos == 0 || n_pos > (1u << 20)) return fail(AZB_ERR_INVALID, "bad argument");
+  if (n->cfg.precision != AZB_NNET_BF16_TC || tc_mode() != 3) return fail(AZB_ERR_UNSUPPORTED, "needs the default tensor-core tower");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  DevBuf stage, dx, ddz, ddw;
+  int rc;
+  if ((rc = upload_padded(x, n_pos, stage, dx)) || (rc = upload_padded(dz, n_pos, stage, ddz))) return rc;
+  CUtensorMap mx, mz;
+  if ((rc = encode_act_map_rows(&mx, dx.p, dx.bytes)) || (rc = encode_act_map_rows(&mz, ddz.p, ddz.bytes))) return rc;
+  const size_t nw = static_cast<size_t>(9) * kNetC * kNetC;
+  AZB_CUDA(ddw.ensure(nw * 4));
+  AZB_CUDA(cudaMemset(ddw.p, 0, nw * 4));
+  WgradArgs g{};
+  g.dw = ddw.as<float>();
+  g.n_pos = static_cast<uint32_t>(n_pos);
+  k_conv3x3_wgrad<<<147, kWgThreads, kWgSmemBytes>>>(g, mx, mz);
+  AZB_CUDA(cudaGetLastError());
+  AZB_CUDA(cudaMemcpy(dw, ddw.p, nw * 4, cudaMemcpyDeviceToHost));
+  return AZB_OK;
+}
+
 int azb_coach_set_nnet(azb_coach* c, azb_nnet* n) {
   if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
   if (n && n->cfg.device != c->cfg.device) return fail(AZB_ERR_INVALID, "network and coach live on different devices");

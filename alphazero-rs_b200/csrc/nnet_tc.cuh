@@ -148,6 +148,10 @@ struct ConvTcArgs {
   const uint32_t* count;          // positions this round (device), or nullptr
   uint32_t max_batch;
   unsigned long long* dbg;        // diagnostic (AZB200_TC_DEBUG=1): per-role cycle counters of CTA pair 0, or nullptr
+  // k_conv3x3_tc3 only.  mode 0 (forward): out = ReLU(acc + bias [+ residual]).  mode 1 (backward data, run with the
+  // tap-mirrored / transposed weight tiles): out = (acc [+ residual]) * (mask > 0), no bias, no ReLU.
+  int mode;
+  const __nv_bfloat16* mask;      // [rows][128] forward activation whose sign gates the gradient, or nullptr
 };
 
 // CL = CTAs per cluster.  With CL > 1 the CTAs of a cluster walk their M tiles in lock-step and share
@@ -781,11 +785,16 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       const uint32_t rem = m % kActPadded.pos_rows;
       const bool real = m < rows && (rem & 7u) != 7u && rem < 48u;  // not the zero column, not the zero row
       // the residual (64 channels = 8 x 16 B of my row) is requested before the accumulator is waited for
-      uint4 res[8];
+      uint4 res[8], msk[8];
       if (real && g.residual) {
         const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + half * 64);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
+      }
+      if (real && g.mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(g.mask + static_cast<size_t>(m) * kNetC + half * 64);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) msk[jj] = mp[jj];
       }
       AZB_DBG_T0();
       mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
@@ -804,16 +813,27 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
           const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c8 * 8 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           const uint32_t rw[4] = {res[c8].x, res[c8].y, res[c8].z, res[c8].w};
+          const uint32_t mw[4] = {msk[c8].x, msk[c8].y, msk[c8].z, msk[c8].w};
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float x0 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e]) + bb[2 * e];
-            float x1 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e + 1]) + bb[2 * e + 1];
+            float x0 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e]), x1 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e + 1]);
+            if (g.mode == 0) {
+              x0 += bb[2 * e];
+              x1 += bb[2 * e + 1];
+            }
             if (g.residual) {
               x0 += __uint_as_float(rw[e] << 16);
               x1 += __uint_as_float(rw[e] & 0xFFFF0000u);
             }
-            const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+            if (g.mode == 0) {
+              x0 = fmaxf(x0, 0.0f);
+              x1 = fmaxf(x1, 0.0f);
+            } else if (g.mask) {  // d ReLU: the gradient passes where the forward activation was positive
+              if (!(__uint_as_float(mw[e] << 16) > 0.0f)) x0 = 0.0f;
+              if (!(__uint_as_float(mw[e] & 0xFFFF0000u) > 0.0f)) x1 = 0.0f;
+            }
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&p2);
           }
           op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -887,6 +907,146 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   __syncthreads();
   cluster_sync_all();
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+// ================================================================================================
+// Weight gradient of the 3x3 convolution on tcgen05 (building block of the training step):
+//   dW[tap][ci][co] = sum over padded rows R of X[R + 8*dy + dx][ci] * dZ[R][co]
+// In the padded layout the zero rows contribute nothing, so this is one plain product per tap,
+// D[M = ci][N = co] += A[ci][K = row] * B[co][K = row], with BOTH operands MN-major: a stage half is
+// [row][64 channels] = 128-byte rows, i.e. the canonical MN-major SWIZZLE_128B atom (64 elements along M/N x 8
+// rows along K, 1024 B), the next 8 rows 1024 B further (SBO), the other 64 channels in the other half of the stage
+// (LBO).  Per 128-row chunk a CTA loads X (with halo, as the forward pass) and dZ once (4 x 20 KB, 2-D TMA) and
+// issues 8 MMAs (K = 16 rows each) per tap: M128 N128 K16, cta_group::1, the tap's accumulator in TMEM.
+// TMEM holds 4 such accumulators, so the 9 taps are split over 3 CTA groups (3 taps = 384 columns each); CTA b
+// works on taps 3*(b % 3) .. +2 and on the row chunks b / 3, b / 3 + grid / 3, ...; at the end every CTA adds its
+// partial sums to dW in HBM with fp32 atomics.
+// ================================================================================================
+constexpr uint32_t kWgStageBytes = 4 * kT3HalfBytes;                     // X half 0/1, dZ half 0/1: 80 KB
+constexpr int kWgStages = 2;
+constexpr uint32_t kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
+constexpr int kWgThreads = 192;                                          // warps 0-3 epilogue, 4 MMA, 5 TMA producer + TMEM alloc
+// A and B MN-major (bits 15, 16), D = F32, A = B = BF16, N = 128, M = 128
+constexpr uint32_t kIdescBf16M128N128MN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// MN-major SWIZZLE_128B descriptor: LBO = distance between the two 64-channel halves, SBO = 8 rows = 1024 B
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__device__ __forceinline__ void tma_tile2d(uint32_t dst, const CUtensorMap* tmap, uint32_t mbar, int c, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c), "r"(row)
+               : "memory");
+}
+struct WgradArgs {
+  float* dw;            // [9][128 ci][128 co] fp32, accumulated into (zero it first)
+  uint32_t n_pos;
+};
+__global__ void __launch_bounds__(kWgThreads, 1)
+k_conv3x3_wgrad(WgradArgs g, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dz) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto stage_x = [&](int s, int half) { return base + s * kWgStageBytes + half * kT3HalfBytes; };
+  auto stage_dz = [&](int s, int half) { return base + s * kWgStageBytes + (2 + half) * kT3HalfBytes; };
+  const uint32_t bars = base + kWgStages * kWgStageBytes;
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 16u + 8u * s; };
+  const uint32_t bar_done = bars + 32u;
+  const uint32_t tmem_slot = bars + 40u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tg = blockIdx.x % 3u, slice = blockIdx.x / 3u, n_slices = gridDim.x / 3u;
+  const uint32_t rows = g.n_pos * kActPadded.pos_rows;
+  const uint32_t n_chunks = (rows + kTcTileM - 1) / kTcTileM;
+  const uint32_t iters = slice < n_chunks && blockIdx.x < 3u * n_slices ? (n_chunks - slice + n_slices - 1) / n_slices : 0u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 5) {
+    if (lane == 0) {
+      for (uint32_t i = 0; i < iters; ++i) {
+        const int s = i % kWgStages;
+        mbar_wait(bar_empty(s), ((i / kWgStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full(s), kWgStageBytes);
+        const int r0 = static_cast<int>((slice + i * n_slices) * kTcTileM) - kT3HaloRows;
+        tma_tile2d(stage_x(s, 0), &tmap_x, bar_full(s), 0, r0);
+        tma_tile2d(stage_x(s, 1), &tmap_x, bar_full(s), kTcBlockK, r0);
+        tma_tile2d(stage_dz(s, 0), &tmap_dz, bar_full(s), 0, r0);
+        tma_tile2d(stage_dz(s, 1), &tmap_dz, bar_full(s), kTcBlockK, r0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (uint32_t i = 0; i < iters; ++i) {
+        const int s = i % kWgStages;
+        mbar_wait(bar_full(s), (i / kWgStages) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t3 = 0; t3 < 3; ++t3) {
+          const int tap = static_cast<int>(tg) * 3 + t3, shift = kT3HaloRows + (tap / 3 - 1) * 8 + (tap % 3 - 1);
+#pragma unroll
+          for (int j = 0; j < kTcTileM / 16; ++j) {  // K = 16 rows per MMA
+            const uint64_t ad = umma_desc_sw128_mn(stage_x(s, 0) + (shift + 16 * j) * 128, kT3HalfBytes);
+            const uint64_t bd = umma_desc_sw128_mn(stage_dz(s, 0) + (kT3HaloRows + 16 * j) * 128, kT3HalfBytes);
+            umma_bf16(tmem_base + t3 * 128u, ad, bd, kIdescBf16M128N128MN, (i | static_cast<uint32_t>(j)) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty(s));
+      }
+      umma_commit(bar_done);
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM lane = ci (warp q: lanes 32q..), columns = co: add this CTA's partial sums to dW =====
+    if (iters > 0) {
+      mbar_wait(bar_done, 0u);
+      tc_fence_after();
+      const int q = warp;
+      const uint32_t ci = q * 32 + lane;
+      for (int t3 = 0; t3 < 3; ++t3) {
+        float* dst = g.dw + (static_cast<size_t>(tg * 3 + t3) * kNetC + ci) * kNetC;
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t3 * 128u + ch * 32u, acc);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) atomicAdd(dst + ch * 32 + c, __uint_as_float(acc[c]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// fp32 dense [pos][42][128] <-> bf16 padded [pos][56][128] (test hooks and, later, the training step's inputs)
+__global__ void k_dense_f32_to_padded_bf16(const float* __restrict__ in, uint32_t n_pos, __nv_bfloat16* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n_pos) * kCells * kNetC) return;
+  const uint32_t c = i % kNetC, m = static_cast<uint32_t>(i / kNetC), pos = m / kCells, cell = m % kCells;
+  out[ActLayout{56u, 8u}.row(pos, cell / 7, cell % 7) * kNetC + c] = __float2bfloat16_rn(in[i]);
+}
+__global__ void k_padded_bf16_to_dense_f32(const __nv_bfloat16* __restrict__ in, uint32_t n_pos, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n_pos) * kCells * kNetC) return;
+  const uint32_t c = i % kNetC, m = static_cast<uint32_t>(i / kNetC), pos = m / kCells, cell = m % kCells;
+  out[i] = __bfloat162float(in[ActLayout{56u, 8u}.row(pos, cell / 7, cell % 7) * kNetC + c]);
 }
 
 // Stem: conv3x3(2 -> 128) + ReLU from the bitboard planes, bf16 out.  The two input planes are

@@ -192,6 +192,16 @@ int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count);
 /* Diagnostic: device-only timing of `iters` forward passes over `batch` synthetic positions that are
  * already resident in HBM (CUDA events on the launching stream).  ms_per_pass is the mean. */
 int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_per_pass);
+/* Building blocks of NNet::train (src/nnet.rs:38) on the tensor cores, exposed as hooks so that they
+ * are pinned by tests before the training step exists.  Activations are fp32 [n_pos][42 cells][128 channels] on the
+ * host (quantised to bf16 on the device); `layer` = 0 .. 2*blocks-1 indexes the tower's 3x3 convolutions.
+ *   mode 0: out = ReLU(conv(x) + bias [+ residual])                         (the forward kernel itself)
+ *   mode 1: out = (conv^T(x) [+ residual]) * (mask > 0)                     (backward data: dX from dZ)
+ * residual and mask may be NULL.  Needs the default tensor-core tower (AZB200_TC_PAIR unset). */
+int azb_nnet_conv_hook(azb_nnet* n, int32_t layer, int32_t mode, const float* x, const float* residual,
+                       const float* mask, uint64_t n_pos, float* out);
+/* dW[9 taps][128 ci][128 co] (fp32) = sum over rows of x[row shifted by the tap][ci] * dz[row][co]. */
+int azb_nnet_wgrad_hook(azb_nnet* n, const float* x, const float* dz, uint64_t n_pos, float* dw);
 /* The network that evaluates leaves when cfg.evaluator == AZB_EVAL_NNET (the NNet the
  * reference's inference thread owns, async_mcts.rs:125).  The coach does not own it. */
 int azb_coach_set_nnet(azb_coach* c, azb_nnet* n);
