@@ -88,6 +88,10 @@ class NnetConfig(C.Structure):
                 ("reserved", C.c_int32), ("seed", C.c_uint64)]
 
 
+class TrainConfig(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
 NNET_BF16_TC, NNET_FP32 = 0, 1
 
 
@@ -143,6 +147,11 @@ def _load():
         "azb_nnet_set_params": [vp, vp, u64],
         "azb_coach_set_nnet": [vp, vp],
         "azb_nnet_benchmark": [vp, u64, u32, C.POINTER(C.c_double)],
+        "azb_nnet_train_begin": [vp, vp, vp, vp, u64, vp],
+        "azb_nnet_grads": [vp, vp, u64],
+        "azb_nnet_set_grads": [vp, vp, u64],
+        "azb_nnet_train_apply": [vp, vp],
+        "azb_nnet_train": [vp, vp, vp, vp, u64, vp, vp],
         "azb_nnet_conv_hook": [vp, C.c_int32, C.c_int32, vp, vp, vp, u64, vp],
         "azb_nnet_wgrad_hook": [vp, vp, vp, u64, vp],
         "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
@@ -446,6 +455,42 @@ class NNet:
         v = np.zeros(n, np.float32)
         _check(lib.azb_nnet_predict(self._h, _ptr(boards), n, model_id, _ptr(pi), _ptr(v)))
         return pi, v
+
+    def train_begin(self, boards, pis, vs):
+        """Forward + loss + backward of NNet::train (nnet.rs:38); returns (policy loss, value loss); gradients stay on the device."""
+        boards = np.ascontiguousarray(boards, np.float32).reshape(-1, 2, 6, 7)
+        pis = np.ascontiguousarray(pis, np.float32).reshape(-1, 7)
+        vs = np.ascontiguousarray(vs, np.float32).reshape(-1)
+        assert len(boards) == len(pis) == len(vs)
+        loss = np.zeros(2, np.float32)
+        _check(lib.azb_nnet_train_begin(self._h, _ptr(boards), _ptr(pis), _ptr(vs), len(vs), _ptr(loss)))
+        return float(loss[0]), float(loss[1])
+
+    def grads(self):
+        out = np.zeros(self.num_params(), np.float32)
+        _check(lib.azb_nnet_grads(self._h, _ptr(out), len(out)))
+        return out
+
+    def set_grads(self, g):
+        g = np.ascontiguousarray(g, np.float32)
+        _check(lib.azb_nnet_set_grads(self._h, _ptr(g), len(g)))
+
+    def train_apply(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        cfg = TrainConfig(lr, beta1, beta2, eps)
+        _check(lib.azb_nnet_train_apply(self._h, C.byref(cfg)))
+
+    def train(self, samples, lr=1e-3, dist=None, **adam):
+        """NNet::train on SOATrainingSamples (boards, pis, vs).  With `dist` (an initialised torch.distributed) the step is
+        data parallel: every rank trains on its own shard, the gradients are averaged with all_reduce before Adam."""
+        loss = self.train_begin(*samples)
+        if dist is not None and dist.get_world_size() > 1:
+            import torch
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            g = torch.from_numpy(self.grads()).to(dev)
+            dist.all_reduce(g)
+            self.set_grads((g / dist.get_world_size()).cpu().numpy())
+        self.train_apply(lr=lr, **adam)
+        return loss
 
     def conv_hook(self, layer, mode, x, residual=None, mask=None):
         """Tower convolution `layer` on the tensor cores: mode 0 forward, mode 1 backward data (see azb200.h).

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "nnet.cuh"
 #include "nnet_tc.cuh"
+#include "nnet_train.cuh"
 #include "rounds.cuh"
 
 using namespace azb;
@@ -202,6 +203,16 @@ struct azb_nnet {
   void* act_map_ptr[3] = {nullptr, nullptr, nullptr};
   size_t act_map_bytes[3] = {0, 0, 0};
   DevBuf d_feat, d_states, d_pi, d_v;  // azb_nnet_predict staging
+  // training step (azb_nnet_train_*): every layer's output is kept for the backward pass
+  std::vector<DevBuf> tr_act;          // [2R + 1] padded bf16: stem output, then every tower convolution's output
+  DevBuf tr_g[3];                      // activation gradients (padded bf16), rotated through the backward pass
+  std::vector<CUtensorMap> tr_act_map; // TMA descriptors of tr_act / tr_g (re-encoded when a buffer moves)
+  CUtensorMap tr_g_map[3];
+  size_t tr_bytes = 0;
+  uint32_t tr_batch = 0;
+  DevBuf d_grad, d_adam_m, d_adam_v, d_loss, d_pis, d_vs;
+  uint64_t adam_t = 0;
+  bool grads_ready = false;
   static uint16_t bf16_rne(float f) {
     uint32_t u;
     std::memcpy(&u, &f, 4);
@@ -1207,6 +1218,196 @@ int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_p
   *ms_per_pass = ms / iters;
   return AZB_OK;
 }
+namespace {
+int tc3_pairs() {
+  static int n = -1;
+  if (n < 0) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(148u);
+    qc.blockDim = dim3(kTcThreads);
+    qc.dynamicSmemBytes = kT3SmemBytes;
+    int k = 0;
+    if (cudaOccupancyMaxActiveClusters(&k, k_conv3x3_tc3, &qc) != cudaSuccess) { cudaGetLastError(); k = 0; }
+    n = k;
+  }
+  return n;
+}
+// one k_conv3x3_tc3 launch on padded buffers of the training step
+int train_conv(azb_nnet* n, int layer, int mode, const DevBuf& in, const CUtensorMap& in_map, const DevBuf* residual, const DevBuf* mask,
+               DevBuf& out, uint32_t B) {
+  ConvTcArgs a{};
+  a.in = in.as<__nv_bfloat16>();
+  a.residual = residual ? residual->as<__nv_bfloat16>() : nullptr;
+  a.mask = mask ? mask->as<__nv_bfloat16>() : nullptr;
+  a.out = out.as<__nv_bfloat16>();
+  a.mode = mode;
+  a.w_tiles = (mode == 0 ? n->d_wtiles.as<uint8_t>() : n->d_wtiles_bwd.as<uint8_t>()) + static_cast<size_t>(layer) * kTcKBlocks * kTcTileBytes;
+  a.bias = n->d_params.as<float>() + n->L.tower_b + static_cast<size_t>(layer) * kNetC;
+  a.max_batch = B;
+  const uint32_t pair_tiles = (B * kActPadded.pos_rows + kT2PairRows - 1) / kT2PairRows;
+  const int pairs = tc3_pairs();
+  if (pairs <= 0) return fail(AZB_ERR_CUDA, "no co-resident CTA pair for k_conv3x3_tc3");
+  k_conv3x3_tc3<<<2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(pairs)), kTcThreads, kT3SmemBytes>>>(a, in_map);
+  AZB_CUDA(cudaGetLastError());
+  return AZB_OK;
+}
+}  // namespace
+
+// NNet::train (src/nnet.rs:38), first half: forward with every layer kept, loss (softmax cross-entropy on pi + squared
+// error on v, means over the batch), backward; the gradients stay on the device (azb_nnet_grads / azb_nnet_set_grads let
+// a data-parallel caller all-reduce them), azb_nnet_train_apply is the optimiser step.
+int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count, float* loss_out) {
+  if (!n || !boards || !pis || !vs || count == 0 || count > (1u << 20)) return fail(AZB_ERR_INVALID, "bad argument");
+  if (n->cfg.precision != AZB_NNET_BF16_TC || tc_mode() != 3) return fail(AZB_ERR_UNSUPPORTED, "training needs the default tensor-core tower");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  const uint32_t B = static_cast<uint32_t>(count);
+  const int nl = 2 * n->L.R;
+  const NetLayout& L = n->L;
+  // inputs
+  AZB_CUDA(n->d_feat.ensure(count * 84 * 4));
+  AZB_CUDA(n->d_states.ensure(count * 16));
+  AZB_CUDA(n->d_pis.ensure(count * 7 * 4));
+  AZB_CUDA(n->d_vs.ensure(count * 4));
+  AZB_CUDA(cudaMemcpy(n->d_feat.p, boards, count * 84 * 4, cudaMemcpyHostToDevice));
+  AZB_CUDA(cudaMemcpy(n->d_pis.p, pis, count * 7 * 4, cudaMemcpyHostToDevice));
+  AZB_CUDA(cudaMemcpy(n->d_vs.p, vs, count * 4, cudaMemcpyHostToDevice));
+  k_features_to_bb<<<(B + 127) / 128, 128>>>(n->d_feat.as<float>(), B, n->d_states.as<uint4>());
+  // buffers: zeroed once when (re)allocated, so that the padded layout's zero rows stay zero
+  const size_t bytes = (static_cast<size_t>(B) + 8) * kActPadded.pos_rows * kNetC * 2;
+  if (n->tr_act.size() != static_cast<size_t>(nl + 1) || n->tr_bytes < bytes) {
+    n->tr_act.clear();
+    n->tr_act.resize(nl + 1);
+    n->tr_act_map.resize(nl + 1);
+    for (int i = 0; i <= nl; ++i) {
+      AZB_CUDA(n->tr_act[i].ensure(bytes));
+      AZB_CUDA(cudaMemset(n->tr_act[i].p, 0, bytes));
+      const int rc = encode_act_map_rows(&n->tr_act_map[i], n->tr_act[i].p, bytes);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < 3; ++i) {
+      n->tr_g[i].release();
+      AZB_CUDA(n->tr_g[i].ensure(bytes));
+      AZB_CUDA(cudaMemset(n->tr_g[i].p, 0, bytes));
+      const int rc = encode_act_map_rows(&n->tr_g_map[i], n->tr_g[i].p, bytes);
+      if (rc) return rc;
+    }
+    n->tr_bytes = bytes;
+    n->tr_batch = B;
+  }
+  if (n->tr_batch != B) {  // rows of a larger earlier batch would leak into the weight gradients' last row chunk
+    for (auto& b : n->tr_act) AZB_CUDA(cudaMemset(b.p, 0, b.bytes));
+    for (auto& b : n->tr_g) AZB_CUDA(cudaMemset(b.p, 0, b.bytes));
+    n->tr_batch = B;
+  }
+  AZB_CUDA(n->d_grad.ensure(L.total * 4));
+  AZB_CUDA(n->d_loss.ensure(8));
+  AZB_CUDA(cudaMemset(n->d_grad.p, 0, L.total * 4));
+  AZB_CUDA(cudaMemset(n->d_loss.p, 0, 8));
+  const float* prm = n->d_params.as<float>();
+  float* grad = n->d_grad.as<float>();
+  // ---- forward, every layer kept ----
+  const size_t total = static_cast<size_t>(B) * kCells * (kNetC / 8);
+  k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes>>>(
+      prm, L, n->d_stem_tab.as<float>(), n->d_states.as<uint4>(), nullptr, B, n->tr_act[0].as<__nv_bfloat16>(), kActPadded);
+  AZB_CUDA(cudaGetLastError());
+  for (int l = 0; l < nl; ++l) {
+    const int rc = train_conv(n, l, 0, n->tr_act[l], n->tr_act_map[l], (l & 1) ? &n->tr_act[l - 1] : nullptr, nullptr, n->tr_act[l + 1], B);
+    if (rc) return rc;
+  }
+  // ---- heads: loss and gradients; g = dL/d(pre-activation of the last convolution) ----
+  int gi = 0;  // index of the current gradient buffer
+  AZB_CUDA(cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadsBwdSmem)));
+  k_heads_backward<<<std::min<uint32_t>(B, 148u * 4u), 128, kHeadsBwdSmem>>>(prm, L, n->tr_act[nl].as<__nv_bfloat16>(), B, n->d_pis.as<float>(),
+                                                                            n->d_vs.as<float>(), 1.0f / static_cast<float>(B), kActPadded,
+                                                                            n->tr_g[gi].as<__nv_bfloat16>(), grad, n->d_loss.as<float>());
+  AZB_CUDA(cudaGetLastError());
+  // ---- backward through the tower ----
+  const uint32_t rows = B * kActPadded.pos_rows;
+  int skip = -1;
+  for (int l = nl - 1; l >= 0; --l) {
+    WgradArgs wg{};
+    wg.dw = grad + L.tower_w + static_cast<size_t>(l) * 9 * kNetC * kNetC;
+    wg.n_pos = B;
+    k_conv3x3_wgrad<<<147, kWgThreads, kWgSmemBytes>>>(wg, n->tr_act_map[l], n->tr_g_map[gi]);
+    k_colsum_bf16<<<148, 256>>>(n->tr_g[gi].as<__nv_bfloat16>(), rows, grad + L.tower_b + static_cast<size_t>(l) * kNetC);
+    AZB_CUDA(cudaGetLastError());
+    // gradient of the previous layer's pre-activation: conv^T(g) [+ the block's skip path], gated by that layer's ReLU
+    int go = 0;
+    while (go == gi || go == skip) ++go;
+    const int rc = train_conv(n, l, 1, n->tr_g[gi], n->tr_g_map[gi], (l & 1) ? nullptr : &n->tr_g[skip], &n->tr_act[l], n->tr_g[go], B);
+    if (rc) return rc;
+    if (l & 1) skip = gi; else skip = -1;
+    if (!(l & 1)) { /* the skip buffer is free again */ }
+    gi = go;
+  }
+  k_stem_backward<<<148 * 2, 128>>>(n->d_states.as<uint4>(), n->tr_g[gi].as<__nv_bfloat16>(), B, kActPadded, grad + L.stem_w, grad + L.stem_b);
+  AZB_CUDA(cudaGetLastError());
+  float hl[2];
+  AZB_CUDA(cudaMemcpy(hl, n->d_loss.p, 8, cudaMemcpyDeviceToHost));
+  if (loss_out) { loss_out[0] = hl[0]; loss_out[1] = hl[1]; }
+  n->grads_ready = true;
+  return AZB_OK;
+}
+
+int azb_nnet_grads(azb_nnet* n, float* out, uint64_t count) {
+  if (!n || !out || !n->grads_ready || count != n->L.total) return fail(AZB_ERR_INVALID, "no gradients / wrong count");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  AZB_CUDA(cudaMemcpy(out, n->d_grad.p, count * 4, cudaMemcpyDeviceToHost));
+  return AZB_OK;
+}
+int azb_nnet_set_grads(azb_nnet* n, const float* in, uint64_t count) {
+  if (!n || !in || count != n->L.total) return fail(AZB_ERR_INVALID, "wrong count");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  AZB_CUDA(n->d_grad.ensure(count * 4));
+  AZB_CUDA(cudaMemcpy(n->d_grad.p, in, count * 4, cudaMemcpyHostToDevice));
+  n->grads_ready = true;
+  return AZB_OK;
+}
+
+// Adam step on the fp32 master parameters, then everything derived from them (bf16 operand tiles forward / backward,
+// the stem table, the head weights in the constant bank, the host copy).
+int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg) {
+  if (!n || !cfg || !n->grads_ready) return fail(AZB_ERR_INVALID, "no gradients");
+  if (n->cfg.precision != AZB_NNET_BF16_TC) return fail(AZB_ERR_UNSUPPORTED, "training needs the tensor-core tower");
+  AZB_CUDA(cudaSetDevice(n->cfg.device));
+  const size_t N = n->L.total;
+  if (n->d_adam_m.bytes < N * 4) {
+    AZB_CUDA(n->d_adam_m.ensure(N * 4));
+    AZB_CUDA(n->d_adam_v.ensure(N * 4));
+    AZB_CUDA(cudaMemset(n->d_adam_m.p, 0, N * 4));
+    AZB_CUDA(cudaMemset(n->d_adam_v.p, 0, N * 4));
+    n->adam_t = 0;
+  }
+  n->adam_t++;
+  const float c1 = 1.0f - std::pow(cfg->beta1, static_cast<float>(n->adam_t)), c2 = 1.0f - std::pow(cfg->beta2, static_cast<float>(n->adam_t));
+  k_adam<<<static_cast<unsigned>((N + 255) / 256), 256>>>(n->d_params.as<float>(), n->d_grad.as<float>(), n->d_adam_m.as<float>(),
+                                                         n->d_adam_v.as<float>(), N, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, c1, c2);
+  const size_t nt = static_cast<size_t>(2 * n->L.R) * kTcKBlocks * 128 * 64;
+  k_build_tiles<<<static_cast<unsigned>((nt + 255) / 256), 256>>>(n->d_params.as<float>(), n->L, n->d_wtiles.as<uint16_t>(),
+                                                                 n->d_wtiles_bwd.as<uint16_t>());
+  k_build_stem_table<<<(3 * 64 * kNetC + 255) / 256, 256>>>(n->d_params.as<float>(), n->L, n->d_stem_tab.as<float>());
+  AZB_CUDA(cudaGetLastError());
+  for (int c = 1; c < kTcWeightCopies; ++c)  // the replicas the single-CTA kernel streams from
+    AZB_CUDA(cudaMemcpy(n->d_wtiles.as<uint8_t>() + c * n->wtile_copy_bytes, n->d_wtiles.p, n->wtile_copy_bytes, cudaMemcpyDeviceToDevice));
+  AZB_CUDA(cudaMemcpy(n->h_params.data(), n->d_params.p, N * 4, cudaMemcpyDeviceToHost));
+  for (int ci = 0; ci < kNetC; ++ci) {
+    n->head_w.w[ci][0] = n->h_params[n->L.pol_w + ci * 2 + 0];
+    n->head_w.w[ci][1] = n->h_params[n->L.pol_w + ci * 2 + 1];
+    n->head_w.w[ci][2] = n->h_params[n->L.val_w + ci];
+  }
+  n->head_w.b[0] = n->h_params[n->L.pol_b + 0];
+  n->head_w.b[1] = n->h_params[n->L.pol_b + 1];
+  n->head_w.b[2] = n->h_params[n->L.val_b];
+  n->grads_ready = false;
+  return AZB_OK;
+}
+
+int azb_nnet_train(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count, const azb_train_config* cfg,
+                   float* loss_out) {
+  const int rc = azb_nnet_train_begin(n, boards, pis, vs, count, loss_out);
+  return rc ? rc : azb_nnet_train_apply(n, cfg);
+}
+
 namespace {
 // a padded bf16 device copy of an fp32 dense host tensor [n_pos][42][128] (zero rows included), or an empty buffer
 int upload_padded(const float* host, uint64_t n_pos, DevBuf& stage, DevBuf& out) {

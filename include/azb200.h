@@ -192,6 +192,24 @@ int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count);
 /* Diagnostic: device-only timing of `iters` forward passes over `batch` synthetic positions that are
  * already resident in HBM (CUDA events on the launching stream).  ms_per_pass is the mean. */
 int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_per_pass);
+/* NNet::train (src/nnet.rs:38: train((boards[N,2,6,7], pis[N,7], vs[N]), prev_id, id)).  Loss and optimiser as the
+ * reference's connect_four_net.py:102-112: softmax cross-entropy on pi + mean squared error on v (means over the
+ * batch), Adam.  Mixed precision: fp32 master parameters and gradients, bf16 tower on the tensor cores.
+ *   azb_nnet_train_begin : forward (every layer kept), loss -> loss_out[2] = {policy, value}, backward; the gradients stay on
+ *                          the device;
+ *   azb_nnet_grads / azb_nnet_set_grads : read / replace them (count = azb_nnet_num_params): the seam where a data-parallel
+ *                          caller all-reduces (NCCL / gloo) and divides by the number of ranks;
+ *   azb_nnet_train_apply : one Adam step, then every derived form of the weights is rebuilt on the device;
+ *   azb_nnet_train       : begin + apply. */
+typedef struct azb_train_config {
+  float lr, beta1, beta2, eps; /* reference: lr 1e-3; TF defaults 0.9, 0.999, 1e-8 */
+} azb_train_config;
+int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count, float* loss_out);
+int azb_nnet_grads(azb_nnet* n, float* out, uint64_t count);
+int azb_nnet_set_grads(azb_nnet* n, const float* in, uint64_t count);
+int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg);
+int azb_nnet_train(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count,
+                   const azb_train_config* cfg, float* loss_out);
 /* Building blocks of NNet::train (src/nnet.rs:38) on the tensor cores, exposed as hooks so that they
  * are pinned by tests before the training step exists.  Activations are fp32 [n_pos][42 cells][128 channels] on the
  * host (quantised to bf16 on the device); `layer` = 0 .. 2*blocks-1 indexes the tower's 3x3 convolutions.
