@@ -150,6 +150,7 @@ def _load():
         "azb_nnet_train_begin": [vp, vp, vp, vp, u64, vp],
         "azb_nnet_grads": [vp, vp, u64],
         "azb_nnet_set_grads": [vp, vp, u64],
+        "azb_nnet_grads_device": [vp, C.POINTER(C.c_void_p), C.POINTER(u64)],
         "azb_nnet_train_apply": [vp, vp],
         "azb_nnet_train": [vp, vp, vp, vp, u64, vp, vp],
         "azb_nnet_conv_hook": [vp, C.c_int32, C.c_int32, vp, vp, vp, u64, vp],
@@ -191,7 +192,7 @@ class PinnedArray:
         self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def close(self):
-        if self._p:
+        if self._p and lib is not None:
             self.array = None
             lib.azb_host_free(self._p)
             self._p = C.c_void_p()
@@ -317,7 +318,7 @@ class AsyncMcts:
         _check(lib.azb_mcts_create(C.byref(self.cfg), n_trees, C.byref(self._h)))
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.azb_mcts_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -383,7 +384,7 @@ class Coach:
                    num_sim_threads=num_sim_threads, max_depth=max_depth, cpuct=cpuct, **extra)
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.azb_coach_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -441,7 +442,7 @@ class NNet:
         _check(lib.azb_nnet_create(C.byref(self.cfg), C.byref(self._h)))
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:  # (lib is None while the interpreter shuts down)
             lib.azb_nnet_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -471,6 +472,16 @@ class NNet:
         _check(lib.azb_nnet_grads(self._h, _ptr(out), len(out)))
         return out
 
+    def grads_tensor(self):
+        """The device gradient buffer as a torch tensor (no copy; valid until the next train_begin)."""
+        import torch
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(lib.azb_nnet_grads_device(self._h, C.byref(p), C.byref(n)))
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_Dev(), device=f"cuda:{self.cfg.device}")
+
     def set_grads(self, g):
         g = np.ascontiguousarray(g, np.float32)
         _check(lib.azb_nnet_set_grads(self._h, _ptr(g), len(g)))
@@ -484,11 +495,12 @@ class NNet:
         data parallel: every rank trains on its own shard, the gradients are averaged with all_reduce before Adam."""
         loss = self.train_begin(*samples)
         if dist is not None and dist.get_world_size() > 1:
-            import torch
-            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-            g = torch.from_numpy(self.grads()).to(dev)
-            dist.all_reduce(g)
-            self.set_grads((g / dist.get_world_size()).cpu().numpy())
+            if dist.get_backend() == "nccl":  # in place on the library's device buffer: NCCL over NVLink, no host round trip
+                g = self.grads_tensor()
+                dist.all_reduce(g)
+                g /= dist.get_world_size()
+            else:
+                self.set_grads(sharding.average_gradients(dist, self.grads()))
         self.train_apply(lr=lr, **adam)
         return loss
 

@@ -1260,6 +1260,8 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
   if (!n || !boards || !pis || !vs || count == 0 || count > (1u << 20)) return fail(AZB_ERR_INVALID, "bad argument");
   if (n->cfg.precision != AZB_NNET_BF16_TC || tc_mode() != 3) return fail(AZB_ERR_UNSUPPORTED, "training needs the default tensor-core tower");
   AZB_CUDA(cudaSetDevice(n->cfg.device));
+  HostTimer tm("train_begin");
+  auto lap = [&](const char* what) { if (tm.on) { cudaDeviceSynchronize(); tm.lap(what); } };
   const uint32_t B = static_cast<uint32_t>(count);
   const int nl = 2 * n->L.R;
   const NetLayout& L = n->L;
@@ -1305,6 +1307,7 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
   AZB_CUDA(cudaMemset(n->d_loss.p, 0, 8));
   const float* prm = n->d_params.as<float>();
   float* grad = n->d_grad.as<float>();
+  lap("inputs + buffers");
   // ---- forward, every layer kept ----
   const size_t total = static_cast<size_t>(B) * kCells * (kNetC / 8);
   k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes>>>(
@@ -1314,6 +1317,7 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
     const int rc = train_conv(n, l, 0, n->tr_act[l], n->tr_act_map[l], (l & 1) ? &n->tr_act[l - 1] : nullptr, nullptr, n->tr_act[l + 1], B);
     if (rc) return rc;
   }
+  lap("forward");
   // ---- heads: loss and gradients; g = dL/d(pre-activation of the last convolution) ----
   int gi = 0;  // index of the current gradient buffer
   AZB_CUDA(cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadsBwdSmem)));
@@ -1321,6 +1325,7 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
                                                                             n->d_vs.as<float>(), 1.0f / static_cast<float>(B), kActPadded,
                                                                             n->tr_g[gi].as<__nv_bfloat16>(), grad, n->d_loss.as<float>());
   AZB_CUDA(cudaGetLastError());
+  lap("heads backward");
   // ---- backward through the tower ----
   const uint32_t rows = B * kActPadded.pos_rows;
   int skip = -1;
@@ -1329,7 +1334,7 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
     wg.dw = grad + L.tower_w + static_cast<size_t>(l) * 9 * kNetC * kNetC;
     wg.n_pos = B;
     k_conv3x3_wgrad<<<147, kWgThreads, kWgSmemBytes>>>(wg, n->tr_act_map[l], n->tr_g_map[gi]);
-    k_colsum_bf16<<<148, 256>>>(n->tr_g[gi].as<__nv_bfloat16>(), rows, grad + L.tower_b + static_cast<size_t>(l) * kNetC);
+    k_colsum_bf16<<<148 * 4, 256>>>(n->tr_g[gi].as<__nv_bfloat16>(), rows, grad + L.tower_b + static_cast<size_t>(l) * kNetC);
     AZB_CUDA(cudaGetLastError());
     // gradient of the previous layer's pre-activation: conv^T(g) [+ the block's skip path], gated by that layer's ReLU
     int go = 0;
@@ -1340,8 +1345,10 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
     if (!(l & 1)) { /* the skip buffer is free again */ }
     gi = go;
   }
+  lap("tower backward");
   k_stem_backward<<<148 * 2, 128>>>(n->d_states.as<uint4>(), n->tr_g[gi].as<__nv_bfloat16>(), B, kActPadded, grad + L.stem_w, grad + L.stem_b);
   AZB_CUDA(cudaGetLastError());
+  lap("stem backward");
   float hl[2];
   AZB_CUDA(cudaMemcpy(hl, n->d_loss.p, 8, cudaMemcpyDeviceToHost));
   if (loss_out) { loss_out[0] = hl[0]; loss_out[1] = hl[1]; }
@@ -1364,12 +1371,21 @@ int azb_nnet_set_grads(azb_nnet* n, const float* in, uint64_t count) {
   return AZB_OK;
 }
 
+int azb_nnet_grads_device(azb_nnet* n, void** ptr, uint64_t* count) {
+  if (!n || !ptr || !count || !n->grads_ready) return fail(AZB_ERR_INVALID, "no gradients");
+  *ptr = n->d_grad.p;
+  *count = n->L.total;
+  return AZB_OK;
+}
+
 // Adam step on the fp32 master parameters, then everything derived from them (bf16 operand tiles forward / backward,
 // the stem table, the head weights in the constant bank, the host copy).
 int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg) {
   if (!n || !cfg || !n->grads_ready) return fail(AZB_ERR_INVALID, "no gradients");
   if (n->cfg.precision != AZB_NNET_BF16_TC) return fail(AZB_ERR_UNSUPPORTED, "training needs the tensor-core tower");
   AZB_CUDA(cudaSetDevice(n->cfg.device));
+  HostTimer tm("train_apply");
+  auto lap = [&](const char* what) { if (tm.on) { cudaDeviceSynchronize(); tm.lap(what); } };
   const size_t N = n->L.total;
   if (n->d_adam_m.bytes < N * 4) {
     AZB_CUDA(n->d_adam_m.ensure(N * 4));
@@ -1387,9 +1403,12 @@ int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg) {
                                                                  n->d_wtiles_bwd.as<uint16_t>());
   k_build_stem_table<<<(3 * 64 * kNetC + 255) / 256, 256>>>(n->d_params.as<float>(), n->L, n->d_stem_tab.as<float>());
   AZB_CUDA(cudaGetLastError());
+  lap("adam + tiles + table");
   for (int c = 1; c < kTcWeightCopies; ++c)  // the replicas the single-CTA kernel streams from
     AZB_CUDA(cudaMemcpy(n->d_wtiles.as<uint8_t>() + c * n->wtile_copy_bytes, n->d_wtiles.p, n->wtile_copy_bytes, cudaMemcpyDeviceToDevice));
+  lap("replicas");
   AZB_CUDA(cudaMemcpy(n->h_params.data(), n->d_params.p, N * 4, cudaMemcpyDeviceToHost));
+  lap("params to host");
   for (int ci = 0; ci < kNetC; ++ci) {
     n->head_w.w[ci][0] = n->h_params[n->L.pol_w + ci * 2 + 0];
     n->head_w.w[ci][1] = n->h_params[n->L.pol_w + ci * 2 + 1];

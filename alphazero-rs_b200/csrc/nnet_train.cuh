@@ -153,13 +153,28 @@ constexpr size_t kHeadsBwdSmem = (kCells * (kNetC + 1) + 84 + 42 + 64 + 8 + 8 + 
 
 // ---- bias gradient: out[c] += sum over rows of dz[row][c] (padding rows are zero) -------------------------------
 __global__ void __launch_bounds__(256) k_colsum_bf16(const __nv_bfloat16* __restrict__ dz, uint32_t rows, float* __restrict__ out) {
-  __shared__ float part[2][kNetC];
-  const int c = threadIdx.x & (kNetC - 1), h = threadIdx.x >> 7;
-  float s = 0.0f;
-  for (uint32_t r = blockIdx.x * 2u + h; r < rows; r += gridDim.x * 2u) s += __bfloat162float(dz[static_cast<size_t>(r) * kNetC + c]);
-  part[h][c] = s;
+  // 16 threads read one 256-byte row as 16-byte vectors, a CTA takes 16 rows per step; 8 fp32 partial sums per thread
+  __shared__ float part[16][kNetC];
+  const int cg = threadIdx.x & 15, rr = threadIdx.x >> 4;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t r = blockIdx.x * 16u + rr; r < rows; r += gridDim.x * 16u) {
+    const uint4 x = *reinterpret_cast<const uint4*>(dz + static_cast<size_t>(r) * kNetC + cg * 8);
+    const uint32_t wd[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[2 * k] += __uint_as_float(wd[k] << 16);
+      s[2 * k + 1] += __uint_as_float(wd[k] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[rr][cg * 8 + k] = s[k];
   __syncthreads();
-  if (h == 0) atomicAdd(out + c, part[0][c] + part[1][c]);
+  if (threadIdx.x < kNetC) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += part[i][threadIdx.x];
+    atomicAdd(out + threadIdx.x, t);
+  }
 }
 
 // ---- stem: dW[tap][plane][c] += x_shift[row][plane] * dz[row][c], db[c] += dz[row][c]; thread = channel, 18 + 1

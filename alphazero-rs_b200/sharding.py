@@ -27,3 +27,25 @@ def reduce_scalar(dist, value, op, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
+
+
+def average_gradients(dist, grads):
+    """The one collective of the data-parallel training step: all-reduce the flat fp32 gradient vector
+    (numpy) over the ranks and divide by the world size — every rank trained on its own equally sized shard, so the
+    mean of the per-rank means is the gradient of the mean loss over the global batch.  Identity without `dist`.
+    NCCL ranks reduce on their GPU (NVLink / NVSwitch), gloo ranks on the host."""
+    if dist is None or dist.get_world_size() == 1:
+        return grads
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    g = torch.from_numpy(grads).to(dev)
+    dist.all_reduce(g)
+    g /= dist.get_world_size()
+    return g.cpu().numpy()
+
+
+def shard_samples(samples, rank, world):
+    """Equal contiguous shards of SOATrainingSamples (boards, pis, vs); the remainder (< world samples) is dropped so
+    that every rank's mean has the same weight."""
+    n = len(samples[2]) // world
+    return tuple(a[rank * n:(rank + 1) * n] for a in samples)

@@ -197,8 +197,9 @@ int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_p
  * batch), Adam.  Mixed precision: fp32 master parameters and gradients, bf16 tower on the tensor cores.
  *   azb_nnet_train_begin : forward (every layer kept), loss -> loss_out[2] = {policy, value}, backward; the gradients stay on
  *                          the device;
- *   azb_nnet_grads / azb_nnet_set_grads : read / replace them (count = azb_nnet_num_params): the seam where a data-parallel
- *                          caller all-reduces (NCCL / gloo) and divides by the number of ranks;
+ *   azb_nnet_grads / azb_nnet_set_grads / azb_nnet_grads_device : read / replace them on the host, or get the device
+ *                          pointer (count = azb_nnet_num_params): the seam where a data-parallel caller all-reduces
+ *                          (NCCL in place on the device, or gloo on the host) and divides by the number of ranks;
  *   azb_nnet_train_apply : one Adam step, then every derived form of the weights is rebuilt on the device;
  *   azb_nnet_train       : begin + apply. */
 typedef struct azb_train_config {
@@ -207,6 +208,9 @@ typedef struct azb_train_config {
 int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count, float* loss_out);
 int azb_nnet_grads(azb_nnet* n, float* out, uint64_t count);
 int azb_nnet_set_grads(azb_nnet* n, const float* in, uint64_t count);
+/* The gradient vector where it lives: a device pointer to count fp32 values (valid until the next train_begin), so that a
+ * caller with NCCL can all-reduce in place over NVLink without a host round trip. */
+int azb_nnet_grads_device(azb_nnet* n, void** ptr, uint64_t* count);
 int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg);
 int azb_nnet_train(azb_nnet* n, const float* boards, const float* pis, const float* vs, uint64_t count,
                    const azb_train_config* cfg, float* loss_out);
