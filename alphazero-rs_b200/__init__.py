@@ -92,6 +92,27 @@ class TrainConfig(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+class LearnConfig(C.Structure):
+    """azb_learn_config: the training schedule of an iteration (connect_four_net.py:13-21) + Coach::learn's flags."""
+    _fields_ = [("epochs", C.c_uint32), ("batch_size", C.c_uint32), ("adam", TrainConfig), ("arena_k_open", C.c_uint32),
+                ("skip_first_play", C.c_uint32), ("save_files", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class LearnReport(C.Structure):
+    _fields_ = ([(n, C.c_uint64) for n in ("iteration", "model_id_before", "model_id_after", "games", "samples_played",
+                                           "samples_kept", "history_iterations", "history_samples", "train_steps")] +
+                [("loss_first", C.c_float * 2), ("loss_last", C.c_float * 2)] +
+                [(n, C.c_uint64) for n in ("nwins", "pwins", "draws")] +
+                [("accepted", C.c_int32), ("reserved", C.c_int32),
+                 ("selfplay_ms", C.c_double), ("train_ms", C.c_double), ("arena_ms", C.c_double)])
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        d["loss_first"] = [float(x) for x in self.loss_first]
+        d["loss_last"] = [float(x) for x in self.loss_last]
+        return d
+
+
 NNET_BF16_TC, NNET_FP32 = 0, 1
 
 
@@ -157,12 +178,29 @@ def _load():
         "azb_nnet_wgrad_hook": [vp, vp, vp, u64, vp],
         "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
                                  C.POINTER(SelfPlayStats)],
+        "azb_examples_write": [C.c_char_p, u64, vp, vp, vp, vp],
+        "azb_examples_stat": [C.c_char_p, C.POINTER(u64), vp, u64, C.POINTER(u64)],
+        "azb_examples_read": [C.c_char_p, vp, vp, vp, u64],
+        "azb_examples_latest": [C.c_char_p, C.POINTER(u64)],
+        "azb_nnet_save": [vp, C.c_char_p],
+        "azb_nnet_load": [vp, C.c_char_p],
+        "azb_nnet_copy": [vp, vp],
+        "azb_coach_learn": [vp, C.POINTER(NnetConfig), C.POINTER(LearnConfig), C.POINTER(LearnReport), u64, C.POINTER(u64),
+                            C.POINTER(vp)],
+        "azb_coach_history_stat": [vp, C.POINTER(u64), vp, u64, C.POINTER(u64)],
+        "azb_coach_history_export": [vp, vp, vp, vp, u64],
+        "azb_coach_save_train_examples": [vp, u64, C.c_char_p],
+        "azb_coach_load_train_examples": [vp, C.c_char_p],
+        "azb_learn_accept": [u64, u64, f32],
+        "azb_learn_shuffle_perm": [u64, u64, u64, vp],
     }
+    lib.azb_learn_config_default.argtypes = [C.POINTER(LearnConfig)]
+    lib.azb_learn_config_default.restype = None
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    return lib, sorted(sigs) + ["azb_last_error", "azb_config_default"]
+    return lib, sorted(sigs) + ["azb_last_error", "azb_config_default", "azb_learn_config_default"]
 
 
 lib, ABI_SYMBOLS = _load()
@@ -433,6 +471,85 @@ class Coach:
         return boards[: w.value], pis[: w.value], vs[: w.value]
 
 
+    # ---- Coach::learn and the sample history (coach.rs:55-81,159-396) ----
+    def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-3, arena_k_open=0,
+              save_files=True, seed=7, blocks=6):
+        """Coach::learn(checkpoint, skip_first_play, ...) — coach.rs:169-396.  Returns (reports, accepted NNet)."""
+        if net_cfg is None:
+            net_cfg = NnetConfig(self.cfg.device, blocks, NNET_BF16_TC, 0, seed)
+        lc = LearnConfig()
+        lib.azb_learn_config_default(C.byref(lc))
+        lc.epochs, lc.batch_size, lc.arena_k_open = epochs, batch_size, arena_k_open
+        lc.adam.lr = lr
+        lc.skip_first_play, lc.save_files = int(skip_first_play), int(save_files)
+        n_it = int(self.cfg.num_iters)
+        reports = (LearnReport * max(1, n_it))()
+        n = C.c_uint64()
+        h = C.c_void_p()
+        _check(lib.azb_coach_learn(self._h, C.byref(net_cfg), C.byref(lc), reports, n_it, C.byref(n), C.byref(h)))
+        net = NNet.__new__(NNet)
+        net.cfg, net._h = net_cfg, h
+        return [reports[i].as_dict() for i in range(n.value)], net
+
+    def history(self):
+        """struct Coach.history (coach.rs:19): (counts per entry, boards, pis, vs) over all entries, oldest first."""
+        n_it, n_s = C.c_uint64(), C.c_uint64()
+        _check(lib.azb_coach_history_stat(self._h, C.byref(n_it), None, 0, C.byref(n_s)))
+        counts = np.zeros(max(1, n_it.value), np.uint64)
+        _check(lib.azb_coach_history_stat(self._h, C.byref(n_it), _ptr(counts), len(counts), C.byref(n_s)))
+        n = n_s.value
+        boards, pis, vs = np.zeros((n, 2, 6, 7), np.float32), np.zeros((n, 7), np.float32), np.zeros(n, np.float32)
+        if n:
+            _check(lib.azb_coach_history_export(self._h, _ptr(boards), _ptr(pis), _ptr(vs), n))
+        return counts[: n_it.value], boards, pis, vs
+
+    def save_train_examples(self, iteration, checkpoint):
+        """Coach::save_train_examples — coach.rs:159-167."""
+        _check(lib.azb_coach_save_train_examples(self._h, iteration, str(checkpoint).encode()))
+
+    def load_train_examples(self, path):
+        _check(lib.azb_coach_load_train_examples(self._h, str(path).encode()))
+
+
+def examples_write(path, counts, boards, pis, vs):
+    """`<iteration>.examples`: bincode of VecDeque<VecDeque<TrainingSample>> (coach.rs:159-167; layout in azb200.h)."""
+    counts = np.ascontiguousarray(counts, np.uint64)
+    boards = np.ascontiguousarray(boards, np.float32)
+    pis = np.ascontiguousarray(pis, np.float32)
+    vs = np.ascontiguousarray(vs, np.float32)
+    assert int(counts.sum()) == len(vs) == len(pis.reshape(-1, 7)) == len(boards.reshape(-1, 84))
+    _check(lib.azb_examples_write(str(path).encode(), len(counts), _ptr(counts), _ptr(boards), _ptr(pis), _ptr(vs)))
+
+
+def examples_read(path):
+    """-> (counts per history entry, boards[n,2,6,7], pis[n,7], vs[n])  (coach.rs:55-77)"""
+    n_it, n_s = C.c_uint64(), C.c_uint64()
+    _check(lib.azb_examples_stat(str(path).encode(), C.byref(n_it), None, 0, C.byref(n_s)))
+    counts = np.zeros(max(1, n_it.value), np.uint64)
+    _check(lib.azb_examples_stat(str(path).encode(), C.byref(n_it), _ptr(counts), len(counts), C.byref(n_s)))
+    n = n_s.value
+    boards, pis, vs = np.zeros((max(n, 1), 2, 6, 7), np.float32), np.zeros((max(n, 1), 7), np.float32), np.zeros(max(n, 1), np.float32)
+    _check(lib.azb_examples_read(str(path).encode(), _ptr(boards), _ptr(pis), _ptr(vs), n))
+    return counts[: n_it.value], boards[:n], pis[:n], vs[:n]
+
+
+def examples_latest(checkpoint_directory):
+    it = C.c_uint64()
+    _check(lib.azb_examples_latest(str(checkpoint_directory).encode(), C.byref(it)))
+    return it.value
+
+
+def learn_accept(nwins, pwins, update_threshold):
+    """The accept rule of coach.rs:383-390."""
+    return bool(lib.azb_learn_accept(nwins, pwins, C.c_float(update_threshold)))
+
+
+def learn_shuffle_perm(seed, iteration, n):
+    perm = np.zeros(max(n, 1), np.uint64)
+    _check(lib.azb_learn_shuffle_perm(seed, iteration, n, _ptr(perm)))
+    return perm[:n]
+
+
 class NNet:
     """trait NNet (src/nnet.rs:35-45): new / predict (+ parameter access).  One handle = one model."""
 
@@ -542,6 +659,16 @@ class NNet:
     def set_params(self, w):
         w = np.ascontiguousarray(w, np.float32)
         _check(lib.azb_nnet_set_params(self._h, _ptr(w), len(w)))
+
+    def save(self, path):
+        """`<model_id>.azbw` weight checkpoint (python_nnet.rs:76-79 save_checkpoint)."""
+        _check(lib.azb_nnet_save(self._h, str(path).encode()))
+
+    def load(self, path):
+        _check(lib.azb_nnet_load(self._h, str(path).encode()))
+
+    def copy_from(self, other):
+        _check(lib.azb_nnet_copy(self._h, other._h))
 
 
 def param_layout(blocks=6, channels=128):

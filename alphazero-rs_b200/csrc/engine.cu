@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -624,8 +625,24 @@ struct RoundEngine {
 };
 }  // namespace
 
+// one history entry = one iteration's samples, structure-of-arrays (the layout NNet::train takes)
+struct SampleBlock {
+  std::vector<float> boards, pis, vs;
+  uint64_t size() const { return vs.size(); }
+  void drop_front(uint64_t k) {  // coach.rs:275-277: while len > max_queue_length pop_front
+    boards.erase(boards.begin(), boards.begin() + static_cast<ptrdiff_t>(k * 84));
+    pis.erase(pis.begin(), pis.begin() + static_cast<ptrdiff_t>(k * 7));
+    vs.erase(vs.begin(), vs.begin() + static_cast<ptrdiff_t>(k));
+  }
+};
+struct CoachHistory {
+  std::deque<SampleBlock> entries;  // struct Coach.history, coach.rs:19
+};
+
 struct azb_coach {
   azb_config cfg;
+  std::string checkpoint_dir;  // owns what cfg.checkpoint_directory points at
+  CoachHistory history;
   TreePool pool;
   bool pool_ready = false;
   azb_nnet* net = nullptr;
@@ -636,6 +653,8 @@ struct azb_coach {
   DevBuf next_game, offsets, out_boards, out_pis, out_vs;
   std::vector<uint32_t> h_plies;
 };
+
+static int coach_resume_history(azb_coach* c);  // learn.cuh
 
 extern "C" {
 
@@ -916,6 +935,12 @@ int azb_coach_setup(const azb_config* cfg, azb_coach** out) {
   AZB_CUDA(cudaSetDevice(cfg->device));
   auto c = std::make_unique<azb_coach>();
   c->cfg = *cfg;
+  if (cfg->checkpoint_directory) {
+    c->checkpoint_dir = cfg->checkpoint_directory;
+    c->cfg.checkpoint_directory = c->checkpoint_dir.c_str();
+    rc = coach_resume_history(c.get());  // coach.rs:55-81
+    if (rc) return rc;
+  }
   *out = c.release();
   return AZB_OK;
 }
@@ -1603,3 +1628,5 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
 }
 
 }  // extern "C"
+
+#include "learn.cuh"

@@ -128,7 +128,8 @@ void azb_config_default(azb_config* cfg);
 
 typedef struct azb_coach azb_coach;
 
-/* Coach::setup — coach.rs:38-102 (history resume is a next-row item). */
+/* Coach::setup — coach.rs:38-102.  When checkpoint_directory is non-NULL and holds a `<n>.examples` file, the
+ * newest one becomes the history (coach.rs:55-81); a missing directory is created (:78-80). */
 int azb_coach_setup(const azb_config* cfg, azb_coach** out);
 int azb_coach_destroy(azb_coach* c);
 
@@ -179,7 +180,7 @@ typedef struct azb_nnet_config {
   uint64_t seed;     /* He-normal initialisation (weights ~ N(0, 2/fan_in), biases 0) */
 } azb_nnet_config;
 typedef struct azb_nnet azb_nnet;
-/* NNet::new(checkpoint) — nnet.rs:36: random-init from cfg->seed (checkpoint files: next row N3) */
+/* NNet::new(checkpoint) — nnet.rs:36: random-init from cfg->seed; azb_nnet_load restores a checkpoint */
 int azb_nnet_create(const azb_nnet_config* cfg, azb_nnet** out);
 int azb_nnet_destroy(azb_nnet* n);
 /* NNet::predict(boards[B,2,6,7], model_id) -> (pi[B,7] probabilities, v[B]) — nnet.rs:40-44.
@@ -239,6 +240,103 @@ int azb_coach_set_nnet(azb_coach* c, azb_nnet* n);
 int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
                          azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
                          azb_selfplay_stats* stats);
+
+/* ---------------------------------------------------------------------------------------
+ * On-disk formats.
+ *
+ * `<checkpoint>/<iteration>.examples` — Coach::save_train_examples, coach.rs:159-167: bincode 1.3.1
+ * (default options: little-endian, fixed-width integers, u64 lengths) of
+ * VecDeque<VecDeque<TrainingSample>> (src/nnet.rs:22-27) with ndarray 0.13's serde form of an array
+ * {v: u8 = 1, dim, data: seq}:
+ *   u64 n_iterations; per iteration: u64 n_samples; per sample:
+ *     board: u8 1 | u64 ndim=3 | u64 2,6,7 | u64 84 | 84 x f32      (IxDyn: dim is a length-prefixed seq)
+ *     pi   : u8 1 | u64 7 | u64 7 | 7 x f32                         (Ix1: dim is a bare [usize; 1])
+ *     v    : f32                                                     426 bytes per sample
+ * Both crates are absent from /root/reference (Cargo.toml:13,24), so the byte layout is restated from
+ * their published formats: parity unpinned by the reference, pinned by oracle/learn.hpp and an independent
+ * Python parser in tests/.  Host-only code: these calls work without a CUDA device.
+ * The reader accepts any 3-d board shape with 84 elements (the literal to_features writes [6,7,2], F11).
+ * ------------------------------------------------------------------------------------- */
+/* counts[n_iters] samples per history entry (oldest first); boards/pis/vs hold sum(counts) samples. */
+int azb_examples_write(const char* path, uint64_t n_iters, const uint64_t* counts, const float* boards,
+                       const float* pis, const float* vs);
+/* Header pass: n_iters and, when counts != NULL, up to cap_iters per-iteration sample counts. */
+int azb_examples_stat(const char* path, uint64_t* n_iters, uint64_t* counts, uint64_t cap_iters,
+                      uint64_t* n_samples);
+/* Data pass into caller buffers of cap_samples samples. */
+int azb_examples_read(const char* path, float* boards, float* pis, float* vs, uint64_t cap_samples);
+/* The most recent `<n>.examples` of a directory (Coach::setup, coach.rs:55-72, restricted to *.examples
+ * so that weight files may share the directory): iteration number, or AZB_ERR_INVALID when none. */
+int azb_examples_latest(const char* checkpoint_directory, uint64_t* iteration);
+
+/* Weight checkpoints `<checkpoint>/<model_id>.azbw` (the reference's python_nnet.rs:76-79 saves
+ * `<model_id>.pth.tar` through TF; this engine's own container): "AZBW" | u32 version=1 | u32 blocks |
+ * u32 has_adam | u64 n_params | u64 adam_t | n_params f32 [| m | v]. */
+int azb_nnet_save(azb_nnet* n, const char* path);
+int azb_nnet_load(azb_nnet* n, const char* path);
+/* dst <- src: parameters, Adam state and every derived device form (NNet::train's previous_model_id ->
+ * model_id hand-over, src/nnet.rs:38). */
+int azb_nnet_copy(azb_nnet* dst, azb_nnet* src);
+
+/* ---------------------------------------------------------------------------------------
+ * Coach::learn — coach.rs:169-396: num_iters iterations of
+ *   self-play (num_eps games, network model_id)            coach.rs:241-272
+ *   keep the newest max_queue_length samples               coach.rs:274-277
+ *   history window of max_history_length iterations        coach.rs:284-289
+ *   save `<iteration>.examples`                            coach.rs:291-293
+ *   shuffle, AOS->SOA, train model_id -> model_id + 1      coach.rs:295-331
+ *   arena new vs previous, num_arena_games, temp 0         coach.rs:333-375
+ *   accept iff nwins/(nwins+pwins) >= update_threshold     coach.rs:383-390
+ * The two models are double-buffered device networks; history lives in the coach (and is resumed from
+ * checkpoint_directory by azb_coach_setup when a `<n>.examples` exists there, coach.rs:55-81).
+ * Deviations, stated: the shuffle is a Fisher-Yates walk driven by Philox (seed, iteration) instead of
+ * rand 0.7's SmallRng; the training schedule is `epochs` Adam steps over consecutive batch_size slices
+ * of the shuffled list (connect_four_net.py:13-14,135-140 draws its minibatches with replacement);
+ * episode e of iteration i uses game id i*num_eps + e (the reference clones one rng into every
+ * episode, Q5, which makes the episodes of an iteration identical).
+ * ------------------------------------------------------------------------------------- */
+typedef struct azb_learn_config {
+  uint32_t epochs;          /* Adam steps per iteration (connect_four_net.py:13: 10); 0 = one pass over the window */
+  uint32_t batch_size;      /* connect_four_net.py:14: 64 */
+  azb_train_config adam;    /* lr 1e-3 (connect_four_net.py:21), 0.9, 0.999, 1e-8 */
+  uint32_t arena_k_open;    /* random opening plies of the gating games (0 = reference) */
+  uint32_t skip_first_play; /* Coach::learn's skip_first_play, coach.rs:172,240 */
+  uint32_t save_files;      /* 1: write <iteration>.examples and <model_id>.azbw into checkpoint_directory */
+  uint32_t reserved;
+} azb_learn_config;
+void azb_learn_config_default(azb_learn_config* lc);
+
+typedef struct azb_learn_report {
+  uint64_t iteration;
+  uint64_t model_id_before, model_id_after;
+  uint64_t games, samples_played, samples_kept; /* this iteration's self-play, before / after the queue trim */
+  uint64_t history_iterations, history_samples; /* the window the network was trained on */
+  uint64_t train_steps;
+  float loss_first[2], loss_last[2];            /* {policy, value} of the first / last step */
+  uint64_t nwins, pwins, draws;                 /* arena: candidate (new) vs current (previous) */
+  int32_t accepted;
+  int32_t reserved;
+  double selfplay_ms, train_ms, arena_ms;       /* host wall-clock of the three phases */
+} azb_learn_report;
+
+/* net_cfg: architecture and seed of model 0 (NNet::new(checkpoint), async_mcts.rs:125).  With save_files set, a
+ * `0.azbw` already in checkpoint_directory is loaded instead of the random init, and every trained candidate is
+ * written as `<model_id + 1>.azbw`.  reports[cap_reports] receives one entry per iteration; *final_net (optional)
+ * receives the accepted model, owned by the caller afterwards (azb_nnet_destroy). */
+int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc,
+                    azb_learn_report* reports, uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net);
+/* The coach's sample history (struct Coach.history, coach.rs:19): entry counts, then the data. */
+int azb_coach_history_stat(azb_coach* c, uint64_t* n_iters, uint64_t* counts, uint64_t cap_iters, uint64_t* n_samples);
+int azb_coach_history_export(azb_coach* c, float* boards, float* pis, float* vs, uint64_t cap_samples);
+/* Coach::save_train_examples(iteration, checkpoint) — coach.rs:159-167 (the reference joins an absolute
+ * "/<n>.examples", which lands in the filesystem root; the intended `<checkpoint>/<n>.examples` is written). */
+int azb_coach_save_train_examples(azb_coach* c, uint64_t iteration, const char* checkpoint_directory);
+/* Replace the history with the contents of a file (what Coach::setup does with the newest one). */
+int azb_coach_load_train_examples(azb_coach* c, const char* path);
+/* The reference's pure decisions, exposed so that they can be checked without a device:
+ * accept rule coach.rs:383-390; shuffle permutation used by azb_coach_learn (perm[n]). */
+int azb_learn_accept(uint64_t nwins, uint64_t pwins, float update_threshold);
+int azb_learn_shuffle_perm(uint64_t seed, uint64_t iteration, uint64_t n, uint64_t* perm);
 
 /* ---------------------------------------------------------------------------------------
  * AsyncMcts test hooks — src/async_mcts.rs and src/node.rs are private modules of the

@@ -20,6 +20,7 @@
 
 #include "c4.hpp"
 #include "coach.hpp"
+#include "learn.hpp"
 #include "mcts.hpp"
 #include "node.hpp"
 #include "philox.hpp"
@@ -390,6 +391,43 @@ int azo_bench_selfplay(const azo_params* p, int eval_kind, uint64_t n_games, uin
   if (expansions) *expansions = tot_exp;
   return 0;
   AZO_CATCH(-1)
+}
+
+// ---- Coach::learn host decisions and the .examples encoding (oracle/learn.hpp) ----------------------
+// counts[n_iters]; boards/pis/vs concatenated; out may be NULL (size query).  Returns the encoded size.
+uint64_t azo_examples_encode(uint64_t n_iters, const uint64_t* counts, const float* boards, const float* pis,
+                             const float* vs, uint8_t* out, uint64_t cap) {
+  std::deque<std::deque<TrainingSample>> h;
+  uint64_t at = 0;
+  for (uint64_t it = 0; it < n_iters; ++it) {
+    std::deque<TrainingSample> q;
+    for (uint64_t i = 0; i < counts[it]; ++i, ++at) {
+      TrainingSample t;
+      t.board.assign(boards + at * 84, boards + at * 84 + 84);
+      t.board_shape = {2, 6, 7};
+      t.pi.assign(pis + at * 7, pis + at * 7 + 7);
+      t.v = vs[at];
+      q.push_back(std::move(t));
+    }
+    h.push_back(std::move(q));
+  }
+  std::vector<uint8_t> enc = ser_history(h);
+  if (out && enc.size() <= cap) std::memcpy(out, enc.data(), enc.size());
+  return enc.size();
+}
+int azo_learn_accept(uint64_t nwins, uint64_t pwins, float thr) { return accept(nwins, pwins, thr) ? 1 : 0; }
+void azo_learn_shuffle_perm(uint64_t seed, uint64_t iteration, uint64_t n, uint64_t* perm) {
+  shuffle_perm(seed, iteration, n, perm);
+}
+// plays `n` iterations of sample counts through the queue trim + history window; out_sizes[n][max_hist] (0 padded),
+// out_dropped[n].
+void azo_learn_window(const uint64_t* played, uint64_t n, uint64_t max_queue, uint64_t max_hist, uint64_t* out_sizes,
+                      uint64_t* out_dropped) {
+  Window w;
+  for (uint64_t i = 0; i < n; ++i) {
+    out_dropped[i] = push_iteration(w, played[i], max_queue, max_hist);
+    for (uint64_t k = 0; k < max_hist; ++k) out_sizes[i * max_hist + k] = k < w.sizes.size() ? w.sizes[k] : 0;
+  }
 }
 
 }  // extern "C"

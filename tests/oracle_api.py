@@ -225,3 +225,46 @@ def bench_selfplay(n_games, n_threads, num_sims=800, quirks=0, seed=0xA1FA0, eva
     if rc != 0:
         raise RuntimeError(L.azo_last_error().decode())
     return dict(sims=sims.value, plies=plies.value, seconds=secs.value, levels=lv.value, expansions=ex.value)
+
+
+# ---- Coach::learn host decisions + the .examples encoding (oracle/learn.hpp) ----
+L.azo_examples_encode.restype = C.c_uint64
+L.azo_examples_encode.argtypes = [C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64]
+L.azo_learn_accept.argtypes = [C.c_uint64, C.c_uint64, C.c_float]
+L.azo_learn_shuffle_perm.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, vp]
+L.azo_learn_shuffle_perm.restype = None
+L.azo_learn_window.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
+L.azo_learn_window.restype = None
+
+
+def examples_encode(counts, boards, pis, vs):
+    """bincode::serialize(&history) (coach.rs:163) -> bytes"""
+    counts = np.ascontiguousarray(counts, np.uint64)
+    boards = np.ascontiguousarray(boards, np.float32)
+    pis = np.ascontiguousarray(pis, np.float32)
+    vs = np.ascontiguousarray(vs, np.float32)
+    p = lambda a: a.ctypes.data_as(vp)
+    n = L.azo_examples_encode(len(counts), p(counts), p(boards), p(pis), p(vs), None, 0)
+    out = np.zeros(n, np.uint8)
+    L.azo_examples_encode(len(counts), p(counts), p(boards), p(pis), p(vs), p(out), n)
+    return out.tobytes()
+
+
+def learn_accept(nwins, pwins, thr):
+    return bool(L.azo_learn_accept(nwins, pwins, C.c_float(thr)))
+
+
+def learn_shuffle_perm(seed, iteration, n):
+    perm = np.zeros(max(n, 1), np.uint64)
+    L.azo_learn_shuffle_perm(seed, iteration, n, perm.ctypes.data_as(vp))
+    return perm[:n]
+
+
+def learn_window(played, max_queue, max_hist):
+    """-> (sizes[n][max_hist] of the history after each iteration, dropped[n])  (coach.rs:274-289)"""
+    played = np.ascontiguousarray(played, np.uint64)
+    sizes = np.zeros((len(played), max_hist), np.uint64)
+    dropped = np.zeros(len(played), np.uint64)
+    L.azo_learn_window(played.ctypes.data_as(vp), len(played), max_queue, max_hist, sizes.ctypes.data_as(vp),
+                       dropped.ctypes.data_as(vp))
+    return sizes, dropped
