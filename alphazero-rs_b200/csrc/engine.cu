@@ -214,6 +214,14 @@ struct azb_nnet {
   DevBuf d_grad, d_adam_m, d_adam_v, d_loss, d_pis, d_vs;
   uint64_t adam_t = 0;
   bool grads_ready = false;
+  bool host_stale = false;             // a training step moved d_params; h_params is refreshed on demand (sync_host)
+  int sync_host() {
+    if (!host_stale) return AZB_OK;
+    AZB_CUDA(cudaSetDevice(cfg.device));
+    AZB_CUDA(cudaMemcpy(h_params.data(), d_params.p, L.total * 4, cudaMemcpyDeviceToHost));
+    host_stale = false;
+    return AZB_OK;
+  }
   static uint16_t bf16_rne(float f) {
     uint32_t u;
     std::memcpy(&u, &f, 4);
@@ -1176,6 +1184,8 @@ int azb_nnet_num_params(azb_nnet* n, uint64_t* count) {
 int azb_nnet_get_params(azb_nnet* n, float* out, uint64_t capacity) {
   if (!n || !out) return fail(AZB_ERR_INVALID, "NULL argument");
   if (capacity < n->L.total) return fail(AZB_ERR_CAPACITY, "parameter buffer too small");
+  const int rc = n->sync_host();
+  if (rc) return rc;
   std::memcpy(out, n->h_params.data(), n->L.total * 4);
   return AZB_OK;
 }
@@ -1184,6 +1194,7 @@ int azb_nnet_set_params(azb_nnet* n, const float* in, uint64_t count) {
   if (count != n->L.total) return fail(AZB_ERR_INVALID, "parameter count mismatch");
   AZB_CUDA(cudaSetDevice(n->cfg.device));
   std::memcpy(n->h_params.data(), in, count * 4);
+  n->host_stale = false;
   return n->upload();
 }
 int azb_nnet_predict(azb_nnet* n, const float* boards, size_t batch, size_t /*model_id*/, float* pi, float* v) {
@@ -1371,7 +1382,7 @@ int azb_nnet_train_begin(azb_nnet* n, const float* boards, const float* pis, con
     gi = go;
   }
   lap("tower backward");
-  k_stem_backward<<<148 * 2, 128>>>(n->d_states.as<uint4>(), n->tr_g[gi].as<__nv_bfloat16>(), B, kActPadded, grad + L.stem_w, grad + L.stem_b);
+  k_stem_backward<<<148 * 2, 128 * kStemBwdGroups>>>(n->d_states.as<uint4>(), n->tr_g[gi].as<__nv_bfloat16>(), B, kActPadded, grad + L.stem_w, grad + L.stem_b);
   AZB_CUDA(cudaGetLastError());
   lap("stem backward");
   float hl[2];
@@ -1432,8 +1443,12 @@ int azb_nnet_train_apply(azb_nnet* n, const azb_train_config* cfg) {
   for (int c = 1; c < kTcWeightCopies; ++c)  // the replicas the single-CTA kernel streams from
     AZB_CUDA(cudaMemcpy(n->d_wtiles.as<uint8_t>() + c * n->wtile_copy_bytes, n->d_wtiles.p, n->wtile_copy_bytes, cudaMemcpyDeviceToDevice));
   lap("replicas");
-  AZB_CUDA(cudaMemcpy(n->h_params.data(), n->d_params.p, N * 4, cudaMemcpyDeviceToHost));
-  lap("params to host");
+  // only the head range comes back now (the 1x1 head convolutions travel as a kernel parameter); the rest of the host
+  // copy is refreshed when someone asks for it (get_params / save / copy)
+  const size_t h0 = n->L.pol_w, h1 = n->L.val_b + 1;
+  AZB_CUDA(cudaMemcpy(n->h_params.data() + h0, n->d_params.as<float>() + h0, (h1 - h0) * 4, cudaMemcpyDeviceToHost));
+  n->host_stale = true;
+  lap("head params to host");
   for (int ci = 0; ci < kNetC; ++ci) {
     n->head_w.w[ci][0] = n->h_params[n->L.pol_w + ci * 2 + 0];
     n->head_w.w[ci][1] = n->h_params[n->L.pol_w + ci * 2 + 1];

@@ -311,6 +311,8 @@ void azb_learn_config_default(azb_learn_config* lc) {
 int azb_nnet_save(azb_nnet* n, const char* path) {
   if (!n || !path) return fail(AZB_ERR_INVALID, "NULL argument");
   const uint64_t N = n->L.total;
+  const int rcs = n->sync_host();
+  if (rcs) return rcs;
   const bool adam = n->d_adam_m.bytes >= N * 4 && n->adam_t > 0;
   std::vector<float> m, v;
   if (adam) {
@@ -386,7 +388,9 @@ int azb_nnet_copy(azb_nnet* dst, azb_nnet* src) {
   if (dst->cfg.blocks != src->cfg.blocks || dst->cfg.precision != src->cfg.precision || dst->cfg.device != src->cfg.device)
     return fail(AZB_ERR_INVALID, "networks differ in architecture, precision or device");
   const uint64_t N = src->L.total;
-  int rc = azb_nnet_set_params(dst, src->h_params.data(), N);
+  int rc = src->sync_host();
+  if (rc) return rc;
+  rc = azb_nnet_set_params(dst, src->h_params.data(), N);
   if (rc) return rc;
   if (src->d_adam_m.bytes >= N * 4 && src->adam_t > 0) {
     AZB_CUDA(dst->d_adam_m.ensure(N * 4));

@@ -178,34 +178,65 @@ __global__ void __launch_bounds__(256) k_colsum_bf16(const __nv_bfloat16* __rest
 }
 
 // ---- stem: dW[tap][plane][c] += x_shift[row][plane] * dz[row][c], db[c] += dz[row][c]; thread = channel, 18 + 1
-// register accumulators, the bit tests are warp-uniform -------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// register accumulators, the bit tests are warp-uniform.  512 threads = 4 position groups x 128 channels (a full SM of
+// warps: the kernel is latency-bound on the dz loads, seven of them in flight per board row), the groups' sums are
+// combined in shared memory and added to the gradient once per CTA. ------------------------------------------------
+constexpr int kStemBwdGroups = 4;
+__global__ void __launch_bounds__(128 * kStemBwdGroups)
 k_stem_backward(const uint4* __restrict__ states, const __nv_bfloat16* __restrict__ dz, uint32_t n_pos, ActLayout lay,
                 float* __restrict__ d_w /*[9][2][128]*/, float* __restrict__ d_b /*[128]*/) {
-  const int c = threadIdx.x;
+  __shared__ float part[kStemBwdGroups - 1][19][kNetC];
+  const int c = threadIdx.x & (kNetC - 1), grp = threadIdx.x >> 7;
   float acc[18], accb = 0.0f;
 #pragma unroll
   for (int i = 0; i < 18; ++i) acc[i] = 0.0f;
-  for (uint32_t pos = blockIdx.x; pos < n_pos; pos += gridDim.x) {
+  for (uint32_t pos = blockIdx.x * kStemBwdGroups + grp; pos < n_pos; pos += gridDim.x * kStemBwdGroups) {
     const uint4 st = states[pos];
     const uint64_t cur = (static_cast<uint64_t>(st.y) << 32) | st.x, opp = (static_cast<uint64_t>(st.w) << 32) | st.z;
-    for (int cell = 0; cell < kCells; ++cell) {
-      const int r = cell / 7, x = cell % 7;
-      const float d = __bfloat162float(dz[lay.row(pos, r, x) * kNetC + c]);
-      accb += d;
+#pragma unroll 1
+    for (int r = 0; r < 6; ++r) {
+      float d[7];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int rr = r + tap / 3 - 1, cc = x + tap % 3 - 1;
-        if (rr < 0 || rr >= 6 || cc < 0 || cc >= 7) continue;
-        const int b = rr * 7 + cc;
-        if ((cur >> b) & 1ull) acc[tap * 2] += d;
-        if ((opp >> b) & 1ull) acc[tap * 2 + 1] += d;
+      for (int x = 0; x < 7; ++x) d[x] = __bfloat162float(dz[lay.row(pos, r, x) * kNetC + c]);
+      // the three board rows the taps of this output row look at, as 7-bit masks (0 outside the board)
+      uint32_t mc[3], mo[3];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int rr = r + dy - 1;
+        const bool in = rr >= 0 && rr < 6;
+        mc[dy] = in ? static_cast<uint32_t>(cur >> (rr * 7)) & 0x7Fu : 0u;
+        mo[dy] = in ? static_cast<uint32_t>(opp >> (rr * 7)) & 0x7Fu : 0u;
+      }
+#pragma unroll
+      for (int x = 0; x < 7; ++x) {
+        accb += d[x];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int cc = x + tap % 3 - 1;
+          if (cc < 0 || cc >= 7) continue;
+          if ((mc[tap / 3] >> cc) & 1u) acc[tap * 2] += d[x];
+          if ((mo[tap / 3] >> cc) & 1u) acc[tap * 2 + 1] += d[x];
+        }
       }
     }
   }
+  if (grp > 0) {
 #pragma unroll
-  for (int i = 0; i < 18; ++i) atomicAdd(d_w + i * kNetC + c, acc[i]);
-  atomicAdd(d_b + c, accb);
+    for (int i = 0; i < 18; ++i) part[grp - 1][i][c] = acc[i];
+    part[grp - 1][18][c] = accb;
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      float t = acc[i];
+      for (int g2 = 0; g2 < kStemBwdGroups - 1; ++g2) t += part[g2][i][c];
+      atomicAdd(d_w + i * kNetC + c, t);
+    }
+    float t = accb;
+    for (int g2 = 0; g2 < kStemBwdGroups - 1; ++g2) t += part[g2][18][c];
+    atomicAdd(d_b + c, t);
+  }
 }
 
 // ---- Adam (connect_four_net.py:112: AdamOptimizer(lr)); t = 1, 2, ... -----------------------------------------
