@@ -113,6 +113,50 @@ class LearnReport(C.Structure):
         return d
 
 
+ALLREDUCE_F32_DEVICE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+ALLREDUCE_U64_HOST = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p)
+
+
+class Dist(C.Structure):
+    """azb_dist: rank, world and the caller's two all-reduce callbacks (the library owns no communicator)."""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("allreduce_sum_f32_device", ALLREDUCE_F32_DEVICE),
+                ("allreduce_sum_u64_host", ALLREDUCE_U64_HOST), ("user", C.c_void_p)]
+
+
+def make_dist(dist, device):
+    """azb_dist over an initialised torch.distributed: NCCL reduces the device buffer in place over NVLink; gloo (CPU
+    tests, or two ranks sharing one GPU) takes CUDA tensors too and stages them through the host."""
+    import torch
+
+    def ar_f32(ptr, count, _user):
+        try:
+            class _Dev:
+                __cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+            t = torch.as_tensor(_Dev(), device=f"cuda:{device}")
+            dist.all_reduce(t)
+            torch.cuda.synchronize(device)
+            return 0
+        except Exception as e:  # never let an exception cross the C frame
+            print("azb200 allreduce_sum_f32_device:", e)
+            return 1
+
+    def ar_u64(ptr, count, _user):
+        try:
+            a = np.ctypeslib.as_array(ptr, shape=(int(count),))
+            t = torch.from_numpy(a.astype(np.int64))
+            if dist.get_backend() == "nccl":
+                t = t.to(f"cuda:{device}")
+            dist.all_reduce(t)
+            a[:] = t.cpu().numpy().astype(np.uint64)
+            return 0
+        except Exception as e:
+            print("azb200 allreduce_sum_u64_host:", e)
+            return 1
+
+    d = Dist(dist.get_rank(), dist.get_world_size(), ALLREDUCE_F32_DEVICE(ar_f32), ALLREDUCE_U64_HOST(ar_u64), None)
+    return d
+
+
 NNET_BF16_TC, NNET_FP32 = 0, 1
 
 
@@ -187,6 +231,8 @@ def _load():
         "azb_nnet_copy": [vp, vp],
         "azb_coach_learn": [vp, C.POINTER(NnetConfig), C.POINTER(LearnConfig), C.POINTER(LearnReport), u64, C.POINTER(u64),
                             C.POINTER(vp)],
+        "azb_coach_learn_dist": [vp, C.POINTER(NnetConfig), C.POINTER(LearnConfig), C.POINTER(Dist), C.POINTER(LearnReport), u64,
+                                 C.POINTER(u64), C.POINTER(vp)],
         "azb_coach_history_stat": [vp, C.POINTER(u64), vp, u64, C.POINTER(u64)],
         "azb_coach_history_export": [vp, vp, vp, vp, u64],
         "azb_coach_save_train_examples": [vp, u64, C.c_char_p],
@@ -473,8 +519,10 @@ class Coach:
 
     # ---- Coach::learn and the sample history (coach.rs:55-81,159-396) ----
     def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-3, arena_k_open=0,
-              save_files=True, seed=7, blocks=6):
-        """Coach::learn(checkpoint, skip_first_play, ...) — coach.rs:169-396.  Returns (reports, accepted NNet)."""
+              save_files=True, seed=7, blocks=6, dist=None):
+        """Coach::learn(checkpoint, skip_first_play, ...) — coach.rs:169-396.  Returns (reports, accepted NNet).
+        With `dist` (an initialised torch.distributed, one process per GPU) the iteration is data parallel
+        (azb_coach_learn_dist): self-play and arena games sharded over the ranks, gradients averaged by all-reduce."""
         if net_cfg is None:
             net_cfg = NnetConfig(self.cfg.device, blocks, NNET_BF16_TC, 0, seed)
         lc = LearnConfig()
@@ -486,7 +534,11 @@ class Coach:
         reports = (LearnReport * max(1, n_it))()
         n = C.c_uint64()
         h = C.c_void_p()
-        _check(lib.azb_coach_learn(self._h, C.byref(net_cfg), C.byref(lc), reports, n_it, C.byref(n), C.byref(h)))
+        if dist is not None and dist.get_world_size() > 1:
+            d = make_dist(dist, self.cfg.device)
+            _check(lib.azb_coach_learn_dist(self._h, C.byref(net_cfg), C.byref(lc), C.byref(d), reports, n_it, C.byref(n), C.byref(h)))
+        else:
+            _check(lib.azb_coach_learn(self._h, C.byref(net_cfg), C.byref(lc), reports, n_it, C.byref(n), C.byref(h)))
         net = NNet.__new__(NNet)
         net.cfg, net._h = net_cfg, h
         return [reports[i].as_dict() for i in range(n.value)], net

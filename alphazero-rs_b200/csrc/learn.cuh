@@ -232,6 +232,11 @@ static int coach_resume_history(azb_coach* c) {
   return read_examples(path.c_str(), &c->history.entries, nullptr);
 }
 
+__global__ void k_scale_f32(float* __restrict__ p, size_t n, float s) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] *= s;
+}
+
 static int ensure_dir(const std::string& dir) {
   struct stat st;
   if (stat(dir.c_str(), &st) == 0) return S_ISDIR(st.st_mode) ? AZB_OK : fail(AZB_ERR_INVALID, dir + " is not a directory");
@@ -454,9 +459,25 @@ int azb_coach_load_train_examples(azb_coach* c, const char* path) {
 }
 
 // ---- Coach::learn — coach.rs:169-396 -----------------------------------------------------------------------
-int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc_in, azb_learn_report* reports,
-                    uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net) {
+// With `dist` (world > 1) the iteration is data parallel over one process per GPU: every rank self-plays a contiguous share
+// of the num_eps games and keeps their samples (no collective on the self-play path), the training steps average the
+// gradients through the caller's all-reduce (NCCL over NVLink in place on the device buffer), the gating games are split
+// over the ranks and their three counters summed, so that every rank takes the same accept decision on identical models.
+int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc_in, const azb_dist* dist,
+                         azb_learn_report* reports, uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net) {
   if (!c || !net_cfg) return fail(AZB_ERR_INVALID, "NULL argument");
+  const uint32_t world = dist ? dist->world : 1u, rank = dist ? dist->rank : 0u;
+  if (dist && (world == 0 || rank >= world || !dist->allreduce_sum_f32_device || !dist->allreduce_sum_u64_host))
+    return fail(AZB_ERR_INVALID, "azb_dist needs rank < world and both all-reduce callbacks");
+  auto sum_u64 = [&](uint64_t* v, uint64_t n) -> int {
+    if (world == 1) return AZB_OK;
+    return dist->allreduce_sum_u64_host(v, n, dist->user) ? fail(AZB_ERR_INVALID, "allreduce_sum_u64_host failed") : AZB_OK;
+  };
+  auto split = [&](uint64_t total, uint64_t* first, uint64_t* n) {  // contiguous shares, the remainder over the first ranks
+    const uint64_t base = total / world, rem = total % world;
+    *n = base + (rank < rem ? 1 : 0);
+    *first = rank * base + std::min<uint64_t>(rank, rem);
+  };
   if (n_reports) *n_reports = 0;
   if (final_net) *final_net = nullptr;
   azb_learn_config lc;
@@ -466,7 +487,8 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
   if (cfg.evaluator != AZB_EVAL_NNET) return fail(AZB_ERR_INVALID, "Coach::learn needs evaluator AZB_EVAL_NNET");
   if (net_cfg->precision != AZB_NNET_BF16_TC) return fail(AZB_ERR_UNSUPPORTED, "training needs the tensor-core tower");
   if (lc.batch_size == 0 || lc.batch_size > (1u << 20)) return fail(AZB_ERR_INVALID, "batch_size out of range");
-  if (cfg.num_eps == 0 || cfg.max_history_length == 0) return fail(AZB_ERR_INVALID, "num_eps and max_history_length must be positive");
+  if (cfg.num_eps < world || cfg.max_history_length == 0) return fail(AZB_ERR_INVALID, "num_eps (>= ranks) and max_history_length must be positive");
+  if (lc.batch_size < world) return fail(AZB_ERR_INVALID, "batch_size is the global batch: it must be >= the number of ranks");
   const bool files = lc.save_files != 0;
   if (files && !cfg.checkpoint_directory) return fail(AZB_ERR_INVALID, "save_files needs checkpoint_directory");
   const std::string dir = cfg.checkpoint_directory ? cfg.checkpoint_directory : "";
@@ -514,7 +536,9 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
       int rc = azb_coach_set_nnet(c, nets[cur].get());
       if (rc) return rc;
       azb_selfplay_stats st{};
-      rc = azb_coach_self_play(c, cfg.num_eps, iteration * cfg.num_eps, &st);  // coach.rs:241-272
+      uint64_t ep_first = 0, ep_n = 0;
+      split(cfg.num_eps, &ep_first, &ep_n);
+      rc = azb_coach_self_play(c, ep_n, iteration * cfg.num_eps + ep_first, &st);  // coach.rs:241-272
       if (rc) return rc;
       uint64_t n = 0;
       azb_coach_num_samples(c, &n);
@@ -525,7 +549,8 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
       if (rc) return rc;
       rep.games = st.games;
       rep.samples_played = n;
-      if (n > cfg.max_queue_length) blk.drop_front(n - cfg.max_queue_length);  // coach.rs:274-277
+      const uint64_t queue_cap = (cfg.max_queue_length + world - 1) / world;  // this rank's share of the queue
+      if (n > queue_cap) blk.drop_front(n - queue_cap);  // coach.rs:274-277
     }
     rep.samples_kept = blk.size();
     rep.selfplay_ms = wall_ms(t0);
@@ -539,12 +564,17 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
     for (auto& b : hist) total += b.size();
     rep.history_iterations = hist.size();
     rep.history_samples = total;
-    if (total == 0) return fail(AZB_ERR_INVALID, "no training samples (coach.rs:304 assert!(num_samples > 0))");
+    uint64_t glob[2] = {total, total == 0 ? 1u : 0u};  // {samples over all ranks, ranks without samples}
+    {
+      const int rcg = sum_u64(glob, 2);
+      if (rcg) return rcg;
+    }
+    if (glob[1]) return fail(AZB_ERR_INVALID, "no training samples (coach.rs:304 assert!(num_samples > 0))");
 
     // coach.rs:295-327: flatten, shuffle, AOS -> SOA
     t0 = std::chrono::steady_clock::now();
     perm.resize(total);
-    shuffle_perm(cfg.seed, iteration, total, perm.data());
+    shuffle_perm(cfg.seed + rank, iteration, total, perm.data());
     sb.resize(total * 84);
     sp.resize(total * 7);
     sv.resize(total);
@@ -570,8 +600,10 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
     azb_nnet* cand = nets[cur ^ 1].get();
     int rc = azb_nnet_copy(cand, nets[cur].get());
     if (rc) return rc;
-    const uint64_t bs = std::min<uint64_t>(lc.batch_size, total);
-    const uint64_t steps = lc.epochs ? lc.epochs : (total + bs - 1) / bs;
+    // batch_size is the global batch: every rank contributes batch_size / world samples per step; the step count is the
+    // same on all ranks (a pass = the global window once)
+    const uint64_t bs = std::min<uint64_t>(std::max<uint64_t>(lc.batch_size / world, 1), total);
+    const uint64_t steps = lc.epochs ? lc.epochs : (glob[0] + static_cast<uint64_t>(lc.batch_size) - 1) / lc.batch_size;
     std::vector<float> wb, wp, wv;  // a batch that wraps around the end of the list
     for (uint64_t s = 0; s < steps; ++s) {
       const uint64_t at = (s * bs) % total;
@@ -591,7 +623,15 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
         pv = wv.data();
       }
       float loss[2] = {0.0f, 0.0f};
-      rc = azb_nnet_train(cand, pb, pp, pv, bs, &lc.adam, loss);
+      rc = azb_nnet_train_begin(cand, pb, pp, pv, bs, loss);
+      if (rc) return rc;
+      if (world > 1) {  // mean over ranks of the per-rank mean gradients = gradient of the mean loss over the global batch
+        AZB_CUDA(cudaDeviceSynchronize());
+        if (dist->allreduce_sum_f32_device(cand->d_grad.p, cand->L.total, dist->user)) return fail(AZB_ERR_INVALID, "allreduce_sum_f32_device failed");
+        k_scale_f32<<<static_cast<unsigned>((cand->L.total + 255) / 256), 256>>>(cand->d_grad.as<float>(), cand->L.total, 1.0f / static_cast<float>(world));
+        AZB_CUDA(cudaGetLastError());
+      }
+      rc = azb_nnet_train_apply(cand, &lc.adam);
       if (rc) return rc;
       if (s == 0) std::memcpy(rep.loss_first, loss, 8);
       std::memcpy(rep.loss_last, loss, 8);
@@ -607,9 +647,17 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
     // coach.rs:333-375: the candidate (player A) against the current model, temp 0
     t0 = std::chrono::steady_clock::now();
     uint64_t counts[3] = {0, 0, 0};
-    rc = azb_arena_play_games(&cfg, cfg.num_arena_games, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), lc.arena_k_open, counts,
-                              nullptr, nullptr);
-    if (rc) return rc;
+    {
+      uint64_t pair_first = 0, pairs = 0;  // arena.rs:83: num / 2 games per seat order; the pairs are split over the ranks
+      split(cfg.num_arena_games / 2, &pair_first, &pairs);
+      azb_config acfg = cfg;
+      acfg.seed = cfg.seed + rank;  // the arena keys its opening streams by (seed, game): one seed per rank
+      rc = azb_arena_play_games(&acfg, 2 * pairs, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), lc.arena_k_open, counts, nullptr,
+                                nullptr);
+      if (rc) return rc;
+      rc = sum_u64(counts, 3);
+      if (rc) return rc;
+    }
     rep.arena_ms = wall_ms(t0);
     rep.nwins = counts[0];  // coach.rs:377-379
     rep.pwins = counts[1];
@@ -625,6 +673,11 @@ int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_lear
   }
   if (final_net) *final_net = nets[cur].release();
   return AZB_OK;
+}
+
+int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc, azb_learn_report* reports,
+                    uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net) {
+  return azb_coach_learn_dist(c, net_cfg, lc, nullptr, reports, cap_reports, n_reports, final_net);
 }
 
 }  // extern "C"

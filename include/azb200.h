@@ -325,6 +325,23 @@ typedef struct azb_learn_report {
  * receives the accepted model, owned by the caller afterwards (azb_nnet_destroy). */
 int azb_coach_learn(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc,
                     azb_learn_report* reports, uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net);
+/* The same loop, data parallel over one process per GPU (BASELINE config 5).  The library has no
+ * communicator of its own: the caller hands in its all-reduce (NCCL through torch.distributed in the ctypes mirror,
+ * ncclAllReduce in a Rust/C++ host).  Per iteration: rank r self-plays a contiguous share of the num_eps games (game
+ * ids iteration*num_eps + first_r ..., NO collective) and keeps their samples, with its share ceil(max_queue_length /
+ * world) of the queue; `batch_size` is the GLOBAL batch, each rank trains on batch_size / world of its own samples per
+ * step and the fp32 gradient vector is summed in place ON THE DEVICE by allreduce_sum_f32_device, then divided by
+ * world; the num_arena_games / 2 seat-order pairs are split over the ranks and the three counters summed by
+ * allreduce_sum_u64_host, so that every rank takes the same decision on bit-identical models.  Every rank needs its own
+ * checkpoint_directory (its share of the history is written there).  Callbacks return 0 on success. */
+typedef struct azb_dist {
+  uint32_t rank, world;
+  int (*allreduce_sum_f32_device)(void* device_ptr, uint64_t count, void* user);
+  int (*allreduce_sum_u64_host)(uint64_t* host_ptr, uint64_t count, void* user);
+  void* user;
+} azb_dist;
+int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc, const azb_dist* dist,
+                         azb_learn_report* reports, uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net);
 /* The coach's sample history (struct Coach.history, coach.rs:19): entry counts, then the data. */
 int azb_coach_history_stat(azb_coach* c, uint64_t* n_iters, uint64_t* counts, uint64_t cap_iters, uint64_t* n_samples);
 int azb_coach_history_export(azb_coach* c, float* boards, float* pis, float* vs, uint64_t cap_samples);

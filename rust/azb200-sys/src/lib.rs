@@ -137,6 +137,17 @@ pub struct azb_learn_report {
     pub arena_ms: f64,
 }
 
+/// The caller's communicator for `azb_coach_learn_dist` (the library owns none): both callbacks return 0 on success.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct azb_dist {
+    pub rank: u32,
+    pub world: u32,
+    pub allreduce_sum_f32_device: Option<unsafe extern "C" fn(device_ptr: *mut c_void, count: u64, user: *mut c_void) -> c_int>,
+    pub allreduce_sum_u64_host: Option<unsafe extern "C" fn(host_ptr: *mut u64, count: u64, user: *mut c_void) -> c_int>,
+    pub user: *mut c_void,
+}
+
 #[repr(C)]
 pub struct azb_coach {
     _opaque: [u8; 0],
@@ -210,6 +221,7 @@ extern "C" {
     // Coach::learn, coach.rs:169-396
     pub fn azb_learn_config_default(lc: *mut azb_learn_config);
     pub fn azb_coach_learn(c: *mut azb_coach, net_cfg: *const azb_nnet_config, lc: *const azb_learn_config, reports: *mut azb_learn_report, cap_reports: u64, n_reports: *mut u64, final_net: *mut *mut azb_nnet) -> c_int;
+    pub fn azb_coach_learn_dist(c: *mut azb_coach, net_cfg: *const azb_nnet_config, lc: *const azb_learn_config, dist: *const azb_dist, reports: *mut azb_learn_report, cap_reports: u64, n_reports: *mut u64, final_net: *mut *mut azb_nnet) -> c_int;
     pub fn azb_coach_history_stat(c: *mut azb_coach, n_iters: *mut u64, counts: *mut u64, cap_iters: u64, n_samples: *mut u64) -> c_int;
     pub fn azb_coach_history_export(c: *mut azb_coach, boards: *mut f32, pis: *mut f32, vs: *mut f32, cap_samples: u64) -> c_int;
     pub fn azb_coach_save_train_examples(c: *mut azb_coach, iteration: u64, checkpoint_directory: *const c_char) -> c_int;
