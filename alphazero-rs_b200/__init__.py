@@ -518,7 +518,7 @@ class Coach:
 
 
     # ---- Coach::learn and the sample history (coach.rs:55-81,159-396) ----
-    def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-3, arena_k_open=0,
+    def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-4, arena_k_open=0,
               save_files=True, seed=7, blocks=6, dist=None):
         """Coach::learn(checkpoint, skip_first_play, ...) — coach.rs:169-396.  Returns (reports, accepted NNet).
         With `dist` (an initialised torch.distributed, one process per GPU) the iteration is data parallel

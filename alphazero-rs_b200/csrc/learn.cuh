@@ -308,7 +308,10 @@ void azb_learn_config_default(azb_learn_config* lc) {
   std::memset(lc, 0, sizeof(*lc));
   lc->epochs = 10;      // connect_four_net.py:13
   lc->batch_size = 64;  // connect_four_net.py:14
-  lc->adam = azb_train_config{1e-3f, 0.9f, 0.999f, 1e-8f};
+  // the reference's Adam runs at 1e-3 (connect_four_net.py:21) on a network with BatchNorm in front of every ReLU; this
+  // network has none (folded away for inference) and at 1e-3 its 2-channel policy head dies within ~100 steps
+  // (profiles/r1_train.md): the default step is 1e-4
+  lc->adam = azb_train_config{1e-4f, 0.9f, 0.999f, 1e-8f};
   lc->save_files = 1;
 }
 

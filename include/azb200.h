@@ -298,7 +298,7 @@ int azb_nnet_copy(azb_nnet* dst, azb_nnet* src);
 typedef struct azb_learn_config {
   uint32_t epochs;          /* Adam steps per iteration (connect_four_net.py:13: 10); 0 = one pass over the window */
   uint32_t batch_size;      /* connect_four_net.py:14: 64 */
-  azb_train_config adam;    /* lr 1e-3 (connect_four_net.py:21), 0.9, 0.999, 1e-8 */
+  azb_train_config adam;    /* default lr 1e-4 (the reference's 1e-3, connect_four_net.py:21, assumes BatchNorm; see learn.cuh), 0.9, 0.999, 1e-8 */
   uint32_t arena_k_open;    /* random opening plies of the gating games (0 = reference) */
   uint32_t skip_first_play; /* Coach::learn's skip_first_play, coach.rs:172,240 */
   uint32_t save_files;      /* 1: write <iteration>.examples and <model_id>.azbw into checkpoint_directory */

@@ -87,7 +87,7 @@ def test_learn_first_iteration_equals_the_phases_run_by_hand(azb, oracle, tmp_pa
     losses = []
     for s in range(EPOCHS):
         idx = perm[(np.arange(BATCH) + s * BATCH) % len(perm)]
-        losses.append(cand.train((hb[idx], hp[idx], hv[idx])))
+        losses.append(cand.train((hb[idx], hp[idx], hv[idx]), lr=1e-4))  # azb_learn_config_default's step
     assert np.allclose(losses[0], r["loss_first"], rtol=1e-4, atol=1e-5)
     assert np.allclose(losses[-1], r["loss_last"], rtol=2e-2, atol=1e-3)  # fp32 atomics in the weight-gradient reduction
     counts, _, _ = azb.arena_play_games(CFG["num_arena_games"], azb.EVAL_NNET, azb.EVAL_NNET, cand, net0, k_open=2,
