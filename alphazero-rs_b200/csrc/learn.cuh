@@ -396,10 +396,22 @@ int azb_nnet_copy(azb_nnet* dst, azb_nnet* src) {
   if (dst->cfg.blocks != src->cfg.blocks || dst->cfg.precision != src->cfg.precision || dst->cfg.device != src->cfg.device)
     return fail(AZB_ERR_INVALID, "networks differ in architecture, precision or device");
   const uint64_t N = src->L.total;
-  int rc = src->sync_host();
-  if (rc) return rc;
-  rc = azb_nnet_set_params(dst, src->h_params.data(), N);
-  if (rc) return rc;
+  AZB_CUDA(cudaSetDevice(src->cfg.device));
+  // everything the forward / backward kernels read is copied device to device (no host-side tile build): the fp32 master
+  // parameters, the forward and backward bf16 weight tiles, the stem table; the head weights travel as a host struct
+  auto d2d = [](DevBuf& d, const DevBuf& s_) -> cudaError_t {
+    if (!s_.p) return cudaSuccess;
+    cudaError_t e = d.ensure(s_.bytes);
+    return e != cudaSuccess ? e : cudaMemcpy(d.p, s_.p, s_.bytes, cudaMemcpyDeviceToDevice);
+  };
+  AZB_CUDA(d2d(dst->d_params, src->d_params));
+  AZB_CUDA(d2d(dst->d_wtiles, src->d_wtiles));
+  AZB_CUDA(d2d(dst->d_wtiles_bwd, src->d_wtiles_bwd));
+  AZB_CUDA(d2d(dst->d_stem_tab, src->d_stem_tab));
+  dst->wtile_copy_bytes = src->wtile_copy_bytes;
+  dst->head_w = src->head_w;
+  dst->h_params = src->h_params;
+  dst->host_stale = src->host_stale;
   if (src->d_adam_m.bytes >= N * 4 && src->adam_t > 0) {
     AZB_CUDA(dst->d_adam_m.ensure(N * 4));
     AZB_CUDA(dst->d_adam_v.ensure(N * 4));
