@@ -574,24 +574,33 @@ struct GameStore {
 
 // Device state of the lock-step round engine (csrc/rounds.cuh).
 struct RoundEngine {
-  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v;
-  uint32_t n_slots = 0;
+  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx;
+  uint32_t n_slots = 0, dedup_mask = 0;
   int alloc(uint32_t slots) {
     n_slots = slots;
+    // leaf de-duplication table (rounds.cuh LeafBufs): 4 entries per slot and model; AZB200_LEAF_DEDUP=0 turns it off
+    static const bool dedup = !(std::getenv("AZB200_LEAF_DEDUP") && std::atoi(std::getenv("AZB200_LEAF_DEDUP")) == 0);
+    dedup_mask = dedup ? pow2_ceil(static_cast<uint64_t>(slots) * 4u) - 1u : 0u;
+    if (dedup) {
+      AZB_CUDA(dedup_keys.ensure(2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
+      AZB_CUDA(dedup_idx.ensure(2 * (static_cast<size_t>(dedup_mask) + 1) * 4));
+      AZB_CUDA(cudaMemset(dedup_keys.p, 0, 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
+    }
     AZB_CUDA(recs.ensure(static_cast<size_t>(slots) * sizeof(GameRec)));
     AZB_CUDA(active.ensure(static_cast<size_t>(slots) * 4));
-    AZB_CUDA(ctl_words.ensure(16));
+    AZB_CUDA(ctl_words.ensure(32));
     AZB_CUDA(leaf_state.ensure(static_cast<size_t>(slots) * 2 * 16));
     AZB_CUDA(leaf_count.ensure(8));
     AZB_CUDA(leaf_pi.ensure(static_cast<size_t>(slots) * 2 * 32));
     AZB_CUDA(leaf_v.ensure(static_cast<size_t>(slots) * 2 * 4));
     AZB_CUDA(cudaMemset(recs.p, 0, static_cast<size_t>(slots) * sizeof(GameRec)));  // phase = Empty
-    AZB_CUDA(cudaMemset(ctl_words.p, 0, 16));
+    AZB_CUDA(cudaMemset(ctl_words.p, 0, 32));
     AZB_CUDA(cudaMemset(leaf_count.p, 0, 8));
     return AZB_OK;
   }
   // Runs every game of the call to completion.  nets[k] evaluates the leaves of player k.
-  int run(const RoundParams& rp, const Pools& pools, GameStore& gs, azb_nnet* nets[2], uint64_t* launches) {
+  int run(const RoundParams& rp, const Pools& pools, GameStore& gs, azb_nnet* nets[2], uint64_t* launches,
+          uint64_t* nn_positions = nullptr) {
     Control ctl{};
     ctl.next_game = ctl_words.as<unsigned int>();
     ctl.n_active = ctl_words.as<unsigned int>() + 1;
@@ -602,11 +611,18 @@ struct RoundEngine {
     leaf.count = leaf_count.as<uint32_t>();
     leaf.pi = leaf_pi.as<float>();
     leaf.v = leaf_v.as<float>();
+    leaf.dkeys = dedup_keys.as<unsigned long long>();
+    leaf.didx = dedup_idx.as<uint32_t>();
+    leaf.dmask = dedup_mask;
+    leaf.nn_total = reinterpret_cast<unsigned long long*>(ctl_words.as<uint8_t>() + 16);
     const bool any_net = rp.ev_kind[0] >= AZB_EVAL_NNET || (rp.mode == kModeArena && rp.ev_kind[1] >= AZB_EVAL_NNET);
     const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
     const int check_every = any_net ? 16 : 1;
     uint64_t n_launch = 0;
     for (uint64_t it = 0;; ++it) {
+      leaf.stamp = static_cast<uint32_t>(it % 32767u) + 1u;
+      if (dedup_mask && it > 0 && leaf.stamp == 1u)  // the 15-bit stamp wrapped: forget the old rounds' entries
+        AZB_CUDA(cudaMemsetAsync(dedup_keys.p, 0, 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
       k_compact<<<1, 1024>>>(rp, recs.as<GameRec>(), ctl, leaf);
       if (it % check_every == 0) {
         unsigned int n_active = 0;
@@ -628,6 +644,11 @@ struct RoundEngine {
       AZB_CUDA(cudaGetLastError());
     }
     if (launches) *launches = n_launch;
+    if (nn_positions) {  // (the last k_compact has added the last round's counts)
+      unsigned long long total = 0;
+      AZB_CUDA(cudaMemcpy(&total, leaf.nn_total, 8, cudaMemcpyDeviceToHost));
+      *nn_positions = total;
+    }
     return AZB_OK;
   }
 };
@@ -657,7 +678,7 @@ struct azb_coach {
   RoundEngine engine;
   GameStore gs;
   // last self-play call
-  uint64_t n_games = 0, n_samples = 0, launches = 0;
+  uint64_t n_games = 0, n_samples = 0, launches = 0, nn_positions = 0;
   DevBuf next_game, offsets, out_boards, out_pis, out_vs;
   std::vector<uint32_t> h_plies;
 };
@@ -1012,6 +1033,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
                                             static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
     AZB_CUDA(cudaGetLastError());
     c->launches = 1;
+    c->nn_positions = 0;
   } else {
     rc = c->engine.alloc(static_cast<uint32_t>(n_trees));
     if (rc) return rc;
@@ -1025,7 +1047,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rp.n_games = static_cast<uint32_t>(G);
     rp.first_game_id = first_game_id;
     azb_nnet* nets[2] = {c->net, nullptr};
-    rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches);
+    rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches, &c->nn_positions);
     if (rc) return rc;
   }
   AZB_CUDA(cudaEventRecord(e1));
@@ -1061,6 +1083,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   s.device_ms = ms;
   s.launches = c->launches;
   s.trees_resident = n_trees;
+  s.nn_positions = c->nn_positions;
   c->n_games = G;
   c->n_samples = s.samples;
   if (stats) *stats = s;
@@ -1603,7 +1626,8 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   AZB_CUDA(cudaEventCreate(&e1));
   AZB_CUDA(cudaEventRecord(e0));
   uint64_t launches = 0;
-  rc = eng.run(rp, pool.pools, gs, nets, &launches);
+  uint64_t nn_positions = 0;
+  rc = eng.run(rp, pool.pools, gs, nets, &launches, &nn_positions);
   if (rc) return rc;
   AZB_CUDA(cudaEventRecord(e1));
   AZB_CUDA(cudaEventSynchronize(e1));
@@ -1637,6 +1661,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   s.games = G;
   s.device_ms = ms;
   s.launches = launches;
+  s.nn_positions = nn_positions;
   if (results) std::memcpy(results, res.data(), G);
   if (stats) *stats = s;
   return AZB_OK;

@@ -48,7 +48,20 @@ struct LeafBufs {
   uint32_t* count;  // [2]           leaves per model this round
   float* pi;        // [2][n_slots][8]  network policy (probabilities), row = dense leaf index
   float* v;         // [2][n_slots]
+  // Leaf de-duplication within a round (dmask != 0): games that share their move history grow identical trees and ask
+  // for the same positions at the same time (all games of a call during the first move, 7 groups during the second,
+  // ...; an arena without opening plies plays ONE game per seat order).  The network's answer for a position does not
+  // depend on the batch it sits in, so a position is evaluated once per round and model: the first slot to claim the
+  // position's key in a per-round hash table owns the dense batch row, the others remember the table entry and read the
+  // owner's row when they resume.  Entries carry a 15-bit round stamp above the 49-bit state key, so the table is never
+  // cleared between rounds (the host clears it when the stamp wraps).
+  unsigned long long* dkeys;    // [2][dmask + 1]  stamp << 49 | state_key
+  uint32_t* didx;               // [2][dmask + 1]  the owner's dense row
+  uint32_t dmask;               // entries per model - 1 (power of two); 0 = no de-duplication
+  uint32_t stamp;               // 1 .. 32767, changes every round
+  unsigned long long* nn_total; // positions sent through the networks so far (k_compact adds the round's counts)
 };
+constexpr uint32_t kLeafIndirect = 0x80000000u;  // GameRec.leaf_idx: low bits index didx[] instead of the batch
 
 struct RoundParams {
   SearchParams p;
@@ -76,6 +89,8 @@ __global__ void __launch_bounds__(1024) k_compact(RoundParams rp, GameRec* recs,
   __shared__ uint32_t s_base;
   const uint32_t tid = threadIdx.x;
   if (tid == 0) s_base = 0;
+  if (tid == 0) *leaf.nn_total += static_cast<unsigned long long>(leaf.count[0]) + leaf.count[1];
+  __syncthreads();
   if (tid < 2) leaf.count[tid] = 0;
   __syncthreads();
   for (uint32_t start = 0; start < rp.n_slots; start += 1024u) {
@@ -209,7 +224,9 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     Pending pd = rec->pd;
     for (uint32_t i = lane; i <= pd.plen && i < kPathCap; i += 32u) t.path[i] = rec->path[i];
     __syncwarp();
-    const size_t row = static_cast<size_t>(side) * rp.n_slots + rec->leaf_idx;
+    uint32_t li = rec->leaf_idx;
+    if (li & kLeafIndirect) li = leaf.didx[li & ~kLeafIndirect];  // a duplicate: the row of the slot that owns the position
+    const size_t row = static_cast<size_t>(side) * rp.n_slots + li;
     const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
     const float val = leaf.v[row];
     if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
@@ -286,15 +303,39 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     if (t.error) { err = t.error; break; }
     if (yielded) break;  // phase stays Search; the slot continues next round
     if (suspended) {  // hand the leaf to the batched evaluator of this side's model
-      uint32_t idx = 0;
-      if (lane == 0) idx = atomicAdd(leaf.count + side, 1u);
-      idx = __shfl_sync(kFull, idx, 0);
       if (lane == 0) {
-        leaf.state[static_cast<size_t>(side) * rp.n_slots + idx] =
-            make_uint4(static_cast<uint32_t>(leaf_pos.cur), static_cast<uint32_t>(leaf_pos.cur >> 32),
-                       static_cast<uint32_t>(leaf_pos.opp), static_cast<uint32_t>(leaf_pos.opp >> 32));
+        uint32_t ref = 0;
+        bool owner = true;
+        uint32_t at = 0;
+        if (leaf.dmask) {  // claim the position for this round, or find the slot that already has
+          const uint64_t skey = state_key(leaf_pos);
+          const unsigned long long key = skey | (static_cast<unsigned long long>(leaf.stamp) << 49);
+          const uint32_t base = static_cast<uint32_t>(side) * (leaf.dmask + 1u);
+          uint32_t h = static_cast<uint32_t>((skey * 0x9E3779B97F4A7C15ull) >> 40) & leaf.dmask;
+          for (;;) {
+            at = base + h;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(leaf.dkeys + at);
+            if ((cur >> 49) != leaf.stamp) {  // empty or left over from an earlier round
+              const unsigned long long old = atomicCAS(leaf.dkeys + at, cur, key);
+              if (old == cur) break;          // claimed
+              cur = old;
+              if ((cur >> 49) != leaf.stamp) continue;
+            }
+            if (cur == key) { owner = false; break; }
+            h = (h + 1u) & leaf.dmask;  // (the table has 4 entries per slot: it never fills)
+          }
+        }
+        if (owner) {
+          ref = atomicAdd(leaf.count + side, 1u);
+          leaf.state[static_cast<size_t>(side) * rp.n_slots + ref] =
+              make_uint4(static_cast<uint32_t>(leaf_pos.cur), static_cast<uint32_t>(leaf_pos.cur >> 32),
+                         static_cast<uint32_t>(leaf_pos.opp), static_cast<uint32_t>(leaf_pos.opp >> 32));
+          if (leaf.dmask) leaf.didx[at] = ref;  // read by the duplicates in the next round's kernel
+        } else {
+          ref = kLeafIndirect | at;
+        }
         rec->pd = pd;
-        rec->leaf_idx = idx;
+        rec->leaf_idx = ref;
       }
       __syncwarp();
       for (uint32_t i = lane; i <= pd.plen && i < kPathCap; i += 32u) rec->path[i] = t.path[i];

@@ -141,6 +141,8 @@ typedef struct azb_selfplay_stats {
   double device_ms;                     /* CUDA-event time of the self-play kernels */
   uint64_t launches;                    /* kernels launched by the call */
   uint64_t trees_resident;              /* games (trees) in flight at once */
+  uint64_t nn_positions;                /* positions that went through the network(s): <= evals, because a position several
+                                           trees ask for in the same round is evaluated once (0 for the fused evaluators) */
 } azb_selfplay_stats;
 
 /* Coach::execute_episode over n_games concurrent games — coach.rs:104-157 and the episode

@@ -80,6 +80,7 @@ pub struct azb_selfplay_stats {
     pub device_ms: f64,
     pub launches: u64,
     pub trees_resident: u64,
+    pub nn_positions: u64,
 }
 
 #[repr(C)]
