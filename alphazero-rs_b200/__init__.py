@@ -77,7 +77,8 @@ class SelfPlayStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "games", "plies", "samples", "sims", "levels", "expansions", "terminal_hits",
         "dup_links", "evals", "blocks_used_max", "owners_max")] + [("device_ms", C.c_double), ("launches", C.c_uint64),
-                                                                ("trees_resident", C.c_uint64), ("nn_positions", C.c_uint64)]
+                                                                ("trees_resident", C.c_uint64), ("nn_positions", C.c_uint64),
+                                                                ("nn_cache_hits", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

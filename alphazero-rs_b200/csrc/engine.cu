@@ -574,8 +574,27 @@ struct GameStore {
 
 // Device state of the lock-step round engine (csrc/rounds.cuh).
 struct RoundEngine {
-  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx;
-  uint32_t n_slots = 0, dedup_mask = 0;
+  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx, cache_keys, cache_vals;
+  uint32_t n_slots = 0, dedup_mask = 0, cache_mask = 0;
+  // evaluation cache (rounds.cuh LeafBufs): 2^AZB200_EVAL_CACHE_LOG2 entries per model (default 2^25 = 1.3 GB per model with
+  // the values), allocated at the first network run; AZB200_EVAL_CACHE=0 turns it off; without memory for it the run goes on
+  // without a cache
+  int ensure_cache() {
+    static const bool on = !(std::getenv("AZB200_EVAL_CACHE") && std::atoi(std::getenv("AZB200_EVAL_CACHE")) == 0);
+    static const int log2n = std::getenv("AZB200_EVAL_CACHE_LOG2") ? std::max(10, std::min(28, std::atoi(std::getenv("AZB200_EVAL_CACHE_LOG2")))) : 25;
+    if (!on) { cache_mask = 0; return AZB_OK; }
+    const size_t n = static_cast<size_t>(1) << log2n;
+    if (cache_keys.ensure(2 * n * 8) != cudaSuccess || cache_vals.ensure(2 * n * 32) != cudaSuccess) {
+      cudaGetLastError();
+      cache_keys.release();
+      cache_vals.release();
+      cache_mask = 0;
+      return AZB_OK;
+    }
+    cache_mask = static_cast<uint32_t>(n - 1);
+    AZB_CUDA(cudaMemsetAsync(cache_keys.p, 0, 2 * n * 8));  // a new call: the networks may have changed
+    return AZB_OK;
+  }
   int alloc(uint32_t slots) {
     n_slots = slots;
     // leaf de-duplication table (rounds.cuh LeafBufs): 4 entries per slot and model; AZB200_LEAF_DEDUP=0 turns it off
@@ -588,19 +607,19 @@ struct RoundEngine {
     }
     AZB_CUDA(recs.ensure(static_cast<size_t>(slots) * sizeof(GameRec)));
     AZB_CUDA(active.ensure(static_cast<size_t>(slots) * 4));
-    AZB_CUDA(ctl_words.ensure(32));
+    AZB_CUDA(ctl_words.ensure(64));
     AZB_CUDA(leaf_state.ensure(static_cast<size_t>(slots) * 2 * 16));
     AZB_CUDA(leaf_count.ensure(8));
     AZB_CUDA(leaf_pi.ensure(static_cast<size_t>(slots) * 2 * 32));
     AZB_CUDA(leaf_v.ensure(static_cast<size_t>(slots) * 2 * 4));
     AZB_CUDA(cudaMemset(recs.p, 0, static_cast<size_t>(slots) * sizeof(GameRec)));  // phase = Empty
-    AZB_CUDA(cudaMemset(ctl_words.p, 0, 32));
+    AZB_CUDA(cudaMemset(ctl_words.p, 0, 64));
     AZB_CUDA(cudaMemset(leaf_count.p, 0, 8));
     return AZB_OK;
   }
   // Runs every game of the call to completion.  nets[k] evaluates the leaves of player k.
   int run(const RoundParams& rp, const Pools& pools, GameStore& gs, azb_nnet* nets[2], uint64_t* launches,
-          uint64_t* nn_positions = nullptr) {
+          uint64_t* nn_positions = nullptr, uint64_t* cache_hits = nullptr) {
     Control ctl{};
     ctl.next_game = ctl_words.as<unsigned int>();
     ctl.n_active = ctl_words.as<unsigned int>() + 1;
@@ -615,7 +634,16 @@ struct RoundEngine {
     leaf.didx = dedup_idx.as<uint32_t>();
     leaf.dmask = dedup_mask;
     leaf.nn_total = reinterpret_cast<unsigned long long*>(ctl_words.as<uint8_t>() + 16);
+    leaf.cache_hits = reinterpret_cast<unsigned long long*>(ctl_words.as<uint8_t>() + 24);
     const bool any_net = rp.ev_kind[0] >= AZB_EVAL_NNET || (rp.mode == kModeArena && rp.ev_kind[1] >= AZB_EVAL_NNET);
+    cache_mask = 0;
+    if (any_net) {
+      const int rcc = ensure_cache();
+      if (rcc) return rcc;
+    }
+    leaf.ckeys = cache_keys.as<unsigned long long>();
+    leaf.cvals = cache_vals.as<float>();
+    leaf.cmask = cache_mask;
     const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
     const int check_every = any_net ? 16 : 1;
     uint64_t n_launch = 0;
@@ -649,6 +677,11 @@ struct RoundEngine {
       AZB_CUDA(cudaMemcpy(&total, leaf.nn_total, 8, cudaMemcpyDeviceToHost));
       *nn_positions = total;
     }
+    if (cache_hits) {
+      unsigned long long total = 0;
+      AZB_CUDA(cudaMemcpy(&total, leaf.cache_hits, 8, cudaMemcpyDeviceToHost));
+      *cache_hits = total;
+    }
     return AZB_OK;
   }
 };
@@ -678,7 +711,7 @@ struct azb_coach {
   RoundEngine engine;
   GameStore gs;
   // last self-play call
-  uint64_t n_games = 0, n_samples = 0, launches = 0, nn_positions = 0;
+  uint64_t n_games = 0, n_samples = 0, launches = 0, nn_positions = 0, nn_cache_hits = 0;
   DevBuf next_game, offsets, out_boards, out_pis, out_vs;
   std::vector<uint32_t> h_plies;
 };
@@ -1034,6 +1067,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     AZB_CUDA(cudaGetLastError());
     c->launches = 1;
     c->nn_positions = 0;
+    c->nn_cache_hits = 0;
   } else {
     rc = c->engine.alloc(static_cast<uint32_t>(n_trees));
     if (rc) return rc;
@@ -1047,7 +1081,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rp.n_games = static_cast<uint32_t>(G);
     rp.first_game_id = first_game_id;
     azb_nnet* nets[2] = {c->net, nullptr};
-    rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches, &c->nn_positions);
+    rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches, &c->nn_positions, &c->nn_cache_hits);
     if (rc) return rc;
   }
   AZB_CUDA(cudaEventRecord(e1));
@@ -1084,6 +1118,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   s.launches = c->launches;
   s.trees_resident = n_trees;
   s.nn_positions = c->nn_positions;
+  s.nn_cache_hits = c->nn_cache_hits;
   c->n_games = G;
   c->n_samples = s.samples;
   if (stats) *stats = s;
@@ -1626,8 +1661,8 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   AZB_CUDA(cudaEventCreate(&e1));
   AZB_CUDA(cudaEventRecord(e0));
   uint64_t launches = 0;
-  uint64_t nn_positions = 0;
-  rc = eng.run(rp, pool.pools, gs, nets, &launches, &nn_positions);
+  uint64_t nn_positions = 0, nn_cache_hits = 0;
+  rc = eng.run(rp, pool.pools, gs, nets, &launches, &nn_positions, &nn_cache_hits);
   if (rc) return rc;
   AZB_CUDA(cudaEventRecord(e1));
   AZB_CUDA(cudaEventSynchronize(e1));
@@ -1662,6 +1697,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   s.device_ms = ms;
   s.launches = launches;
   s.nn_positions = nn_positions;
+  s.nn_cache_hits = nn_cache_hits;
   if (results) std::memcpy(results, res.data(), G);
   if (stats) *stats = s;
   return AZB_OK;

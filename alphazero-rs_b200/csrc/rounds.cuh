@@ -60,7 +60,61 @@ struct LeafBufs {
   uint32_t dmask;               // entries per model - 1 (power of two); 0 = no de-duplication
   uint32_t stamp;               // 1 .. 32767, changes every round
   unsigned long long* nn_total; // positions sent through the networks so far (k_compact adds the round's counts)
+  // Evaluation cache for the duration of one call (cmask != 0): (state key -> raw policy[7], value) of every position a
+  // network has evaluated, per model.  A simulation whose leaf is in the cache finishes at once instead of suspending
+  // for a round; the slot that owned a batch row inserts the answer when it resumes.  Entry states: 0 empty,
+  // key | kCacheBusy while the values are being written, key | kCacheReady afterwards (values read with ld.cg).
+  unsigned long long* ckeys;    // [2][cmask + 1]
+  float* cvals;                 // [2][cmask + 1][8]
+  uint32_t cmask;
+  unsigned long long* cache_hits;
 };
+constexpr unsigned long long kCacheBusy = 1ull << 63, kCacheReady = 1ull << 62, kCacheKeyMask = (1ull << 49) - 1ull;
+constexpr int kCacheProbes = 8;
+__device__ __forceinline__ uint32_t cache_hash(uint64_t skey, uint32_t mask) {
+  return static_cast<uint32_t>((skey * 0xD6E8FEB86659FD93ull) >> 32) & mask;
+}
+// lane 0 probes; returns the entry index (warp-uniform) or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t cache_find(const LeafBufs& leaf, uint32_t side, uint64_t skey, int lane) {
+  uint32_t found = 0xFFFFFFFFu;
+  if (lane == 0) {
+    const uint32_t base = side * (leaf.cmask + 1u);
+    uint32_t h = cache_hash(skey, leaf.cmask);
+    for (int i = 0; i < kCacheProbes; ++i, h = (h + 1u) & leaf.cmask) {
+      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(leaf.ckeys + base + h);
+      if (cur == 0ull) break;
+      if ((cur & kCacheKeyMask) == skey) {
+        if (cur & kCacheReady) found = base + h;
+        break;
+      }
+    }
+  }
+  found = __shfl_sync(kFull, found, 0);
+  if (found != 0xFFFFFFFFu) __threadfence();  // the values were written before the ready key
+  return found;
+}
+// lanes 0-6 hold pi, `val` is warp-uniform
+__device__ __forceinline__ void cache_insert(const LeafBufs& leaf, uint32_t side, uint64_t skey, float pi, float val, int lane) {
+  uint32_t at = 0xFFFFFFFFu;
+  if (lane == 0) {
+    const uint32_t base = side * (leaf.cmask + 1u);
+    uint32_t h = cache_hash(skey, leaf.cmask);
+    for (int i = 0; i < kCacheProbes; ++i, h = (h + 1u) & leaf.cmask) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(leaf.ckeys + base + h);
+      if (cur == 0ull) {
+        cur = atomicCAS(leaf.ckeys + base + h, 0ull, skey | kCacheBusy);
+        if (cur == 0ull) { at = base + h; break; }
+      }
+      if ((cur & kCacheKeyMask) == skey) break;  // already there, or another slot is writing it
+    }
+  }
+  at = __shfl_sync(kFull, at, 0);
+  if (at == 0xFFFFFFFFu) return;
+  if (lane < 8) __stcg(leaf.cvals + static_cast<size_t>(at) * 8u + lane, lane < 7 ? pi : val);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(leaf.ckeys + at) = skey | kCacheReady;
+}
 constexpr uint32_t kLeafIndirect = 0x80000000u;  // GameRec.leaf_idx: low bits index didx[] instead of the batch
 
 struct RoundParams {
@@ -229,6 +283,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     const size_t row = static_cast<size_t>(side) * rp.n_slots + li;
     const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
     const float val = leaf.v[row];
+    if (leaf.cmask && !(rec->leaf_idx & kLeafIndirect)) cache_insert(leaf, side, pd.key, pi, val, lane);
     if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
     else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false, /*predict=*/true);
     sims_done++;
@@ -280,6 +335,8 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     bool suspended = false, yielded = false;
     Pending pd;
     BB leaf_pos;
+  search_more:
+    suspended = false;
     while (sims_done < p.num_sims && !t.error) {
       if (sims_left == 0u) { yielded = true; break; }
       sims_left--;
@@ -287,6 +344,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
         if (ev >= AZB_EVAL_NNET) {
           pd.kind = kPendRoot;
           pd.plen = 0;
+          pd.key = state_key(board);
           leaf_pos = board;
           suspended = true;
           break;
@@ -302,6 +360,18 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     }
     if (t.error) { err = t.error; break; }
     if (yielded) break;  // phase stays Search; the slot continues next round
+    if (suspended && leaf.cmask) {  // a position this model has already evaluated in this call: no round trip
+      const uint32_t ce = cache_find(leaf, side, pd.key, lane);
+      if (ce != 0xFFFFFFFFu) {
+        const float pi = lane < 7 ? __ldcg(leaf.cvals + static_cast<size_t>(ce) * 8u + lane) : 0.0f;
+        const float val = __ldcg(leaf.cvals + static_cast<size_t>(ce) * 8u + 7u);
+        if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
+        else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false, /*predict=*/true);
+        if (lane == 0) atomicAdd(leaf.cache_hits, 1ull);
+        sims_done++;
+        goto search_more;
+      }
+    }
     if (suspended) {  // hand the leaf to the batched evaluator of this side's model
       if (lane == 0) {
         uint32_t ref = 0;

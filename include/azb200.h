@@ -143,6 +143,8 @@ typedef struct azb_selfplay_stats {
   uint64_t trees_resident;              /* games (trees) in flight at once */
   uint64_t nn_positions;                /* positions that went through the network(s): <= evals, because a position several
                                            trees ask for in the same round is evaluated once (0 for the fused evaluators) */
+  uint64_t nn_cache_hits;               /* evaluations answered from the call's evaluation cache (positions the same network
+                                           evaluated in an earlier round of this call): no network row, no suspension */
 } azb_selfplay_stats;
 
 /* Coach::execute_episode over n_games concurrent games — coach.rs:104-157 and the episode

@@ -81,6 +81,7 @@ pub struct azb_selfplay_stats {
     pub launches: u64,
     pub trees_resident: u64,
     pub nn_positions: u64,
+    pub nn_cache_hits: u64,
 }
 
 #[repr(C)]

@@ -12,7 +12,7 @@ t0 = time.time()
 st = coach.self_play(games, 0)
 dt = time.time() - t0
 flop_per_pos = 2 * 42 * 18 * 128 + 2 * blocks * 2 * 42 * 1152 * 128 + 21504 + 1176 + 10752 + 5376 + 128
-print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "evals", "nn_positions", "device_ms", "launches")})
+print({k: st[k] for k in ("games", "plies", "sims", "levels", "expansions", "evals", "nn_positions", "nn_cache_hits", "device_ms", "launches")})
 print("sims/s=%.3e games/s=%.1f evals/s=%.3e nn_TFLOP/s(whole run, positions actually evaluated)=%.1f wall=%.1fs" % (
     st["sims"] / st["device_ms"] * 1e3, st["games"] / st["device_ms"] * 1e3, st["evals"] / st["device_ms"] * 1e3,
     st["nn_positions"] * flop_per_pos / st["device_ms"] / 1e9, dt))

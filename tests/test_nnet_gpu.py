@@ -245,8 +245,9 @@ def test_config3_parameters_sampled_games(azb, oracle):
 def test_leaf_dedup_is_invisible_and_saves_evaluations(azb, tmp_path):
     """A position several trees ask for in the same round goes through the network once (rounds.cuh LeafBufs): games
     with the same move history grow identical trees, so during the first move of a call every game wants the same
-    leaves.  The games themselves must not change: the run without de-duplication (child process, AZB200_LEAF_DEDUP=0)
-    produces the same actions, root counts and samples; only the number of evaluated positions differs."""
+    leaves; and a position the network evaluated in an earlier round of the call is answered from the call's evaluation
+    cache.  The games themselves must not change: the run without either (child process, AZB200_LEAF_DEDUP=0
+    AZB200_EVAL_CACHE=0) produces the same actions, root counts and samples; only the number of network rows differs."""
     import os, subprocess, sys
     script = (
         "import importlib, sys, numpy as np\n"
@@ -257,14 +258,14 @@ def test_leaf_dedup_is_invisible_and_saves_evaluations(azb, tmp_path):
         "st = coach.self_play(96, 0)\n"
         "tr = coach.traces(); b, p, v = coach.export_samples()\n"
         "np.savez(sys.argv[1], actions=tr['actions'], counts=tr['counts'], plies=tr['plies'], boards=b, pis=p, vs=v,\n"
-        "         evals=st['evals'], nn=st['nn_positions'])\n"
+        "         evals=st['evals'], nn=st['nn_positions'], hits=st['nn_cache_hits'])\n"
         "a = azb.NNet(seed=7, blocks=1); bnet = azb.NNet(seed=8, blocks=1)\n"
         "c0, r0, s0 = azb.arena_play_games(16, azb.EVAL_NNET, azb.EVAL_NNET, a, bnet, k_open=0, num_sims=20, seed=5)\n"
         "c2, r2, s2 = azb.arena_play_games(16, azb.EVAL_NNET, azb.EVAL_NNET, a, bnet, k_open=3, num_sims=20, seed=5)\n"
         "np.savez(sys.argv[2], r0=r0, r2=r2, e0=s0['evals'], n0=s0['nn_positions'], e2=s2['evals'], n2=s2['nn_positions'])\n")
     out = {}
     for tag, val in (("on", "1"), ("off", "0")):
-        env = dict(os.environ, AZB200_LEAF_DEDUP=val)
+        env = dict(os.environ, AZB200_LEAF_DEDUP=val, AZB200_EVAL_CACHE=val)
         r = subprocess.run([sys.executable, "-c", script, str(tmp_path / f"sp_{tag}.npz"), str(tmp_path / f"ar_{tag}.npz")],
                            env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
@@ -274,6 +275,8 @@ def test_leaf_dedup_is_invisible_and_saves_evaluations(azb, tmp_path):
         assert np.array_equal(sp_on[k], sp_off[k]), k
     assert int(sp_on["evals"]) == int(sp_off["evals"]) == int(sp_off["nn"])  # without it every evaluation is a network row
     assert int(sp_on["nn"]) < int(sp_on["evals"])                            # the shared first moves are evaluated once
+    assert int(sp_on["hits"]) > 0 and int(sp_off["hits"]) == 0               # ... and later games find them in the cache
+    assert int(sp_on["nn"]) + int(sp_on["hits"]) <= int(sp_on["evals"])
     assert np.array_equal(ar_on["r0"], ar_off["r0"]) and np.array_equal(ar_on["r2"], ar_off["r2"])
     # an arena without opening plies plays the same game 8 times per seat order: 2 distinct games' worth of rows
     assert int(ar_on["n0"]) * 6 <= int(ar_on["e0"]) and int(ar_off["n0"]) == int(ar_off["e0"])
