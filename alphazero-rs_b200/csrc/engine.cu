@@ -349,10 +349,11 @@ int encode_act_map_rows(CUtensorMap* map, void* ptr, size_t bytes) {
 // Network rounds: a slot that needs no evaluation for this many simulations yields (endgames that only hit
 // terminal nodes would otherwise hold the whole round back, every simulation of a round starting from cold
 // caches).  Measured on config 3 (8192 games x 400 sims): 1: 10.1 s, 2: 9.1, 3: 8.8, 4-6: 8.7, 8: 8.8, 16: 9.3,
-// 32: 9.8.  AZB200_ROUND_SIMS overrides for sweeps; results do not depend on it.
+// 32: 9.8; with the leaf de-duplication and the evaluation cache (a cache hit does not end a slot's round): 3: 4.1 s,
+// 5: 3.8, 8: 3.7, 12: 3.8, 20: 4.1, 32: 4.5.  AZB200_ROUND_SIMS overrides for sweeps; results do not depend on it.
 uint32_t round_sim_budget(bool arena = false) {
   static const uint32_t n = std::getenv("AZB200_ROUND_SIMS") ? static_cast<uint32_t>(std::max(1, std::atoi(std::getenv("AZB200_ROUND_SIMS")))) : 0u;
-  return n ? n : (arena ? 16u : 5u);  // (the arena share of config 4: 3.07 s with 16, 3.17 s with 5)
+  return n ? n : (arena ? 5u : 8u);  // (the arena share of config 4 with the cache: 2.49 s with 5, 2.57 with 16, 2.70 with 32)
 }
 
 // Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout),

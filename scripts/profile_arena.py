@@ -11,5 +11,5 @@ a = azb.NNet(seed=7, blocks=blocks, precision=azb.NNET_BF16_TC)
 b = azb.NNet(seed=8, blocks=blocks, precision=azb.NNET_BF16_TC)
 t0 = time.time()
 counts, res, st = azb.arena_play_games(games, azb.EVAL_NNET, azb.EVAL_NNET, a, b, k_open=k_open, num_sims=sims, seed=0xA1FA0)
-print("W/L/D of net A:", counts, {k: st[k] for k in ("games", "plies", "sims", "evals", "device_ms", "launches")})
+print("W/L/D of net A:", counts, {k: st[k] for k in ("games", "plies", "sims", "evals", "nn_positions", "nn_cache_hits", "device_ms", "launches")})
 print("games/s=%.1f sims/s=%.3e wall=%.1fs" % (st["games"] / st["device_ms"] * 1e3, st["sims"] / st["device_ms"] * 1e3, time.time() - t0))
