@@ -575,8 +575,18 @@ struct GameStore {
 
 // Device state of the lock-step round engine (csrc/rounds.cuh).
 struct RoundEngine {
-  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx, cache_keys, cache_vals;
+  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx;
   uint32_t n_slots = 0, dedup_mask = 0, cache_mask = 0;
+  // The cache's memory belongs to the calling thread (one buffer per thread, re-used by every run of that thread: a coach's
+  // self-play and the arena calls of Coach::learn follow each other): a run borrows it and clears the keys first.
+  struct CacheBufs {
+    DevBuf keys, vals;
+    int device = -1;
+  };
+  static CacheBufs& thread_cache() {
+    static thread_local CacheBufs b;
+    return b;
+  }
   // evaluation cache (rounds.cuh LeafBufs): 2^AZB200_EVAL_CACHE_LOG2 entries per model (default 2^25 = 1.3 GB per model with
   // the values), allocated at the first network run; AZB200_EVAL_CACHE=0 turns it off; without memory for it the run goes on
   // without a cache
@@ -585,15 +595,23 @@ struct RoundEngine {
     static const int log2n = std::getenv("AZB200_EVAL_CACHE_LOG2") ? std::max(10, std::min(28, std::atoi(std::getenv("AZB200_EVAL_CACHE_LOG2")))) : 25;
     if (!on) { cache_mask = 0; return AZB_OK; }
     const size_t n = static_cast<size_t>(1) << log2n;
-    if (cache_keys.ensure(2 * n * 8) != cudaSuccess || cache_vals.ensure(2 * n * 32) != cudaSuccess) {
+    CacheBufs& cb = thread_cache();
+    int dev = 0;
+    AZB_CUDA(cudaGetDevice(&dev));
+    if (cb.device != dev) {
+      cb.keys.release();
+      cb.vals.release();
+      cb.device = dev;
+    }
+    if (cb.keys.ensure(2 * n * 8) != cudaSuccess || cb.vals.ensure(2 * n * 32) != cudaSuccess) {
       cudaGetLastError();
-      cache_keys.release();
-      cache_vals.release();
+      cb.keys.release();
+      cb.vals.release();
       cache_mask = 0;
       return AZB_OK;
     }
     cache_mask = static_cast<uint32_t>(n - 1);
-    AZB_CUDA(cudaMemsetAsync(cache_keys.p, 0, 2 * n * 8));  // a new call: the networks may have changed
+    AZB_CUDA(cudaMemsetAsync(cb.keys.p, 0, 2 * n * 8));  // a new call: the networks may have changed
     return AZB_OK;
   }
   int alloc(uint32_t slots) {
@@ -642,8 +660,8 @@ struct RoundEngine {
       const int rcc = ensure_cache();
       if (rcc) return rcc;
     }
-    leaf.ckeys = cache_keys.as<unsigned long long>();
-    leaf.cvals = cache_vals.as<float>();
+    leaf.ckeys = thread_cache().keys.as<unsigned long long>();
+    leaf.cvals = thread_cache().vals.as<float>();
     leaf.cmask = cache_mask;
     const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
     const int check_every = any_net ? 16 : 1;

@@ -25,7 +25,8 @@ if "config3" in which:
     s = st["device_ms"] * 1e-3
     print(json.dumps({"workload": "config3: 8192 games x 400 sims, ResNet-6x128 bf16 leaf evaluator", "device_s": s,
                       "sims_per_sec": st["sims"] / s, "games_per_sec": st["games"] / s, "leaf_evals_per_sec": st["evals"] / s,
-                      "nn_tflops_whole_run": st["evals"] * FLOP(6) / s / 1e12, "rounds": st["launches"] // 3, "plies": st["plies"]}))
+                      "nn_positions": st["nn_positions"], "nn_cache_hits": st["nn_cache_hits"],
+                      "nn_tflops_whole_run": st["nn_positions"] * FLOP(6) / s / 1e12, "rounds": st["launches"] // 3, "plies": st["plies"]}))
 if "config4" in which:
     a = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
     b = azb.NNet(seed=8, blocks=6, precision=azb.NNET_BF16_TC)
