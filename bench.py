@@ -293,6 +293,21 @@ def main():
                                                  "kernel": "k_conv3x3_tc3 (tcgen05 cta_group::2, resident weights, TMA tiles reused by all taps)"}}
         except Exception as e:  # never fail the headline line on the secondary measurement
             line["nnet_forward"] = {"error": repr(e)}
+        # secondary evidence: BASELINE config 3 itself, one pass (8192 games x 400 sims to completion with that network as the
+        # batched leaf evaluator; CUDA-event device time from the library).  evaluations = what the trees asked for;
+        # network_rows = positions that went through the network (a position is evaluated once per call: in-round
+        # de-duplication + evaluation cache); the games are identical with both switched off.
+        try:
+            c3 = azb.Coach(nnet=net, num_sims=400, seed=0xA1FA0, evaluator=azb.EVAL_NNET, device=local_rank)
+            st3 = c3.self_play(8192, 0)
+            s3 = st3["device_ms"] * 1e-3
+            line["config3"] = {"workload": "connect-four self-play, random-init ResNet-6x128 bf16 tcgen05 leaf evaluator, 8192 games x 400 sims",
+                               "device_s": s3, "sims_per_sec": st3["sims"] / s3, "games_per_sec": st3["games"] / s3,
+                               "evaluations": st3["evals"], "network_rows": st3["nn_positions"], "cache_hits": st3["nn_cache_hits"],
+                               "rounds": st3["launches"] // 3, "plies": st3["plies"]}
+            c3.close()
+        except Exception as e:
+            line["config3"] = {"error": repr(e)}
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
         ge.build_oracle()
         import oracle_api as orc
