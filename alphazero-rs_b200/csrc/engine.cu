@@ -670,7 +670,9 @@ struct RoundEngine {
       leaf.stamp = static_cast<uint32_t>(it % 32767u) + 1u;
       if (dedup_mask && it > 0 && leaf.stamp == 1u)  // the 15-bit stamp wrapped: forget the old rounds' entries
         AZB_CUDA(cudaMemsetAsync(dedup_keys.p, 0, 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
-      k_compact<<<1, 1024>>>(rp, recs.as<GameRec>(), ctl, leaf);
+      ctl.n_active = ctl_words.as<unsigned int>() + 1 + (it & 1u);       // double-buffered (k_compact)
+      ctl.n_active_next = ctl_words.as<unsigned int>() + 1 + ((it + 1u) & 1u);
+      k_compact<<<(rp.n_slots + 255u) / 256u, 256>>>(rp, recs.as<GameRec>(), ctl, leaf);
       if (it % check_every == 0) {
         unsigned int n_active = 0;
         AZB_CUDA(cudaMemcpy(&n_active, ctl.n_active, 4, cudaMemcpyDeviceToHost));
