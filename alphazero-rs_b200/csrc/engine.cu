@@ -620,9 +620,9 @@ struct RoundEngine {
     static const bool dedup = !(std::getenv("AZB200_LEAF_DEDUP") && std::atoi(std::getenv("AZB200_LEAF_DEDUP")) == 0);
     dedup_mask = dedup ? pow2_ceil(static_cast<uint64_t>(slots) * 4u) - 1u : 0u;
     if (dedup) {
-      AZB_CUDA(dedup_keys.ensure(2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
-      AZB_CUDA(dedup_idx.ensure(2 * (static_cast<size_t>(dedup_mask) + 1) * 4));
-      AZB_CUDA(cudaMemset(dedup_keys.p, 0, 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
+      AZB_CUDA(dedup_keys.ensure(4 * (static_cast<size_t>(dedup_mask) + 1) * 8));  // 2 round parities x 2 models
+      AZB_CUDA(dedup_idx.ensure(4 * (static_cast<size_t>(dedup_mask) + 1) * 4));
+      AZB_CUDA(cudaMemset(dedup_keys.p, 0, 4 * (static_cast<size_t>(dedup_mask) + 1) * 8));
     }
     AZB_CUDA(recs.ensure(static_cast<size_t>(slots) * sizeof(GameRec)));
     AZB_CUDA(active.ensure(static_cast<size_t>(slots) * 4));
@@ -668,8 +668,12 @@ struct RoundEngine {
     uint64_t n_launch = 0;
     for (uint64_t it = 0;; ++it) {
       leaf.stamp = static_cast<uint32_t>(it % 32767u) + 1u;
-      if (dedup_mask && it > 0 && leaf.stamp == 1u)  // the 15-bit stamp wrapped: forget the old rounds' entries
-        AZB_CUDA(cudaMemsetAsync(dedup_keys.p, 0, 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
+      leaf.dpar = static_cast<uint32_t>(it & 1u);
+      // the 15-bit stamp wrapped: forget the old rounds' entries of the table this round claims in (the other one is still
+      // being read by the previous round's duplicates; its turn comes next round)
+      if (dedup_mask && it > 1 && (leaf.stamp == 1u || leaf.stamp == 2u))
+        AZB_CUDA(cudaMemsetAsync(dedup_keys.as<uint8_t>() + static_cast<size_t>(leaf.dpar) * 2 * (static_cast<size_t>(dedup_mask) + 1) * 8, 0,
+                                 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
       ctl.n_active = ctl_words.as<unsigned int>() + 1 + (it & 1u);       // double-buffered (k_compact)
       ctl.n_active_next = ctl_words.as<unsigned int>() + 1 + ((it + 1u) & 1u);
       k_compact<<<(rp.n_slots + 255u) / 256u, 256>>>(rp, recs.as<GameRec>(), ctl, leaf);

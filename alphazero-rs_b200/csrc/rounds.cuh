@@ -55,10 +55,13 @@ struct LeafBufs {
   // position's key in a per-round hash table owns the dense batch row, the others remember the table entry and read the
   // owner's row when they resume.  Entries carry a 15-bit round stamp above the 49-bit state key, so the table is never
   // cleared between rounds (the host clears it when the stamp wraps).
-  unsigned long long* dkeys;    // [2][dmask + 1]  stamp << 49 | state_key
-  uint32_t* didx;               // [2][dmask + 1]  the owner's dense row
+  // Two tables, used by even and odd rounds in turn: the entries of round r are read when its duplicates resume in round
+  // r + 1, WHILE other slots of round r + 1 already claim entries for their new leaves — in the other table.
+  unsigned long long* dkeys;    // [2 parities][2 models][dmask + 1]  stamp << 49 | state_key
+  uint32_t* didx;               // [2 parities][2 models][dmask + 1]  the owner's dense row
   uint32_t dmask;               // entries per model - 1 (power of two); 0 = no de-duplication
   uint32_t stamp;               // 1 .. 32767, changes every round
+  uint32_t dpar;                // round parity: which table this round's claims go to
   unsigned long long* nn_total; // positions sent through the networks so far (k_compact adds the round's counts)
   // Evaluation cache for the duration of one call (cmask != 0): (state key -> raw policy[7], value) of every position a
   // network has evaluated, per model.  A simulation whose leaf is in the cache finishes at once instead of suspending
@@ -375,7 +378,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
         if (leaf.dmask) {  // claim the position for this round, or find the slot that already has
           const uint64_t skey = state_key(leaf_pos);
           const unsigned long long key = skey | (static_cast<unsigned long long>(leaf.stamp) << 49);
-          const uint32_t base = static_cast<uint32_t>(side) * (leaf.dmask + 1u);
+          const uint32_t base = (leaf.dpar * 2u + static_cast<uint32_t>(side)) * (leaf.dmask + 1u);
           uint32_t h = static_cast<uint32_t>((skey * 0x9E3779B97F4A7C15ull) >> 40) & leaf.dmask;
           for (;;) {
             at = base + h;
