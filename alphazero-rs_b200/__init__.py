@@ -84,6 +84,11 @@ class SelfPlayStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ArenaOpts(C.Structure):
+    """azb_arena_opts"""
+    _fields_ = [("k_open", C.c_uint32), ("shared_trees", C.c_uint32), ("first_game_id", C.c_uint64)]
+
+
 class NnetConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("blocks", C.c_int32), ("precision", C.c_int32),
                 ("reserved", C.c_int32), ("seed", C.c_uint64)]
@@ -96,7 +101,7 @@ class TrainConfig(C.Structure):
 class LearnConfig(C.Structure):
     """azb_learn_config: the training schedule of an iteration (connect_four_net.py:13-21) + Coach::learn's flags."""
     _fields_ = [("epochs", C.c_uint32), ("batch_size", C.c_uint32), ("adam", TrainConfig), ("arena_k_open", C.c_uint32),
-                ("skip_first_play", C.c_uint32), ("save_files", C.c_uint32), ("reserved", C.c_uint32)]
+                ("skip_first_play", C.c_uint32), ("save_files", C.c_uint32), ("arena_shared_trees", C.c_uint32)]
 
 
 class LearnReport(C.Structure):
@@ -223,6 +228,8 @@ def _load():
         "azb_nnet_wgrad_hook": [vp, vp, vp, u64, vp],
         "azb_arena_play_games": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, u32, vp, vp,
                                  C.POINTER(SelfPlayStats)],
+        "azb_arena_play_games_ex": [C.POINTER(Config), u64, C.c_int32, C.c_int32, vp, vp, C.POINTER(ArenaOpts), vp, vp, vp, vp, vp,
+                                    C.POINTER(SelfPlayStats)],
         "azb_examples_write": [C.c_char_p, u64, vp, vp, vp, vp],
         "azb_examples_stat": [C.c_char_p, C.POINTER(u64), vp, u64, C.POINTER(u64)],
         "azb_examples_read": [C.c_char_p, vp, vp, vp, u64],
@@ -519,8 +526,8 @@ class Coach:
 
 
     # ---- Coach::learn and the sample history (coach.rs:55-81,159-396) ----
-    def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-4, arena_k_open=0,
-              save_files=True, seed=7, blocks=6, dist=None):
+    def learn(self, net_cfg=None, skip_first_play=False, epochs=10, batch_size=64, lr=1e-4, arena_k_open=None,
+              save_files=True, seed=7, blocks=6, dist=None, arena_shared_trees=False):
         """Coach::learn(checkpoint, skip_first_play, ...) — coach.rs:169-396.  Returns (reports, accepted NNet).
         With `dist` (an initialised torch.distributed, one process per GPU) the iteration is data parallel
         (azb_coach_learn_dist): self-play and arena games sharded over the ranks, gradients averaged by all-reduce."""
@@ -528,7 +535,10 @@ class Coach:
             net_cfg = NnetConfig(self.cfg.device, blocks, NNET_BF16_TC, 0, seed)
         lc = LearnConfig()
         lib.azb_learn_config_default(C.byref(lc))
-        lc.epochs, lc.batch_size, lc.arena_k_open = epochs, batch_size, arena_k_open
+        lc.epochs, lc.batch_size = epochs, batch_size
+        if arena_k_open is not None:
+            lc.arena_k_open = arena_k_open
+        lc.arena_shared_trees = int(arena_shared_trees)
         lc.adam.lr = lr
         lc.skip_first_play, lc.save_files = int(skip_first_play), int(save_files)
         n_it = int(self.cfg.num_iters)
@@ -748,3 +758,24 @@ def arena_play_games(num, eval_a, eval_b, net_a=None, net_b=None, k_open=0, **cf
     _check(lib.azb_arena_play_games(C.byref(config), num, eval_a, eval_b, net_a._h if net_a else None,
                                     net_b._h if net_b else None, k_open, _ptr(counts), _ptr(results), C.byref(st)))
     return tuple(int(x) for x in counts), results[: 2 * (num // 2)], st.as_dict()
+
+
+def arena_play_games_traced(num, eval_a, eval_b, net_a=None, net_b=None, k_open=0, shared_trees=0, first_game_id=0, **cfg):
+    """azb_arena_play_games_ex: the match with its options (shared_trees = the reference's persistent tree pair,
+    coach.rs:333-354) and the per-game traces.  Returns ((win, loss, draw), results, stats,
+    dict(actions[G, 64], counts[G, 64, 7], plies[G]))."""
+    config = cfg.pop("config", None) or default_config(**cfg)
+    g = max(1, 2 * (num // 2))
+    counts = np.zeros(3, np.uint64)
+    results = np.zeros(g, np.int8)
+    actions = np.full((g, 64), 0xFF, np.uint8)
+    rc = np.zeros((g, 64, 7), np.uint16)
+    plies = np.zeros(g, np.uint32)
+    st = SelfPlayStats()
+    opts = ArenaOpts(k_open, shared_trees, first_game_id)
+    _check(lib.azb_arena_play_games_ex(C.byref(config), num, eval_a, eval_b, net_a._h if net_a else None,
+                                       net_b._h if net_b else None, C.byref(opts), _ptr(counts), _ptr(results),
+                                       _ptr(actions), _ptr(rc), _ptr(plies), C.byref(st)))
+    n = 2 * (num // 2)
+    return (tuple(int(x) for x in counts), results[:n], st.as_dict(),
+            dict(actions=actions[:n], counts=rc[:n], plies=plies[:n]))

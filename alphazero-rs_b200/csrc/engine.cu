@@ -12,6 +12,7 @@
 #include <memory>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/azb200.h"
@@ -356,6 +357,10 @@ uint32_t round_sim_budget(bool arena = false) {
   return n ? n : (arena ? 5u : 8u);  // (the arena share of config 4 with the cache: 2.49 s with 5, 2.57 with 16, 2.70 with 32)
 }
 
+// Programmatic dependent launch between the tower's layers (AZB200_TC_PDL=0 turns it off; the round graph's capture
+// also turns it off when the driver refuses programmatic edges inside a capture)
+bool g_tc_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
+
 // Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout),
 // 2 = k_conv3x3_tc2 (CTA pair, TMA im2col per tap, dense layout), default 3 = k_conv3x3_tc3 (CTA pair, the
 // tile fetched once and reused by all taps, padded layout).
@@ -431,7 +436,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
   // single-CTA kernel with streamed weight tiles.
   const bool use_pair = mode != 0;
-  static const bool use_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
+  const bool use_pdl = g_tc_pdl;
   const uint32_t pair_tiles = (max_batch * lay.pos_rows + kT2PairRows - 1) / kT2PairRows;
   static int max_pairs = -1;  // co-resident CTA pairs (one CTA per SM; a GPC with an odd SM count leaves one out)
   if (max_pairs < 0) {
@@ -636,10 +641,37 @@ struct RoundEngine {
     AZB_CUDA(cudaMemset(leaf_count.p, 0, 8));
     return AZB_OK;
   }
+  // One stream per engine: a blocking stream (it orders itself against the legacy default stream the rest of the library
+  // uses) — stream capture needs a real stream.  The host-visible progress word lives in page-locked memory.
+  cudaStream_t stream = nullptr;
+  unsigned long long* h_progress = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~RoundEngine() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (stream) cudaStreamDestroy(stream);
+    if (h_progress) cudaFreeHost(h_progress);
+  }
   // Runs every game of the call to completion.  nets[k] evaluates the leaves of player k.
+  //
+  // A round = k_compact, k_round and one dense forward pass per model (stem, 2R convolutions, heads): ~16 launches of
+  // 5-25 us each.  Launched one by one with a blocking copy every 16 rounds they left ~40 % of the device timeline empty
+  // (profiles/r1_configs.md: 323 us per round against 186 us of kernels).  Now nothing in a round depends on the host:
+  // the round number lives on the device (de-duplication stamp), grids are sized for the slot count and read the live
+  // counts from device memory, so an even + odd round pair is captured ONCE into a CUDA graph and replayed; the host
+  // follows the run through a page-locked progress word that every k_round writes and stops launching when it reads
+  // "no live slot" (it runs at most kRunAhead rounds ahead; rounds after the end find nothing to do and cost a few us).
+  // AZB200_GRAPH=0 launches the same kernels one by one.
   int run(const RoundParams& rp, const Pools& pools, GameStore& gs, azb_nnet* nets[2], uint64_t* launches,
           uint64_t* nn_positions = nullptr, uint64_t* cache_hits = nullptr) {
+    constexpr uint64_t kRunAhead = 48;
+    static const bool use_graph = !(std::getenv("AZB200_GRAPH") && std::atoi(std::getenv("AZB200_GRAPH")) == 0) &&
+                                  !std::getenv("AZB200_TC_DEBUG");
+    if (!stream) AZB_CUDA(cudaStreamCreate(&stream));
+    if (!h_progress) AZB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_progress), 8, cudaHostAllocMapped));
+    *reinterpret_cast<volatile unsigned long long*>(h_progress) = 0ull;
     Control ctl{};
+    ctl.round = ctl_words.as<unsigned int>() + 8;
+    ctl.host_progress = h_progress;
     ctl.next_game = ctl_words.as<unsigned int>();
     ctl.n_active = ctl_words.as<unsigned int>() + 1;
     ctl.active_list = active.as<uint32_t>();
@@ -664,38 +696,104 @@ struct RoundEngine {
     leaf.cvals = thread_cache().vals.as<float>();
     leaf.cmask = cache_mask;
     const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int check_every = any_net ? 16 : 1;
-    uint64_t n_launch = 0;
-    for (uint64_t it = 0;; ++it) {
-      leaf.stamp = static_cast<uint32_t>(it % 32767u) + 1u;
-      leaf.dpar = static_cast<uint32_t>(it & 1u);
-      // the 15-bit stamp wrapped: forget the old rounds' entries of the table this round claims in (the other one is still
-      // being read by the previous round's duplicates; its turn comes next round)
-      if (dedup_mask && it > 1 && (leaf.stamp == 1u || leaf.stamp == 2u))
-        AZB_CUDA(cudaMemsetAsync(dedup_keys.as<uint8_t>() + static_cast<size_t>(leaf.dpar) * 2 * (static_cast<size_t>(dedup_mask) + 1) * 8, 0,
-                                 2 * (static_cast<size_t>(dedup_mask) + 1) * 8));
-      ctl.n_active = ctl_words.as<unsigned int>() + 1 + (it & 1u);       // double-buffered (k_compact)
-      ctl.n_active_next = ctl_words.as<unsigned int>() + 1 + ((it + 1u) & 1u);
-      k_compact<<<(rp.n_slots + 255u) / 256u, 256>>>(rp, recs.as<GameRec>(), ctl, leaf);
-      if (it % check_every == 0) {
-        unsigned int n_active = 0;
-        AZB_CUDA(cudaMemcpy(&n_active, ctl.n_active, 4, cudaMemcpyDeviceToHost));
-        if (n_active == 0) break;
-      }
-      k_round<<<grid, kWarpsPerCta * 32>>>(rp, pools, recs.as<GameRec>(), ctl, leaf, gs.g);
-      n_launch += 2;
+    uint64_t per_round = 2;
+    // one round of parity `par` on `stream` (the only per-round differences: which counter / which de-duplication table)
+    auto launch_round = [&](uint32_t par) -> int {
+      Control c = ctl;
+      LeafBufs lf = leaf;
+      lf.dpar = par;
+      c.n_active = ctl_words.as<unsigned int>() + 1 + par;  // double-buffered (k_compact)
+      c.n_active_next = ctl_words.as<unsigned int>() + 1 + (par ^ 1u);
+      k_compact<<<(rp.n_slots + 255u) / 256u, 256, 0, stream>>>(rp, recs.as<GameRec>(), c, lf);
+      k_round<<<grid, kWarpsPerCta * 32, 0, stream>>>(rp, pools, recs.as<GameRec>(), c, lf, gs.g);
+      AZB_CUDA(cudaGetLastError());
       if (any_net) {
         for (int k = 0; k < 2; ++k) {
           if (!nets[k] || rp.ev_kind[k] < AZB_EVAL_NNET) continue;
           if (k == 1 && rp.mode != kModeArena) continue;
-          int rc = nnet_forward(nets[k], leaf.state + static_cast<size_t>(k) * rp.n_slots, leaf.count + k, rp.n_slots,
-                                leaf.pi + static_cast<size_t>(k) * rp.n_slots * 8, leaf.v + static_cast<size_t>(k) * rp.n_slots, 0);
+          int rc = nnet_forward(nets[k], lf.state + static_cast<size_t>(k) * rp.n_slots, lf.count + k, rp.n_slots,
+                                lf.pi + static_cast<size_t>(k) * rp.n_slots * 8, lf.v + static_cast<size_t>(k) * rp.n_slots, stream);
           if (rc) return rc;
-          n_launch += 1;
         }
       }
-      AZB_CUDA(cudaGetLastError());
+      return AZB_OK;
+    };
+    if (any_net)
+      for (int k = 0; k < 2; ++k)
+        if (nets[k] && rp.ev_kind[k] >= AZB_EVAL_NNET && (k == 0 || rp.mode == kModeArena))
+          per_round += (nets[k]->cfg.precision == AZB_NNET_FP32) ? 1 : 2 + 2 * nets[k]->L.R;
+    // the progress word: what the last started round saw
+    auto progress = [&](uint64_t* round_seen, uint32_t* live) {
+      const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(h_progress);
+      *round_seen = v >> 32;
+      *live = static_cast<uint32_t>(v);
+    };
+    auto wrap_clear = [&](uint64_t it) -> int {  // the stamp wraps at this round pair: forget the old rounds' claims
+      if (dedup_mask && it > 0 && it % kStampPeriod == 0)
+        AZB_CUDA(cudaMemsetAsync(dedup_keys.p, 0, 4 * (static_cast<size_t>(dedup_mask) + 1) * 8, stream));
+      return AZB_OK;
+    };
+    uint64_t it = 0;  // rounds launched
+    bool done = false;
+    // rounds 0 and 1 one by one: they also run every first-use initialisation of the forward pass outside a capture
+    for (; it < 2; ++it) {
+      const int rc = launch_round(static_cast<uint32_t>(it & 1u));
+      if (rc) return rc;
     }
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (use_graph) {
+      for (int attempt = 0; attempt < 2 && !graph_exec; ++attempt) {
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          ok = launch_round(0u) == AZB_OK && launch_round(1u) == AZB_OK;
+          const bool ended = cudaStreamEndCapture(stream, &graph) == cudaSuccess && graph != nullptr;
+          ok = ok && ended;
+        }
+        if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+          cudaGetLastError();
+          graph_exec = nullptr;
+          if (attempt == 0 && g_tc_pdl) g_tc_pdl = false;  // programmatic edges refused inside a capture: plain edges
+          else break;
+        }
+      }
+    }
+    uint64_t last_seen = 0;
+    auto last_change = std::chrono::steady_clock::now();
+    while (!done) {
+      uint64_t seen = 0;
+      uint32_t live = 1;
+      progress(&seen, &live);
+      if (seen >= 1 && live == 0u) break;
+      if (it >= seen + kRunAhead) {  // far enough ahead: let the device catch up
+        if (seen != last_seen) {
+          last_seen = seen;
+          last_change = std::chrono::steady_clock::now();
+        } else if (std::chrono::steady_clock::now() - last_change > std::chrono::seconds(60)) {
+          // no round has started for a minute: a fault on the device (the next CUDA call reports it) or a stuck kernel
+          const cudaError_t e = cudaStreamQuery(stream);
+          return fail(AZB_ERR_CUDA, std::string("round engine made no progress for 60 s: ") +
+                                        (e == cudaSuccess || e == cudaErrorNotReady ? "kernels still running" : cudaGetErrorString(e)));
+        }
+        std::this_thread::yield();
+        continue;
+      }
+      int rc = wrap_clear(it);
+      if (rc) return rc;
+      if (graph_exec) {
+        AZB_CUDA(cudaGraphLaunch(graph_exec, stream));
+      } else {
+        rc = launch_round(0u);
+        if (rc) return rc;
+        rc = launch_round(1u);
+        if (rc) return rc;
+      }
+      it += 2;
+    }
+    AZB_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t n_launch = it * per_round;
     if (launches) *launches = n_launch;
     if (nn_positions) {  // (the last k_compact has added the last round's counts)
       unsigned long long total = 0;
@@ -1630,10 +1728,13 @@ int azb_coach_set_nnet(azb_coach* c, azb_nnet* n) {
 // ---------------------------------------------------------------------------------------------
 // arena
 // ---------------------------------------------------------------------------------------------
-int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
-                         azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
-                         azb_selfplay_stats* stats) {
+int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
+                            azb_nnet* net_b, const azb_arena_opts* opts, uint64_t out_counts[3], int8_t* results,
+                            uint8_t* actions, uint16_t* root_counts, uint32_t* plies, azb_selfplay_stats* stats) {
   if (!out_counts) return fail(AZB_ERR_INVALID, "NULL argument");
+  const azb_arena_opts o = opts ? *opts : azb_arena_opts{0u, 0u, 0ull};
+  const uint32_t k_open = o.k_open;
+  const bool shared = o.shared_trees != 0u;
   int rc = validate(cfg);
   if (rc) return rc;
   for (int k = 0; k < 2; ++k) {
@@ -1647,8 +1748,9 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   if (G > (1u << 26)) return fail(AZB_ERR_INVALID, "num out of range");
   if (azb_device_count() == 0) return fail(AZB_ERR_CUDA, "no CUDA device: libazb200 has no CPU fallback");
   AZB_CUDA(cudaSetDevice(cfg->device));
-  // each player's tree sees every second ply: at most 21 searches + F12 roots
-  const SearchParams p = make_params(*cfg, kMaxPlies / 2 + 1);
+  // each player's tree sees every second ply: at most 21 searches + F12 roots (per game; a shared tree pair lives
+  // through all G games of the match)
+  const SearchParams p = make_params(*cfg, (kMaxPlies / 2 + 1) * (shared ? G : 1));
   uint32_t resident = 0;
   rc = resident_trees(cfg->device, &resident);
   if (rc) return rc;
@@ -1658,6 +1760,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   uint64_t n_slots = std::min<uint64_t>({G, resident, by_mem});
   if (cfg->max_concurrent_games) n_slots = std::min<uint64_t>(n_slots, cfg->max_concurrent_games);
   if (n_slots == 0) return fail(AZB_ERR_CAPACITY, "not enough device memory for one tree pair");
+  if (shared) n_slots = 1;  // coach.rs:333-372: one pmcts, one nmcts, games one after the other
   TreePool pool;
   rc = pool.alloc(p, static_cast<uint32_t>(2 * n_slots));
   if (rc) return rc;
@@ -1679,7 +1782,8 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   rp.n_games = static_cast<uint32_t>(G);
   rp.half = static_cast<uint32_t>(half);
   rp.k_open = k_open;
-  rp.first_game_id = 0;
+  rp.shared = shared ? 1u : 0u;
+  rp.first_game_id = o.first_game_id;
   azb_nnet* nets[2] = {net_a, net_b};
   cudaEvent_t e0, e1;
   AZB_CUDA(cudaEventCreate(&e0));
@@ -1709,6 +1813,7 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
     else if (res[i] == -win_cond) out_counts[1]++;
     else out_counts[2]++;
     s.plies += h_plies[i];
+    if (shared && i + 1 < G) continue;  // shared trees: the counters are cumulative, the last game carries the totals
     s.sims += h_stats[i * 8 + 0];
     s.levels += h_stats[i * 8 + 1];
     s.expansions += h_stats[i * 8 + 2];
@@ -1724,9 +1829,21 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
   s.nn_positions = nn_positions;
   s.nn_cache_hits = nn_cache_hits;
   if (results) std::memcpy(results, res.data(), G);
+  if (actions) AZB_CUDA(cudaMemcpy(actions, gs.actions.p, G * kTraceStride, cudaMemcpyDeviceToHost));
+  if (root_counts) AZB_CUDA(cudaMemcpy(root_counts, gs.counts.p, G * kTraceStride * 14, cudaMemcpyDeviceToHost));
+  if (plies) std::memcpy(plies, h_plies.data(), G * 4);
   if (stats) *stats = s;
   return AZB_OK;
 }
+
+int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
+                         azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
+                         azb_selfplay_stats* stats) {
+  const azb_arena_opts o{k_open, 0u, 0ull};
+  return azb_arena_play_games_ex(cfg, num, eval_a, eval_b, net_a, net_b, &o, out_counts, results, nullptr, nullptr, nullptr,
+                                 stats);
+}
+
 
 }  // extern "C"
 

@@ -28,7 +28,8 @@ __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchPa
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
   t.path = s_path[wi];
   t.n_blocks = t.n_owners = t.error = t.slow = 0u;
-  t.pred_len = 0u;
+  t.pred_len = t.hold = 0u;
+  t.leaf_slot = t.leaf_meta = 0u;
   t.stat = 0u;
   t.uni_prior = uniform_prior_table(threadIdx.x & 31);
   return t;

@@ -313,6 +313,8 @@ void azb_learn_config_default(azb_learn_config* lc) {
   // (profiles/r1_train.md): the default step is 1e-4
   lc->adam = azb_train_config{1e-4f, 0.9f, 0.999f, 1e-8f};
   lc->save_files = 1;
+  // gating games: 4 random opening plies (see azb_learn_config.arena_k_open for why 0 is not the default here)
+  lc->arena_k_open = 4;
 }
 
 // ---- weight checkpoints ------------------------------------------------------------------------------------
@@ -666,9 +668,13 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
       uint64_t pair_first = 0, pairs = 0;  // arena.rs:83: num / 2 games per seat order; the pairs are split over the ranks
       split(cfg.num_arena_games / 2, &pair_first, &pairs);
       azb_config acfg = cfg;
-      acfg.seed = cfg.seed + rank;  // the arena keys its opening streams by (seed, game): one seed per rank
-      rc = azb_arena_play_games(&acfg, 2 * pairs, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), lc.arena_k_open, counts, nullptr,
-                                nullptr);
+      // the arena keys its opening streams by (seed, game id): ids are distinct over iterations, ranks and games
+      azb_arena_opts ao{};
+      ao.k_open = lc.arena_k_open;
+      ao.shared_trees = lc.arena_shared_trees;
+      ao.first_game_id = iteration * cfg.num_arena_games + 2 * pair_first;
+      rc = azb_arena_play_games_ex(&acfg, 2 * pairs, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), &ao, counts, nullptr,
+                                   nullptr, nullptr, nullptr, nullptr);
       if (rc) return rc;
       rc = sum_u64(counts, 3);
       if (rc) return rc;

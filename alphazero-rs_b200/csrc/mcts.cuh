@@ -67,6 +67,11 @@ struct __align__(16) PathEnt {
   uint32_t blk;  // the node's child block
   uint32_t n;    // the node's N after the last backup that passed through it
   uint32_t sq;   // f32 bits of sqrt(n + 1 + 1e-6): best_child's parent term for the next visit
+  // hold bound (see backup_path): written when the level's arg-max is taken, s0 = the parent term it was taken with
+  float m0;      // >= u of every edge but the chosen one at s0, rounding slack included (-inf: no other edge)
+  float e0s;     // >= (largest non-negative exploration term of those edges at s0) / s0
+  float s0;
+  float cp;      // RN(cpuct * P[action]) of the chosen edge
   uint64_t cur, opp;  // the node's position, canonical for its side to move
 };
 
@@ -77,6 +82,8 @@ struct WarpTree {
   PathEnt* path;   // shared memory, kPathCap entries
   const uint4* win;  // shared memory, 8 entries: win_table()
   uint32_t pred_len;  // levels [0, pred_len) of `path` describe nodes the previous simulation walked
+  uint32_t hold;      // bit l: level l (< pred_len, < 31) provably selects its recorded edge again (backup_path)
+  uint32_t leaf_slot, leaf_meta;  // the finished game the previous simulation ended in (when it did)
   uint32_t n_blocks, n_owners, error;
   uint32_t slow;  // != 0: use __fdiv_rn in the level loop (a prior outside the range the FMA division
                   // is proven for, or visit counts that may wrap the 16-bit N field, quirk Q6)
@@ -386,20 +393,52 @@ struct Pending {
 
 // backup (:361-370): the leaf gets +v, then up node_path; Q2 corrected alternates the sign.
 // Entry l < plen is path node l, entry plen is the leaf; the sign flips with distance.
+//
+// HOLD: the backup also decides, for every level l < plen at once (lane l), whether the NEXT simulation's best_child
+// at that node is certain to pick the recorded edge again.  Between two simulations only the chosen edge's statistics
+// change (q, n of the child: lane l + 1 has just computed them) and the parent term s = sqrt(N + 1e-6) grows; every
+// other edge j keeps q_j, n_j (a persisting level is on every path in between, its other children are on none), so
+//   u_j(s1) <= u_j(s0) + ex_j(s0) * (s1/s0 - 1) + rounding  <=  m0 + e0s * (s1 - s0)
+// with the two maxima m0 / e0s recorded when the level's arg-max was last taken (score_level).  If the chosen edge's
+// exact new u (same operations as best_child) is strictly above that bound, it is the unique maximum: the level holds
+// and the next walk skips it without reading its block.  A level that does not hold is simply evaluated in full, which
+// refreshes the bound; results are bit-identical with the one-level-at-a-time walk.
+template <bool HOLD>
 __device__ __forceinline__ void backup_path(WarpTree& t, const SearchParams& p, uint32_t plen,
                                             uint32_t leaf_slot, float v, uint32_t levels, int lane) {
   const bool alternate = !(p.quirks & AZB_Q2_BACKUP_NO_ALTERNATE);
   __syncwarp();
+  uint32_t hold = 0u;
   for (uint32_t base = 0; base <= plen; base += 32u) {
     const uint32_t l = base + lane;
+    uint32_t n_new = 0u, q_bits = 0u;
+    float sq = 0.0f;
     if (l <= plen) {
       const uint32_t slot = l < plen ? (t.path[l].sa >> 3) : leaf_slot;
       const bool neg = alternate && ((plen - l) & 1u);
-      const uint32_t n_new = backup_node(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
-      const float sq = sqrt_count(__fadd_rn(static_cast<float>((n_new + 1u) & 0xFFFFu), kEps));
+      const BackupRegs r = backup_prepare(t, slot, __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+      backup_commit(t, slot, r);
+      n_new = r.n_new;
+      q_bits = r.q_bits;
+      sq = sqrt_count(__fadd_rn(static_cast<float>((n_new + 1u) & 0xFFFFu), kEps));
       *reinterpret_cast<uint2*>(&t.path[l].n) = make_uint2(n_new, __float_as_uint(sq));
     }
+    if (HOLD && base == 0u) {
+      const uint32_t cn = __shfl_down_sync(kFull, n_new, 1);  // the chosen edge's child is level l + 1
+      const float cq = __uint_as_float(__shfl_down_sync(kFull, q_bits, 1));
+      bool h = false;
+      if (l < plen && lane < 31) {
+        const float4 b = *reinterpret_cast<const float4*>(&t.path[l].m0);  // {m0, e0s, s0, cp}
+        const float t3 = __fmul_rn(b.w, sq);
+        const float t4 = static_cast<float>((1u + cn) & 0xFFFFu);
+        const float up = __fadd_rn(cq, fdiv_by_int(t3, t4));
+        const float bound = __fmaf_rn(b.y, __fsub_rn(sq, b.z), b.x);  // (s1 - s0 is exact for s0 <= s1 <= 2 s0)
+        h = up > bound && sq <= __fmul_rn(2.0f, b.z);
+      }
+      hold = __ballot_sync(kFull, h);
+    }
   }
+  t.hold = hold;
   t.stat += static_cast<uint32_t>(lane == kStatSims) + (lane == kStatLevels ? levels : 0u);
   __syncwarp();
 }
@@ -415,7 +454,7 @@ __device__ __forceinline__ void finish_root_eval(WarpTree& t, const SearchParams
   if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;  // set_policy
   if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
   t.stat += static_cast<uint32_t>(lane == kStatEvals);
-  backup_path(t, p, 0u, root_slot, -val, 1u, lane);
+  backup_path<false>(t, p, 0u, root_slot, -val, 1u, lane);
 }
 
 // upgrade -> Some(true), second half (node.rs:290-322, async_mcts.rs:317-353): mask + normalise
@@ -439,7 +478,8 @@ __device__ __forceinline__ void finish_expand(WarpTree& t, const SearchParams& p
   tt_insert(t, pd.ins, pd.key, pd.my_slot, pd.new_meta, lane);
   t.n_owners++;
   t.stat += static_cast<uint32_t>(lane == kStatEvals || lane == kStatExpansions);
-  backup_path(t, p, pd.plen, pd.my_slot, -val, pd.levels, lane);  // :353 returns -v
+  if (predict) backup_path<true>(t, p, pd.plen, pd.my_slot, -val, pd.levels, lane);  // :353 returns -v
+  else backup_path<false>(t, p, pd.plen, pd.my_slot, -val, pd.levels, lane);
 }
 
 // True when the node needs the F1 root evaluation before it can be searched.
@@ -458,7 +498,7 @@ __device__ __forceinline__ void load_edges(const WarpTree& t, uint32_t blk, uint
 }
 template <bool GENERIC>
 __device__ __forceinline__ void score_edges(const WarpTree& t, float cpuct_f, float sq, bool use, uint32_t la,
-                                            const uint4& w, uint32_t& nn, float& u, bool& ok) {
+                                            const uint4& w, uint32_t& nn, float& u, float& ex, float& cp, bool& ok) {
   ok = use && la < 7u && w.w != kMetaInvalid;
   float q = __uint_as_float(w.y);
   if (__any_sync(kFull, ok && w.w == kMetaLink)) {  // rare; kept off the common instruction stream
@@ -467,16 +507,11 @@ __device__ __forceinline__ void score_edges(const WarpTree& t, float cpuct_f, fl
       nn = ld_n(t, w.x);
     }
   }
-  const float t3 = __fmul_rn(__fmul_rn(cpuct_f, __uint_as_float(w.z)), sq);
+  cp = __fmul_rn(cpuct_f, __uint_as_float(w.z));
+  const float t3 = __fmul_rn(cp, sq);
   const float t4 = static_cast<float>((1u + nn) & 0xFFFFu);  // u16 arithmetic (quirk Q6)
-  const float ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
+  ex = GENERIC ? __fdiv_rn(t3, t4) : fdiv_by_int(t3, t4);
   u = ok ? __fadd_rn(q, ex) : __uint_as_float(0xFF800000u);
-}
-template <bool GENERIC>
-__device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uint32_t blk, float sq,
-                                           bool use, uint32_t la, uint4& w, uint32_t& nn, float& u, bool& ok) {
-  load_edges(t, blk, la, w, nn);
-  score_edges<GENERIC>(t, cpuct_f, sq, use, la, w, nn, u, ok);
 }
 
 // One simulation from an evaluated (or terminal) root.  Returns false when it suspended for a
@@ -484,24 +519,26 @@ __device__ __forceinline__ void eval_edges(const WarpTree& t, float cpuct_f, uin
 // evaluate.  ev_kind < AZB_EVAL_NNET evaluates inline and never suspends.
 // GENERIC = false is the hot variant: no max_depth check (depth counts moves into existing nodes, at
 // most 42 on this board, so the check is dead unless max_depth < 43), the slow-path-free division,
-// and a SPECULATIVE PREFIX: consecutive simulations of a tree share most of their path, so the walk
-// first re-checks the previous simulation's path (t.pred_len levels of t.path) four levels at a time,
-// one per 8-lane group (group g: level base + g; lane 8g + a: edge a).  What a node selects depends
-// only on that node's own block, never on how the walk got there, so a level's check is exact
-// whenever every level above it still selects the predicted edge; a level "holds" when no other edge
-// beats the predicted one under max_by's last-maximum rule (one shuffle + one ballot for four
-// levels, no arg-max).  The first level that does not hold is resolved with the real arg-max and the
-// walk goes on from there one level per iteration.  Results are bit-identical with the
-// one-level-at-a-time walk (the GENERIC variant, and the oracle).
-// GENERIC = true keeps the depth check, uses __fdiv_rn and never speculates (trees whose `slow`
-// flag is set).
+// and HELD LEVELS: consecutive simulations of a tree share most of their path, and the previous
+// simulation's backup has already decided (backup_path, t.hold) which levels of that path are certain
+// to select their recorded edge again.  What a node selects depends only on that node's own block,
+// never on how the walk got there, so the walk starts at the first level that does not hold (its node,
+// N, sqrt term and position sit in its path entry), takes that level's real arg-max, and, while the
+// arg-max confirms the recorded edge, jumps over the following held levels in the same way; the first
+// level that picks another edge ends the prediction and the walk goes on one level per iteration.
+// Held levels cost nothing here: no block read, no arg-max, no board arithmetic (their visit counts
+// move at backup).  Results are bit-identical with the one-level-at-a-time walk (the GENERIC variant,
+// and the oracle).
+// GENERIC = true keeps the depth check, uses __fdiv_rn and never skips (trees whose `slow` flag is set).
 template <bool GENERIC>
 __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
                                              uint32_t root_slot, uint32_t root_meta, int lane,
                                              Pending& pd, BB& leaf) {
   const float neg_inf = __uint_as_float(0xFF800000u);
-  const uint32_t grp8 = lane & 24u, la = lane & 7u;  // first lane of my 8-lane group, my edge
+  const uint32_t la = lane & 7u;
+  const bool grp0 = lane < 8;
   const uint32_t pred_len = t.pred_len;  // (GENERIC: never read)
+  const uint32_t nhold = ~t.hold;        // bit l clear: level l is held
   t.pred_len = 0u;  // set again by the exits that leave a usable path behind
   uint32_t cur_slot = root_slot, cur_meta = root_meta;
   uint32_t par_n = 0u;  // N of the current node before this simulation's visit
@@ -518,64 +555,90 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
   if (cur_meta >= kMaxBlockId) {
     at_terminal(cur_meta);
   } else {
-    bool spec = !GENERIC && pred_len > 1u;  // GENERIC callers keep t.pred_len == 0
-    BB pos = root;  // position of the level being resolved (spec: reloaded from its path entry)
-    if (!spec) par_n = ld_n(t, root_slot);
-    for (;;) {
-      if (GENERIC && depth > p.max_depth) break;  // :241-244 (+F6): v = eval_heuristic() == 0
-      uint4 w;
-      uint32_t nn, a, sl, ch_meta, blk, sa;
-      float u;
-      bool ok;
-      if (!GENERIC && spec) {
-        // ---- speculative prefix: which predicted levels still select the predicted edge? ----
-        uint32_t base = 0u, stop;
-        uint4 e;
-        for (;;) {
-          const uint32_t l = base + (grp8 >> 3);
-          const bool have = l < pred_len;
-          e = *reinterpret_cast<const uint4*>(t.path + (have ? l : 0u));  // {sa, blk, n, sqrt}
-          eval_edges<GENERIC>(t, p.cpuct_f, e.y, __uint_as_float(e.w), have, la, w, nn, u, ok);
-          const uint32_t pa = e.x & 7u;  // the predicted edge (7 on the previous leaf: nothing holds)
-          const float upred = __shfl_sync(kFull, u, pa, 8);
-          const bool beaten = ok && (u > upred || (la > pa && u == upred));  // last maximum wins (node.rs:366)
-          // the last predicted level always stops the prefix: it is resolved with the real arg-max
-          // below (after a terminal / link exit its edge may hold again; the previous leaf has none)
-          stop = __ballot_sync(kFull, beaten || l + 1u >= pred_len);
-          if (stop) break;
-          base += 4u;
-        }
-        const uint32_t gs8 = (static_cast<uint32_t>(__ffs(static_cast<int>(stop))) - 1u) & 24u;
-        plen = base + (gs8 >> 3);  // the levels before it took the predicted edges; their entries stay
-        const bool mine = ok && grp8 == gs8;
-        const float mx = redux_max_f32(mine ? u : neg_inf);
-        const uint32_t ball = __ballot_sync(kFull, mine && u == mx);
-        empty_seen |= (ball == 0u);
-        sl = bfind_u32(ball | (1u << gs8));
-        a = sl & 7u;
-        ch_meta = __shfl_sync(kFull, w.w, sl);
-        blk = __shfl_sync(kFull, e.y, gs8);
-        sa = __shfl_sync(kFull, e.x, gs8);
-        if (plen) pos = BB{t.path[plen].cur, t.path[plen].opp};
-        spec = false;
-      } else {
-        // ---- best_child of the current node; max_by keeps the LAST maximum (node.rs:366).  An
-        // empty / all-NaN candidate set (node.rs:367 unwrap panics) is detected after the walk
-        // (empty_seen); the walk itself stays in bounds. ----
-        blk = cur_meta;
-        sa = cur_slot << 3;
-        const float sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
-        eval_edges<GENERIC>(t, p.cpuct_f, blk, sq, grp8 == 0u, la, w, nn, u, ok);
+    bool on_pred = !GENERIC && pred_len > 0u;
+    BB pos = root;  // position of the level being resolved
+    float sq = 0.0f;
+    uint32_t pred_a = 8u;
+    // on_pred: continue at the first level >= `from` that is not held.  Returns false when every remaining
+    // level is held: the walk ends in the finished game the previous simulation ended in.
+    auto jump = [&](uint32_t from) -> bool {
+      // (levels 31 and up are never held: from there on the walk goes level by level)
+      const uint32_t rest = from < 32u ? (nhold >> from) << from : 0u;
+      const uint32_t f = from < 32u ? (rest ? static_cast<uint32_t>(__ffs(static_cast<int>(rest))) - 1u : 32u) : from;
+      if (f >= pred_len) {  // (only when pred_len <= 32: level 31 and up are never held)
+        plen = pred_len;
+        cur_slot = t.leaf_slot;
+        cur_meta = t.leaf_meta;
+        return false;
+      }
+#ifdef AZB_HOLD_VERIFY  // debug build: every skipped level must select its recorded edge in the exact evaluation
+      for (uint32_t l = from; l < f && l < pred_len; ++l) {
+        const uint4 ev = *reinterpret_cast<const uint4*>(t.path + l);
+        uint4 w;
+        uint32_t nn;
+        float u, ex, cp;
+        bool ok;
+        load_edges(t, ev.y, la, w, nn);
+        score_edges<false>(t, p.cpuct_f, __uint_as_float(ev.w), grp0, la, w, nn, u, ex, cp, ok);
         const float mx = redux_max_f32(u);
         const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
-        empty_seen |= (ball == 0u);
-        a = bfind_u32(ball | 1u);
-        sl = a;
-        ch_meta = __shfl_sync(kFull, w.w, sl);
+        if (ball == 0u || bfind_u32(ball) != (ev.x & 7u)) t.error = kErrInternal;
       }
+#endif
+      const uint4 e = *reinterpret_cast<const uint4*>(t.path + f);  // {sa, blk, n, sqrt}
+      plen = f;
+      cur_slot = e.x >> 3;
+      cur_meta = e.y;
+      par_n = e.z;
+      sq = __uint_as_float(e.w);
+      pred_a = e.x & 7u;
+      if (f) pos = BB{t.path[f].cur, t.path[f].opp};
+      return true;
+    };
+    bool walking = true;
+    if (on_pred) {
+      walking = jump(0u);
+      if (!walking) at_terminal(cur_meta);
+    } else {
+      par_n = ld_n(t, root_slot);
+    }
+    uint32_t guard = 0u;
+    while (walking) {
+      if (++guard > 4u * kPathCap) { t.error = kErrInternal; return true; }  // (a walk has at most 42 moves + link hops)
+      if (GENERIC && depth > p.max_depth) break;  // :241-244 (+F6): v = eval_heuristic() == 0
+      // ---- best_child of the current node; max_by keeps the LAST maximum (node.rs:366).  An
+      // empty / all-NaN candidate set (node.rs:367 unwrap panics) is detected after the walk
+      // (empty_seen); the walk itself stays in bounds. ----
+      const uint32_t blk = cur_meta;
+      uint4 w;
+      uint32_t nn;
+      float u, ex, cp;
+      bool ok;
+      load_edges(t, blk, la, w, nn);
+      if (GENERIC || !on_pred) sq = sqrt_count(__fadd_rn(static_cast<float>((par_n + 1u) & 0xFFFFu), kEps));
+      score_edges<GENERIC>(t, p.cpuct_f, sq, grp0, la, w, nn, u, ex, cp, ok);
+      const float mx = redux_max_f32(u);
+      const uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+      empty_seen |= (ball == 0u);
+      const uint32_t a = bfind_u32(ball | 1u);
+      const uint32_t ch_meta = __shfl_sync(kFull, w.w, a);
       // node_path.push(current_head_id) (:270 / F3) together with the action taken.  Every lane
       // stores the same words to the same address (cheaper than electing a lane)
-      *reinterpret_cast<uint2*>(t.path + plen) = make_uint2((sa & ~7u) | a, blk);
+      *reinterpret_cast<uint2*>(t.path + plen) = make_uint2((cur_slot << 3) | a, blk);
+      if (!GENERIC) {
+        // the hold bound of this level (backup_path): maxima over the edges NOT taken, with the slack that
+        // covers every rounding between here and the bound's use (|q| <= 1.01, s1 <= 2 s0)
+        const bool other = ok && la != a;
+        const float m0 = redux_max_f32(other ? u : neg_inf);
+        const float e0 = redux_max_f32(other ? ex : 0.0f);
+        const float slack = __fmul_rn(__fadd_rn(__fadd_rn(fabsf(m0), 2.0f), __fmul_rn(4.0f, e0)), 9.5367431640625e-07f);
+        float rs;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sq));
+        const float e0s = __fmul_rn(__fmul_rn(e0, rs), 1.0000038146972656f);
+        const float cpa = __shfl_sync(kFull, cp, a);
+        *reinterpret_cast<float4*>(&t.path[plen].m0) =
+            make_float4(m0 > neg_inf ? __fadd_rn(m0, slack) : neg_inf, e0s, sq, cpa);
+      }
       plen++;
       // get_next_state + get_canonical_form (:284-287 with F4, F10) for the edge taken: the child's
       // position, kept with its path level (a link leads to the same position's owner)
@@ -583,19 +646,27 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       *reinterpret_cast<uint4*>(&t.path[plen].cur) =
           make_uint4(static_cast<uint32_t>(pos.cur), static_cast<uint32_t>(pos.cur >> 32),
                      static_cast<uint32_t>(pos.opp), static_cast<uint32_t>(pos.opp >> 32));
+      if (!GENERIC && on_pred) {
+        if (a == pred_a && plen < pred_len) {  // confirmed: the next recorded level is this edge's child
+          if (jump(plen)) continue;
+          at_terminal(cur_meta);
+          break;
+        }
+        on_pred = false;
+      }
       if (ch_meta < kMaxBlockId) {  // an expanded child: descend (:269-274 + F2)
         cur_slot = blk * 8u + a;
         cur_meta = ch_meta;
-        par_n = __shfl_sync(kFull, nn, sl);
+        par_n = __shfl_sync(kFull, nn, a);
         if (GENERIC) depth++;
         continue;
       }
       if (ch_meta != kMetaPlaceholder) {  // a link or a finished game
         if (GENERIC) depth++;
         if (ch_meta == kMetaLink) {
-          cur_slot = __shfl_sync(kFull, w.x, sl);
-          cur_meta = __shfl_sync(kFull, w.y, sl);
-          par_n = __shfl_sync(kFull, nn, sl);
+          cur_slot = __shfl_sync(kFull, w.x, a);
+          cur_meta = __shfl_sync(kFull, w.y, a);
+          par_n = __shfl_sync(kFull, nn, a);
           if (cur_meta < kMaxBlockId) continue;
         } else {
           cur_slot = blk * 8u + a;
@@ -619,7 +690,7 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       if (tt_find(t, p.bucket_mask, key2, e_home, lane, o_slot, o_meta, ins)) {
         // upgrade -> Some(false): the slot becomes a link (node.rs:284-289); continue from the
         // owner without incrementing depth (async_mcts.rs:293-299)
-        if (lane == static_cast<int>(sl)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
+        if (lane == static_cast<int>(a)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
         t.stat += static_cast<uint32_t>(lane == kStatDupLinks);
         __syncwarp();
         cur_slot = o_slot;
@@ -635,11 +706,12 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
       if (code) {  // repair F5: terminal leaf, the net is skipped
         const uint32_t new_meta = kMetaTerminal | static_cast<uint32_t>(code);
         v = terminal_e(static_cast<uint32_t>(code));
-        if (lane == static_cast<int>(sl)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+        if (lane == static_cast<int>(a)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
         tt_insert(t, ins, key2, my_slot, new_meta, lane);
         t.n_owners++;
         t.stat += static_cast<uint32_t>(lane == kStatTerminal || lane == kStatExpansions);
         cur_slot = my_slot;  // :309 visit() of the fresh node happens in its backup
+        cur_meta = new_meta;
         end_level = 0;
         break;
       }
@@ -662,8 +734,14 @@ __device__ __forceinline__ bool one_sim_impl(WarpTree& t, const SearchParams& p,
     }
   }
   if (empty_seen) { t.error = kErrInternal; return true; }
-  backup_path(t, p, plen, cur_slot, v, plen + end_level, lane);
-  if (!GENERIC) t.pred_len = plen;  // the walked nodes (not the terminal / depth-limit leaf)
+  if (!GENERIC) {
+    backup_path<true>(t, p, plen, cur_slot, v, plen + end_level, lane);
+    t.pred_len = plen;  // the walked nodes; the finished game (or nothing, at the root) below them:
+    t.leaf_slot = cur_slot;
+    t.leaf_meta = cur_meta;
+  } else {
+    backup_path<false>(t, p, plen, cur_slot, v, plen + end_level, lane);
+  }
   return true;
 }
 

@@ -60,7 +60,7 @@ struct LeafBufs {
   unsigned long long* dkeys;    // [2 parities][2 models][dmask + 1]  stamp << 49 | state_key
   uint32_t* didx;               // [2 parities][2 models][dmask + 1]  the owner's dense row
   uint32_t dmask;               // entries per model - 1 (power of two); 0 = no de-duplication
-  uint32_t stamp;               // 1 .. 32767, changes every round
+  uint32_t stamp;               // 1 .. 32766, changes every round (k_round derives it from the device round counter)
   uint32_t dpar;                // round parity: which table this round's claims go to
   unsigned long long* nn_total; // positions sent through the networks so far (k_compact adds the round's counts)
   // Evaluation cache for the duration of one call (cmask != 0): (state key -> raw policy[7], value) of every position a
@@ -130,10 +130,16 @@ struct RoundParams {
   uint32_t n_slots, n_games;
   uint32_t half;    // arena: games [0, half) seat A first, [half, 2*half) seat B first (arena.rs:74-83)
   uint32_t k_open;  // arena: random opening plies
+  uint32_t shared;  // arena: 1 = the reference's layout (coach.rs:333-354): ONE tree pair for the whole match, games
+                    // strictly sequential (n_slots == 1); the trees and their counters survive from game to game
   uint64_t first_game_id;
 };
 
+constexpr uint32_t kStampPeriod = 32766u;  // even: a round pair (one graph launch) never straddles the stamp's wrap
 struct Control {
+  unsigned int* round;       // rounds started so far: k_compact counts, k_round derives the de-duplication stamp from it
+  unsigned long long* host_progress;  // page-locked host word: (round << 32) | live slots, written by every k_round, so
+                                      // that the host follows the run (and sees its end) without a blocking copy
   unsigned int* next_game;   // games handed out so far
   unsigned int* n_active;    // live slots after k_compact (this round's counter)
   unsigned int* n_active_next;  // the next round's counter: zeroed by this round's k_compact
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(256) k_compact(RoundParams rp, GameRec* recs, 
     leaf.count[0] = 0u;
     leaf.count[1] = 0u;
     *ctl.n_active_next = 0u;
+    *ctl.round += 1u;  // (read by this round's k_round only)
   }
   uint32_t alive = 0;
   if (slot < rp.n_slots) {
@@ -230,6 +237,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, GameBufs g) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t round = *ctl.round;  // 1-based
+  leaf.stamp = (round - 1u) % kStampPeriod + 1u;
+  if (w == 0u && lane == 0 && ctl.host_progress) {
+    *reinterpret_cast<volatile unsigned long long*>(ctl.host_progress) =
+        (static_cast<unsigned long long>(round) << 32) | *ctl.n_active;
+    __threadfence_system();
+  }
   if (w >= *ctl.n_active) return;
   const uint32_t slot = ctl.active_list[w];
   GameRec* rec = recs + slot;
@@ -256,11 +270,12 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
   WarpTree t = open_tree(pools, p, slot * tps);
 
   if (phase == kPhaseFresh) {  // AsyncMcts::default (coach.rs:246-255): fresh tree(s) on the initial board
-    for (uint32_t k = 0; k < tps; ++k) {
-      WarpTree tk = open_tree(pools, p, slot * tps + k);
-      clear_table(tk, p, lane);
-      if (lane < 12) reinterpret_cast<uint32_t*>(&rec->tv[k])[lane] = 0u;
-    }
+    if (!(rp.mode == kModeArena && rp.shared && gi != 0u))
+      for (uint32_t k = 0; k < tps; ++k) {
+        WarpTree tk = open_tree(pools, p, slot * tps + k);
+        clear_table(tk, p, lane);
+        if (lane < 12) reinterpret_cast<uint32_t*>(&rec->tv[k])[lane] = 0u;
+      }
     board = BB{0ull, 0ull};
     player = 1;
     step = 0;
@@ -324,7 +339,8 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
       }
       step++;                                             // coach.rs:119
       if (!make_root(t, p, board, lane, root_slot, root_meta)) { err = t.error; break; }  // :81 (+F12)
-      if (step * p.num_sims >= kSafeVisits) t.slow = 1u;
+      // visit counts near the 16-bit wrap (quirk Q6) take the generic walk: this tree's simulations so far + this search
+      if (__shfl_sync(kFull, t.stat, kStatSims) + p.num_sims >= kSafeVisits) t.slow = 1u;
       sims_done = 0;
       phase = kPhaseSearch;
     }

@@ -245,6 +245,26 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
                          azb_nnet* net_b, uint32_t k_open, uint64_t out_counts[3], int8_t* results,
                          azb_selfplay_stats* stats);
 
+/* The same match with its options spelled out and the per-game traces returned.
+ *   shared_trees = 0: a fresh tree pair per game, all games concurrent (the device layout; every game of a seat order is
+ *                     the same game unless k_open > 0, because the players are deterministic);
+ *   shared_trees = 1: the reference's own layout, coach.rs:333-354 — pmcts / nmcts are created ONCE, every game of the
+ *                     match searches and grows the same two trees, games strictly one after the other (arena.rs:82-93),
+ *                     so later games see the statistics of the earlier ones.  One game in flight: a latency-bound mode
+ *                     kept for parity with the reference, not for throughput.  cfg->mcts_reserve_size bounds each tree
+ *                     (node.rs:237 asserts; here AZB_ERR_CAPACITY).
+ *   first_game_id   : game i draws its opening plies from Philox stream (cfg->seed, first_game_id + i).
+ * actions[G][64] (0xFF padded), root_counts[G][64][7] (searched plies only), plies[G] with G = 2*(num/2); each may be
+ * NULL.  opts == NULL means {0, 0, 0}. */
+typedef struct azb_arena_opts {
+  uint32_t k_open;
+  uint32_t shared_trees;
+  uint64_t first_game_id;
+} azb_arena_opts;
+int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a, int32_t eval_b, azb_nnet* net_a,
+                            azb_nnet* net_b, const azb_arena_opts* opts, uint64_t out_counts[3], int8_t* results,
+                            uint8_t* actions, uint16_t* root_counts, uint32_t* plies, azb_selfplay_stats* stats);
+
 /* ---------------------------------------------------------------------------------------
  * On-disk formats.
  *
@@ -303,10 +323,14 @@ typedef struct azb_learn_config {
   uint32_t epochs;          /* Adam steps per iteration (connect_four_net.py:13: 10); 0 = one pass over the window */
   uint32_t batch_size;      /* connect_four_net.py:14: 64 */
   azb_train_config adam;    /* default lr 1e-4 (the reference's 1e-3, connect_four_net.py:21, assumes BatchNorm; see learn.cuh), 0.9, 0.999, 1e-8 */
-  uint32_t arena_k_open;    /* random opening plies of the gating games (0 = reference) */
+  uint32_t arena_k_open;    /* random opening plies of the gating games.  Default 4: with concurrent fresh-tree games and
+                             * deterministic players, 0 makes every game of a seat order the SAME game (the gate would be
+                             * decided by two distinct games).  The reference gets its variety from the tree pair it keeps
+                             * across the games: arena_shared_trees = 1, arena_k_open = 0 is its literal behaviour. */
   uint32_t skip_first_play; /* Coach::learn's skip_first_play, coach.rs:172,240 */
   uint32_t save_files;      /* 1: write <iteration>.examples and <model_id>.azbw into checkpoint_directory */
-  uint32_t reserved;
+  uint32_t arena_shared_trees; /* 1: pmcts / nmcts persist across the gating games, played one after the other
+                                * (coach.rs:333-372); 0 (default): fresh tree pair per game, all games concurrent */
 } azb_learn_config;
 void azb_learn_config_default(azb_learn_config* lc);
 

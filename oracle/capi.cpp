@@ -22,6 +22,7 @@
 #include "coach.hpp"
 #include "learn.hpp"
 #include "mcts.hpp"
+#include "nnet_cpu.hpp"
 #include "node.hpp"
 #include "philox.hpp"
 
@@ -291,13 +292,17 @@ int azo_execute_episode(const azo_params* p, uint64_t episode_id, int eval_kind,
 // games sequential (coach.rs:333-372); 0: a fresh tree pair per game (the device layout).
 // k_open random opening plies per game come from Philox (seed, game_index, ply, OPENING).
 // out_counts = {Win, Loss, Draw} of player A; results[num] (optional) = play_game's i8.
-int azo_arena_play_games(const azo_params* p, uint64_t num, int eval_a, int eval_b,
-                         int shared_trees, uint32_t k_open, uint64_t* out_counts,
-                         int8_t* results) {
+// _cb: the evaluators may be predict callbacks (kind AZO_EVAL_CALLBACK: fn_a / fn_b), game i draws its opening plies
+// from Philox stream (seed, first_game_id + i), and the per-game traces come back: actions[num][64] (0xFF padded),
+// root_counts[num][64][7] (searched plies only) and plies[num] (all optional).
+int azo_arena_play_games_cb(const azo_params* p, uint64_t num, int eval_a, void* fn_a, void* user_a, int eval_b,
+                            void* fn_b, void* user_b, int shared_trees, uint32_t k_open, uint64_t first_game_id,
+                            uint64_t* out_counts, int8_t* results, uint8_t* actions, uint16_t* root_counts,
+                            uint32_t* plies) {
   AZO_TRY
   C4::quirks() = p->quirks;
   CoachParams cp = cp_of(p);
-  std::unique_ptr<Evaluator> ea(make_eval(eval_a, nullptr, nullptr)), eb(make_eval(eval_b, nullptr, nullptr));
+  std::unique_ptr<Evaluator> ea(make_eval(eval_a, fn_a, user_a)), eb(make_eval(eval_b, fn_b, user_b));
   auto mk = [&](Evaluator* e) {
     return std::make_unique<AsyncMcts<C4>>(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims,
                                            cp.max_depth, 0, cp.cpuct, cp.quirks, e);
@@ -320,23 +325,33 @@ int azo_arena_play_games(const azo_params* p, uint64_t num, int eval_a, int eval
       AsyncMcts<C4>* A = ta.get();
       AsyncMcts<C4>* B = tb.get();
       size_t ply = 0;
+      if (actions) std::memset(actions + 64 * gi, 0xFF, 64);
+      if (root_counts) std::memset(root_counts + 64 * 7 * gi, 0, 64 * 7 * 2);
       auto mover = [&](AsyncMcts<C4>* t) {
         return [&, t](const C4& s) -> uint8_t {
           size_t my_ply = ply++;
+          uint8_t act;
           if (my_ply < k_open) {
             auto v = s.get_valid_moves(1);
             float w[7];
             for (int a = 0; a < 7; ++a) w[a] = v[a] ? 1.0f : 0.0f;
-            return static_cast<uint8_t>(choose_weighted(
-                w, 7, uniform01(cp.seed, gi, static_cast<uint32_t>(my_ply), PURPOSE_OPENING)));
+            act = static_cast<uint8_t>(choose_weighted(
+                w, 7, uniform01(cp.seed, first_game_id + gi, static_cast<uint32_t>(my_ply), PURPOSE_OPENING)));
+          } else {
+            uint16_t c8[8] = {0};
+            act = argmax(t->get_action_prob(s, 0.0f, c8));
+            if (root_counts && my_ply < 64)
+              for (int a = 0; a < 7; ++a) root_counts[(64 * gi + my_ply) * 7 + a] = c8[a];
           }
-          return argmax(t->get_action_prob(s, 0.0f));
+          if (actions && my_ply < 64) actions[64 * gi + my_ply] = act;
+          return act;
         };
       };
       std::array<std::function<uint8_t(const C4&)>, 2> seated =
           ordering == 0 ? std::array<std::function<uint8_t(const C4&)>, 2>{mover(A), mover(B)}
                         : std::array<std::function<uint8_t(const C4&)>, 2>{mover(B), mover(A)};
       int8_t r = play_game<C4>(seated, nullptr);
+      if (plies) plies[gi] = static_cast<uint32_t>(ply);
       res.push_back(r);
       if (r == win_cond) all.win++;
       else if (r == lose_cond) all.loss++;
@@ -347,6 +362,12 @@ int azo_arena_play_games(const azo_params* p, uint64_t num, int eval_a, int eval
   if (results) std::memcpy(results, res.data(), res.size());
   return 0;
   AZO_CATCH(-1)
+}
+int azo_arena_play_games(const azo_params* p, uint64_t num, int eval_a, int eval_b,
+                         int shared_trees, uint32_t k_open, uint64_t* out_counts,
+                         int8_t* results) {
+  return azo_arena_play_games_cb(p, num, eval_a, nullptr, nullptr, eval_b, nullptr, nullptr, shared_trees, k_open, 0,
+                                 out_counts, results, nullptr, nullptr, nullptr);
 }
 
 // ---- CPU timing leg (bench.py cpu_baseline / --impl reference) ---------------------------
@@ -389,6 +410,60 @@ int azo_bench_selfplay(const azo_params* p, int eval_kind, uint64_t n_games, uin
   *seconds = std::chrono::duration<double>(t1 - t0).count();
   if (levels) *levels = tot_levels;
   if (expansions) *expansions = tot_exp;
+  return 0;
+  AZO_CATCH(-1)
+}
+
+// The same leg with the network evaluator on the CPU (BASELINE configs 1 and 3): a plain fp32 forward pass of the
+// ResNet (oracle/nnet_cpu.hpp, `blocks` residual blocks, the flat parameter vector of azb_nnet_get_params) called
+// inline per leaf, one game per thread, each game cut after `max_plies` plies (0 = whole games) so that the sample is
+// bounded.  Also returns the number of network evaluations.
+int azo_bench_selfplay_net(const azo_params* p, int blocks, const float* params, uint64_t n_params, uint64_t n_games,
+                           uint64_t n_threads, uint64_t first_game_id, uint64_t max_plies, uint64_t* sims,
+                           uint64_t* plies, double* seconds, uint64_t* evals) {
+  AZO_TRY
+  if (n_params != CpuNet::num_params(blocks)) { g_err = "parameter count does not match the architecture"; return -1; }
+  CoachParams cp = cp_of(p);
+  const CpuNet net(blocks, params);
+  std::atomic<uint64_t> next{0}, tot_sims{0}, tot_plies{0}, tot_evals{0};
+  std::atomic<int> failed{0};
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (uint64_t t = 0; t < n_threads; ++t)
+    th.emplace_back([&] {
+      C4::quirks() = cp.quirks;
+      try {
+        for (;;) {
+          uint64_t g = next.fetch_add(1);
+          if (g >= n_games) break;
+          CpuNetEvaluator ev(&net);
+          AsyncMcts<C4> mcts(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims, cp.max_depth, 0, cp.cpuct,
+                             cp.quirks, &ev);
+          auto tr = execute_episode<C4>(cp, mcts, first_game_id + g, max_plies ? max_plies : static_cast<size_t>(-1));
+          tot_sims += tr.stats.sims;
+          tot_plies += tr.actions.size();
+          tot_evals += tr.stats.evals;
+        }
+      } catch (...) {
+        failed = 1;
+      }
+    });
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  if (failed) { g_err = "a worker threw"; return -1; }
+  *sims = tot_sims; *plies = tot_plies;
+  *seconds = std::chrono::duration<double>(t1 - t0).count();
+  if (evals) *evals = tot_evals;
+  return 0;
+  AZO_CATCH(-1)
+}
+// NNet::predict of that CPU network (tests: third witness of the network's numerics next to torch and the device)
+int azo_cpu_net_predict(int blocks, const float* params, uint64_t n_params, const float* boards, uint64_t batch,
+                        float* pi, float* v) {
+  AZO_TRY
+  if (n_params != CpuNet::num_params(blocks)) { g_err = "parameter count does not match the architecture"; return -1; }
+  const CpuNet net(blocks, params);
+  for (uint64_t i = 0; i < batch; ++i) net.predict_one(boards + 84 * i, pi + 7 * i, v + i);
   return 0;
   AZO_CATCH(-1)
 }

@@ -39,8 +39,10 @@ struct EpisodeTrace {
 };
 
 // coach.rs:104-157.  `episode_id` keys the per-game Philox stream.
+// `max_plies` (timing legs only): stop after that many plies of an unfinished game (no labels are produced then).
 template <class G>
-EpisodeTrace<G> execute_episode(const CoachParams& cp, AsyncMcts<G>& mcts, uint64_t episode_id) {
+EpisodeTrace<G> execute_episode(const CoachParams& cp, AsyncMcts<G>& mcts, uint64_t episode_id,
+                                size_t max_plies = static_cast<size_t>(-1)) {
   EpisodeTrace<G> tr;
   const size_t A = G::num_actions();
   const size_t F = G::feature_len();
@@ -79,6 +81,12 @@ EpisodeTrace<G> execute_episode(const CoachParams& cp, AsyncMcts<G>& mcts, uint6
         else
           tr.vs.push_back(p == cur_player ? r : -r);
       }
+      tr.stats = mcts.stats;
+      tr.nodes_len = mcts.nodes->size();
+      tr.seen_len = mcts.nodes->seen.size();
+      return tr;
+    }
+    if (episode_step >= max_plies) {  // bounded timing sample: the game is cut short
       tr.stats = mcts.stats;
       tr.nodes_len = mcts.nodes->size();
       tr.seen_len = mcts.nodes->seen.size();

@@ -112,7 +112,15 @@ pub struct azb_learn_config {
     pub arena_k_open: u32,
     pub skip_first_play: u32,
     pub save_files: u32,
-    pub reserved: u32,
+    pub arena_shared_trees: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct azb_arena_opts {
+    pub k_open: u32,
+    pub shared_trees: u32,
+    pub first_game_id: u64,
 }
 
 #[repr(C)]
@@ -210,6 +218,7 @@ extern "C" {
 
     // arena, src/arena.rs:7-99
     pub fn azb_arena_play_games(cfg: *const azb_config, num: u64, eval_a: i32, eval_b: i32, net_a: *mut azb_nnet, net_b: *mut azb_nnet, k_open: u32, out_counts: *mut u64, results: *mut i8, stats: *mut azb_selfplay_stats) -> c_int;
+    pub fn azb_arena_play_games_ex(cfg: *const azb_config, num: u64, eval_a: i32, eval_b: i32, net_a: *mut azb_nnet, net_b: *mut azb_nnet, opts: *const azb_arena_opts, out_counts: *mut u64, results: *mut i8, actions: *mut u8, root_counts: *mut u16, plies: *mut u32, stats: *mut azb_selfplay_stats) -> c_int;
 
     // on-disk formats: coach.rs:55-81,159-167 and the weight checkpoints
     pub fn azb_examples_write(path: *const c_char, n_iters: u64, counts: *const u64, boards: *const f32, pis: *const f32, vs: *const f32) -> c_int;

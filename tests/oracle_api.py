@@ -62,6 +62,11 @@ L.azo_mcts_dump.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp]
 L.azo_execute_episode.argtypes = [C.POINTER(Params), C.c_uint64, C.c_int, vp, vp] + [vp] * 11
 L.azo_arena_play_games.argtypes = [C.POINTER(Params), C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, vp]
 L.azo_bench_selfplay.argtypes = [C.POINTER(Params), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+L.azo_arena_play_games_cb.argtypes = [C.POINTER(Params), C.c_uint64, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_uint32,
+                                      C.c_uint64, vp, vp, vp, vp, vp]
+L.azo_bench_selfplay_net.argtypes = [C.POINTER(Params), C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                     C.c_uint64, vp, vp, vp, vp]
+L.azo_cpu_net_predict.argtypes = [C.c_int, vp, C.c_uint64, vp, C.c_uint64, vp, vp]
 
 
 def _p(a):
@@ -217,6 +222,25 @@ def arena_play_games(num, eval_a, eval_b, num_sims=25, quirks=0, seed=1, shared_
     return out, res[: 2 * (num // 2)]
 
 
+def arena_play_games_traced(num, eval_a, eval_b, callback_a=None, callback_b=None, num_sims=25, quirks=0, seed=1,
+                            shared_trees=0, k_open=0, first_game_id=0, **kw):
+    """arena::play_games of the oracle with per-game traces; EVAL_CALLBACK players search with callback_a / callback_b
+    as NNet::predict.  Returns (counts[3], results, dict(actions[G, 64], counts[G, 64, 7], plies[G]))."""
+    p = params(num_sims=num_sims, quirks=quirks, seed=seed, **kw)
+    G = 2 * (num // 2)
+    out = np.zeros(3, np.uint64); res = np.zeros(max(G, 1), np.int8)
+    actions = np.full((max(G, 1), 64), 0xFF, np.uint8); rc = np.zeros((max(G, 1), 64, 7), np.uint16)
+    plies = np.zeros(max(G, 1), np.uint32)
+    cba = make_callback(callback_a) if callback_a else None
+    cbb = make_callback(callback_b) if callback_b else None
+    fa = C.cast(cba, vp) if cba else None
+    fb = C.cast(cbb, vp) if cbb else None
+    if L.azo_arena_play_games_cb(C.byref(p), num, eval_a, fa, None, eval_b, fb, None, shared_trees, k_open,
+                                 first_game_id, _p(out), _p(res), _p(actions), _p(rc), _p(plies)) != 0:
+        raise RuntimeError(L.azo_last_error().decode())
+    return out, res[:G], dict(actions=actions[:G], counts=rc[:G], plies=plies[:G])
+
+
 def bench_selfplay(n_games, n_threads, num_sims=800, quirks=0, seed=0xA1FA0, evaluator=EVAL_UNIFORM, first_game_id=0, **kw):
     p = params(num_sims=num_sims, quirks=quirks, seed=seed, **kw)
     sims = C.c_uint64(); plies = C.c_uint64(); secs = C.c_double(); lv = C.c_uint64(); ex = C.c_uint64()
@@ -225,6 +249,28 @@ def bench_selfplay(n_games, n_threads, num_sims=800, quirks=0, seed=0xA1FA0, eva
     if rc != 0:
         raise RuntimeError(L.azo_last_error().decode())
     return dict(sims=sims.value, plies=plies.value, seconds=secs.value, levels=lv.value, expansions=ex.value)
+
+
+def bench_selfplay_net(params_vec, blocks, n_games, n_threads, num_sims=400, quirks=0, seed=0xA1FA0, first_game_id=0, max_plies=0, **kw):
+    """Oracle self-play with the network evaluated on the CPU (oracle/nnet_cpu.hpp), one game per thread, every game cut
+    after max_plies plies (0 = whole games): the CPU leg of BASELINE configs 1 and 3."""
+    p = params(num_sims=num_sims, quirks=quirks, seed=seed, **kw)
+    w = np.ascontiguousarray(params_vec, np.float32)
+    sims = C.c_uint64(); plies = C.c_uint64(); secs = C.c_double(); ev = C.c_uint64()
+    rc = L.azo_bench_selfplay_net(C.byref(p), blocks, _p(w), len(w), n_games, n_threads, first_game_id, max_plies,
+                                  C.addressof(sims), C.addressof(plies), C.addressof(secs), C.addressof(ev))
+    if rc != 0:
+        raise RuntimeError(L.azo_last_error().decode())
+    return dict(sims=sims.value, plies=plies.value, seconds=secs.value, evals=ev.value)
+
+
+def cpu_net_predict(params_vec, blocks, boards):
+    w = np.ascontiguousarray(params_vec, np.float32)
+    b = np.ascontiguousarray(boards, np.float32).reshape(-1, 2, 6, 7)
+    pi = np.zeros((len(b), 7), np.float32); v = np.zeros(len(b), np.float32)
+    if L.azo_cpu_net_predict(blocks, _p(w), len(w), _p(b), len(b), _p(pi), _p(v)) != 0:
+        raise RuntimeError(L.azo_last_error().decode())
+    return pi, v
 
 
 # ---- Coach::learn host decisions + the .examples encoding (oracle/learn.hpp) ----

@@ -45,7 +45,8 @@ def test_extern_block_matches_header():
 
 def test_structs_match_ctypes_mirror(azb):
     pairs = [("azb_config", azb.Config), ("azb_selfplay_stats", azb.SelfPlayStats), ("azb_nnet_config", azb.NnetConfig),
-             ("azb_train_config", azb.TrainConfig), ("azb_learn_config", azb.LearnConfig), ("azb_learn_report", azb.LearnReport)]
+             ("azb_train_config", azb.TrainConfig), ("azb_learn_config", azb.LearnConfig), ("azb_learn_report", azb.LearnReport),
+             ("azb_arena_opts", azb.ArenaOpts)]
     for rname, cls in pairs:
         rf = rust_struct(rname)
         assert [n for n, _ in rf] == [n for n, _ in cls._fields_], rname
