@@ -166,6 +166,81 @@ def make_dist(dist, device):
 NNET_BF16_TC, NNET_FP32 = 0, 1
 
 
+class Comm:
+    """The library's own NCCL communicator (azb_dist_*): one process per GPU, no torch.  The 128-byte unique id travels
+    from rank 0 to the others through a file next to the rendezvous port (every rank of a box sees /tmp)."""
+    OPS = {"SUM": 0, "MAX": 1, "MIN": 2}
+
+    @staticmethod
+    def _pick_nccl():
+        """The library loads NCCL with dlopen("libnccl.so.2") unless AZB200_NCCL_LIB names a file.  In a Python process
+        that may import torch LATER, the system library must not be the one loaded first: the loader would hand that copy
+        (same soname, older version) to torch, whose libtorch_cuda then misses symbols.  So when the torch wheel's own
+        NCCL (site-packages/nvidia/nccl) is installed, point the library at it — found by path, torch is not imported."""
+        if os.environ.get("AZB200_NCCL_LIB"):
+            return
+        spec = importlib.util.find_spec("nvidia")
+        for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["AZB200_NCCL_LIB"] = cand
+                return
+
+    def __init__(self, rank, world, device, id_path, timeout_s=120.0):
+        import time
+        self._pick_nccl()
+        self.rank, self.world, self.device = rank, world, device
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _check(lib.azb_dist_unique_id(buf))
+            tmp = f"{id_path}.tmp{os.getpid()}"
+            with open(tmp, "wb") as f:
+                f.write(bytes(buf))
+            os.replace(tmp, id_path)  # atomic: the other ranks never see a partial id
+            raw = bytes(buf)
+        else:
+            t0 = time.time()
+            while not (os.path.exists(id_path) and os.path.getsize(id_path) == 128):
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"no NCCL unique id at {id_path}")
+                time.sleep(0.01)
+            raw = open(id_path, "rb").read()
+        self._h = C.c_void_p()
+        _check(lib.azb_dist_init((C.c_uint8 * 128).from_buffer_copy(raw), rank, world, device, C.byref(self._h)))
+
+    def dist(self):
+        """azb_dist for azb_coach_learn_dist (callbacks backed by this communicator)."""
+        d = Dist()
+        _check(lib.azb_dist_make(self._h, C.byref(d)))
+        return d
+
+    def reduce(self, value, op):
+        a = np.array([float(value)], np.float64)
+        _check(lib.azb_dist_allreduce_f64(self._h, _ptr(a), 1, self.OPS[op]))
+        return float(a[0])
+
+    def barrier(self):
+        self.reduce(0.0, "SUM")
+
+    def close(self):
+        if self._h and lib is not None:
+            lib.azb_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+
+def self_play_multi(devices, games_per_device, first_game_id=0, net_cfg=None, **cfg):
+    """azb_coach_self_play_multi: one call, one host thread per device.  Returns (per-device stats dicts, wall ms)."""
+    config = cfg.pop("config", None) or default_config(**cfg)
+    dev = np.ascontiguousarray(devices, np.int32)
+    stats = (SelfPlayStats * len(dev))()
+    wall = C.c_double()
+    _check(lib.azb_coach_self_play_multi(C.byref(config), C.byref(net_cfg) if net_cfg is not None else None, _ptr(dev), len(dev),
+                                         games_per_device, first_game_id, stats, C.byref(wall)))
+    return [s.as_dict() for s in stats], wall.value
+
+
 def build_module():
     spec = importlib.util.spec_from_file_location("azb200_build", os.path.join(_HERE, "build.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -241,6 +316,12 @@ def _load():
                             C.POINTER(vp)],
         "azb_coach_learn_dist": [vp, C.POINTER(NnetConfig), C.POINTER(LearnConfig), C.POINTER(Dist), C.POINTER(LearnReport), u64,
                                  C.POINTER(u64), C.POINTER(vp)],
+        "azb_dist_unique_id": [vp],
+        "azb_dist_init": [vp, u32, u32, C.c_int32, C.POINTER(vp)],
+        "azb_dist_destroy": [vp],
+        "azb_dist_make": [vp, C.POINTER(Dist)],
+        "azb_dist_allreduce_f64": [vp, vp, u64, C.c_int32],
+        "azb_coach_self_play_multi": [C.POINTER(Config), C.POINTER(NnetConfig), vp, u32, u64, u64, vp, C.POINTER(C.c_double)],
         "azb_coach_history_stat": [vp, C.POINTER(u64), vp, u64, C.POINTER(u64)],
         "azb_coach_history_export": [vp, vp, vp, vp, u64],
         "azb_coach_save_train_examples": [vp, u64, C.c_char_p],
@@ -251,6 +332,8 @@ def _load():
     lib.azb_learn_config_default.argtypes = [C.POINTER(LearnConfig)]
     lib.azb_learn_config_default.restype = None
     for name, argtypes in sigs.items():
+        if "AZB200_LIB" in os.environ and not hasattr(lib, name):
+            continue  # an older build loaded for a kernel-variant A/B (scripts/ab.sh): calls to it fail at use
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.argtypes = argtypes
         fn.restype = C.c_int
@@ -545,7 +628,10 @@ class Coach:
         reports = (LearnReport * max(1, n_it))()
         n = C.c_uint64()
         h = C.c_void_p()
-        if dist is not None and dist.get_world_size() > 1:
+        if isinstance(dist, Comm):
+            d = dist.dist()
+            _check(lib.azb_coach_learn_dist(self._h, C.byref(net_cfg), C.byref(lc), C.byref(d), reports, n_it, C.byref(n), C.byref(h)))
+        elif dist is not None and dist.get_world_size() > 1:
             d = make_dist(dist, self.cfg.device)
             _check(lib.azb_coach_learn_dist(self._h, C.byref(net_cfg), C.byref(lc), C.byref(d), reports, n_it, C.byref(n), C.byref(h)))
         else:

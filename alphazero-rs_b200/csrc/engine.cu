@@ -131,7 +131,9 @@ struct TreePool {
     pools.blocks = blocks.as<uint4>();
     pools.tables = tables.as<uint4>();
     pools.recs = recs.as<TreeRec>();
-    return AZB_OK;
+    // a new geometry: every table empty, every generation 0 (from here on a new game bumps its tree's generation instead
+    // of zero-filling the table)
+    return reset();
   }
   int reset() {
     AZB_CUDA(cudaMemset(tables.p, 0, static_cast<size_t>(n_trees) * (static_cast<size_t>(p.bucket_mask) + 1) * 128));
@@ -580,7 +582,7 @@ struct GameStore {
 
 // Device state of the lock-step round engine (csrc/rounds.cuh).
 struct RoundEngine {
-  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx;
+  DevBuf recs, active, ctl_words, leaf_state, leaf_count, leaf_pi, leaf_v, dedup_keys, dedup_idx, times;
   uint32_t n_slots = 0, dedup_mask = 0, cache_mask = 0;
   // The cache's memory belongs to the calling thread (one buffer per thread, re-used by every run of that thread: a coach's
   // self-play and the arena calls of Coach::learn follow each other): a run borrows it and clears the keys first.
@@ -696,6 +698,13 @@ struct RoundEngine {
     leaf.cvals = thread_cache().vals.as<float>();
     leaf.cmask = cache_mask;
     const unsigned grid = (rp.n_slots + kWarpsPerCta - 1) / kWarpsPerCta;
+    constexpr uint32_t kTimesCap = 1u << 16;
+    unsigned long long* d_times = nullptr;  // AZB200_ROUND_TIMES=1: per-round phase times on stderr at the end of the run
+    if (std::getenv("AZB200_ROUND_TIMES")) {
+      AZB_CUDA(times.ensure(static_cast<size_t>(kTimesCap) * 32));
+      AZB_CUDA(cudaMemset(times.p, 0, static_cast<size_t>(kTimesCap) * 32));
+      d_times = times.as<unsigned long long>();
+    }
     uint64_t per_round = 2;
     // one round of parity `par` on `stream` (the only per-round differences: which counter / which de-duplication table)
     auto launch_round = [&](uint32_t par) -> int {
@@ -704,8 +713,11 @@ struct RoundEngine {
       lf.dpar = par;
       c.n_active = ctl_words.as<unsigned int>() + 1 + par;  // double-buffered (k_compact)
       c.n_active_next = ctl_words.as<unsigned int>() + 1 + (par ^ 1u);
+      if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 0u, kTimesCap);
       k_compact<<<(rp.n_slots + 255u) / 256u, 256, 0, stream>>>(rp, recs.as<GameRec>(), c, lf);
+      if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 1u, kTimesCap);
       k_round<<<grid, kWarpsPerCta * 32, 0, stream>>>(rp, pools, recs.as<GameRec>(), c, lf, gs.g);
+      if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 2u, kTimesCap);
       AZB_CUDA(cudaGetLastError());
       if (any_net) {
         for (int k = 0; k < 2; ++k) {
@@ -716,6 +728,7 @@ struct RoundEngine {
           if (rc) return rc;
         }
       }
+      if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 3u, kTimesCap);
       return AZB_OK;
     };
     if (any_net)
@@ -793,6 +806,28 @@ struct RoundEngine {
       it += 2;
     }
     AZB_CUDA(cudaStreamSynchronize(stream));
+    if (d_times) {  // where a round's time goes, in 10 slices of the run
+      std::vector<unsigned long long> h(static_cast<size_t>(kTimesCap) * 4);
+      AZB_CUDA(cudaMemcpy(h.data(), d_times, h.size() * 8, cudaMemcpyDeviceToHost));
+      uint64_t seen = 0;
+      uint32_t live = 0;
+      progress(&seen, &live);
+      const uint64_t R = std::min<uint64_t>(seen > 1 ? seen - 1 : 0, kTimesCap - 1);
+      std::fprintf(stderr, "[azb200 rounds] %llu rounds; per slice: rounds, us/round total | k_compact | k_round | forward | gap to next round\n",
+                   static_cast<unsigned long long>(R));
+      for (int sl = 0; sl < 10 && R >= 20; ++sl) {
+        const uint64_t a = R * sl / 10, b = R * (sl + 1) / 10;
+        double tot = 0, tc = 0, tr = 0, tf = 0, tg = 0;
+        for (uint64_t r = a; r < b; ++r) {
+          const unsigned long long* t = h.data() + r * 4;
+          const unsigned long long* n = h.data() + (r + 1) * 4;
+          tot += double(n[0] - t[0]); tc += double(t[1] - t[0]); tr += double(t[2] - t[1]); tf += double(t[3] - t[2]); tg += double(n[0] - t[3]);
+        }
+        const double k = 1e-3 / double(b - a);
+        std::fprintf(stderr, "[azb200 rounds] slice %d: %6llu rounds  %7.1f | %6.1f | %6.1f | %6.1f | %6.1f\n", sl,
+                     static_cast<unsigned long long>(b - a), tot * k, tc * k, tr * k, tf * k, tg * k);
+      }
+    }
     const uint64_t n_launch = it * per_round;
     if (launches) *launches = n_launch;
     if (nn_positions) {  // (the last k_compact has added the last round's counts)
@@ -828,6 +863,7 @@ struct azb_coach {
   azb_config cfg;
   std::string checkpoint_dir;  // owns what cfg.checkpoint_directory points at
   CoachHistory history;
+  uint64_t resume_base = 0;  // Coach::setup resumed from `<n>.examples`: n + 1 (learn.cuh), else 0
   TreePool pool;
   bool pool_ready = false;
   azb_nnet* net = nullptr;
@@ -1848,3 +1884,4 @@ int azb_arena_play_games(const azb_config* cfg, uint64_t num, int32_t eval_a, in
 }  // extern "C"
 
 #include "learn.cuh"
+#include "dist.cuh"

@@ -27,6 +27,7 @@ __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchPa
   t.blocks = pools.blocks + static_cast<size_t>(tree) * p.cap_blocks * 8u;
   t.table = pools.tables + static_cast<size_t>(tree) * (static_cast<size_t>(p.bucket_mask) + 1u) * 8u;
   t.path = s_path[wi];
+  t.tt_stamp = static_cast<uint64_t>(pools.recs[tree].tt_gen + 1u) << 49;
   t.n_blocks = t.n_owners = t.error = t.slow = 0u;
   t.pred_len = t.hold = 0u;
   t.leaf_slot = t.leaf_meta = 0u;
@@ -35,9 +36,18 @@ __device__ __forceinline__ WarpTree open_tree(const Pools& pools, const SearchPa
   return t;
 }
 
-__device__ __forceinline__ void clear_table(const WarpTree& t, const SearchParams& p, int lane) {
-  const uint32_t n = (p.bucket_mask + 1u) * 8u;
-  for (uint32_t i = lane; i < n; i += 32u) t.table[i] = make_uint4(0u, 0u, 0u, 0u);
+// A fresh tree for a new game (AsyncMcts::default, coach.rs:246-255): the transposition table's generation moves on, so
+// every entry of the previous game reads as empty; the table is zero-filled only when the 15-bit generation wraps.
+__device__ __forceinline__ void fresh_table(WarpTree& t, const Pools& pools, const SearchParams& p, uint32_t tree, int lane) {
+  uint32_t gen = pools.recs[tree].tt_gen + 1u;
+  __syncwarp();
+  if (gen >= kTtGenWrap) {
+    const uint32_t n = (p.bucket_mask + 1u) * 8u;
+    for (uint32_t i = lane; i < n; i += 32u) t.table[i] = make_uint4(0u, 0u, 0u, 0u);
+    gen = 0u;
+  }
+  if (lane == 0) pools.recs[tree].tt_gen = gen;
+  t.tt_stamp = static_cast<uint64_t>(gen + 1u) << 49;
   __syncwarp();
 }
 
@@ -99,10 +109,10 @@ __global__ void k_dump_tree(SearchParams p, Pools pools, uint32_t tree, uint64_t
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint4 en = t.table[i];
     const uint64_t k = (static_cast<uint64_t>(en.y) << 32) | en.x;
-    if (k == 0ull) continue;
+    if (((k ^ t.tt_stamp) >> 49) != 0ull) continue;  // empty, or an earlier game's entry
     const unsigned long long row = atomicAdd(n_rows, 1ull);
     if (row >= cap) continue;
-    keys[row] = k;
+    keys[row] = k & kKeyMask;
     counters[row] = ld_counter(t, en.z);
     const uint32_t meta = en.w;
     e[row] = meta_is_terminal(meta) ? terminal_e(meta & 3u) : -0.0f;  // -get_game_ended == -0.0
@@ -145,7 +155,7 @@ k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_tree
     gi = __shfl_sync(kFull, gi, 0);
     if (gi >= n_games) break;
     // AsyncMcts::default (coach.rs:246-255): a fresh tree per episode
-    clear_table(t, p, lane);
+    fresh_table(t, pools, p, tree, lane);
     t.n_blocks = t.n_owners = t.error = t.slow = 0u;
     t.stat = 0u;
     BB board{0ull, 0ull};  // canonical board of the side to move (coach.rs:120)

@@ -63,15 +63,25 @@ size_t decode_sample(const uint8_t* p, const uint8_t* end, float* board, float* 
     p += 8;
     return true;
   };
-  uint64_t nd = 0, d = 0, prod = 1, len = 0;
+  uint64_t nd = 0, d = 0, len = 0, dims[3] = {0, 0, 0};
   if (!need(1) || *p++ != 1) return 0;
   if (!u64(&nd) || nd != 3) return 0;
-  for (int i = 0; i < 3; ++i) {
-    if (!u64(&d) || d == 0 || d > 84) return 0;
-    prod *= d;
+  for (int i = 0; i < 3; ++i)
+    if (!u64(&dims[i])) return 0;
+  // two layouts exist: [2,6,7] (C,H,W: the declared get_feature_shape, connect_four_game.rs:87, and what this engine
+  // writes) and [6,7,2] (H,W,C: what the reference's literal to_features produces, :219-237, defect F11).  The engine's
+  // planes are channel-first, so a channel-last sample is transposed here; any other shape is not a connect-four sample.
+  const bool chw = dims[0] == 2 && dims[1] == 6 && dims[2] == 7;
+  const bool hwc = dims[0] == 6 && dims[1] == 7 && dims[2] == 2;
+  if (!(chw || hwc) || !u64(&len) || len != 84 || !need(84 * 4)) return 0;
+  if (board) {
+    if (chw) {
+      std::memcpy(board, p, 84 * 4);
+    } else {
+      for (int cell = 0; cell < 42; ++cell)
+        for (int c = 0; c < 2; ++c) std::memcpy(board + c * 42 + cell, p + (cell * 2 + c) * 4, 4);
+    }
   }
-  if (prod != 84 || !u64(&len) || len != 84 || !need(84 * 4)) return 0;
-  if (board) std::memcpy(board, p, 84 * 4);
   p += 84 * 4;
   if (!need(1) || *p++ != 1) return 0;
   if (!u64(&d) || d != 7 || !u64(&len) || len != 7 || !need(7 * 4 + 4)) return 0;
@@ -229,7 +239,11 @@ static int coach_resume_history(azb_coach* c) {
   bool exists = false;
   if (latest_examples(c->checkpoint_dir.c_str(), &it, &exists) != AZB_OK) return AZB_OK;  // no directory / no file yet
   const std::string path = c->checkpoint_dir + "/" + std::to_string(it) + ".examples";
-  return read_examples(path.c_str(), &c->history.entries, nullptr);
+  const int rc = read_examples(path.c_str(), &c->history.entries, nullptr);
+  // a resumed coach numbers its iterations after the file it resumed from: game ids (the Philox streams), shuffles and
+  // `<n>.examples` names continue instead of replaying iteration 0 into a window that already holds it
+  if (rc == AZB_OK) c->resume_base = it + 1;
+  return rc;
 }
 
 __global__ void k_scale_f32(float* __restrict__ p, size_t n, float s) {
@@ -490,6 +504,17 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     if (world == 1) return AZB_OK;
     return dist->allreduce_sum_u64_host(v, n, dist->user) ? fail(AZB_ERR_INVALID, "allreduce_sum_u64_host failed") : AZB_OK;
   };
+  // Every rank must leave a collective phase together: a rank that failed locally (capacity, file I/O, a CUDA error)
+  // tells the others at the next phase boundary instead of returning while they wait in an all-reduce forever.
+  auto agree = [&](int rc) -> int {
+    if (world == 1) return rc;
+    const std::string mine = rc ? g_err : std::string();
+    uint64_t bad = rc ? 1u : 0u;
+    if (dist->allreduce_sum_u64_host(&bad, 1, dist->user)) return fail(AZB_ERR_INVALID, "allreduce_sum_u64_host failed");
+    if (rc) return fail(rc, mine);
+    if (bad) return fail(AZB_ERR_INVALID, "another rank failed in this phase of Coach::learn (its own call reports why)");
+    return AZB_OK;
+  };
   auto split = [&](uint64_t total, uint64_t* first, uint64_t* n) {  // contiguous shares, the remainder over the first ranks
     const uint64_t base = total / world, rem = total % world;
     *n = base + (rank < rem ? 1 : 0);
@@ -549,20 +574,22 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     rep.model_id_before = model_id;
     SampleBlock blk;
     auto t0 = std::chrono::steady_clock::now();
+    const uint64_t it_id = c->resume_base + iteration;  // numbering continues after a resumed `<n>.examples`
     if (!lc.skip_first_play || iteration > 0) {  // coach.rs:240
       int rc = azb_coach_set_nnet(c, nets[cur].get());
-      if (rc) return rc;
       azb_selfplay_stats st{};
       uint64_t ep_first = 0, ep_n = 0;
       split(cfg.num_eps, &ep_first, &ep_n);
-      rc = azb_coach_self_play(c, ep_n, iteration * cfg.num_eps + ep_first, &st);  // coach.rs:241-272
-      if (rc) return rc;
+      if (!rc) rc = azb_coach_self_play(c, ep_n, it_id * cfg.num_eps + ep_first, &st);  // coach.rs:241-272
       uint64_t n = 0;
-      azb_coach_num_samples(c, &n);
-      blk.boards.resize(n * 84);
-      blk.pis.resize(n * 7);
-      blk.vs.resize(n);
-      rc = azb_coach_export_samples(c, blk.boards.data(), blk.pis.data(), blk.vs.data(), n, nullptr);
+      if (!rc) {
+        azb_coach_num_samples(c, &n);
+        blk.boards.resize(n * 84);
+        blk.pis.resize(n * 7);
+        blk.vs.resize(n);
+        rc = azb_coach_export_samples(c, blk.boards.data(), blk.pis.data(), blk.vs.data(), n, nullptr);
+      }
+      rc = agree(rc);
       if (rc) return rc;
       rep.games = st.games;
       rep.samples_played = n;
@@ -573,8 +600,8 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     rep.selfplay_ms = wall_ms(t0);
     hist.push_back(std::move(blk));                                    // coach.rs:284
     if (hist.size() > cfg.max_history_length) hist.pop_front();        // coach.rs:286-289
-    if (files) {                                                       // coach.rs:291-293
-      const int rc = azb_coach_save_train_examples(c, iteration, dir.c_str());
+    {                                                                  // coach.rs:291-293
+      const int rc = agree(files ? azb_coach_save_train_examples(c, it_id, dir.c_str()) : AZB_OK);
       if (rc) return rc;
     }
     uint64_t total = 0;
@@ -591,7 +618,7 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     // coach.rs:295-327: flatten, shuffle, AOS -> SOA
     t0 = std::chrono::steady_clock::now();
     perm.resize(total);
-    shuffle_perm(cfg.seed + rank, iteration, total, perm.data());
+    shuffle_perm(cfg.seed + rank, it_id, total, perm.data());
     sb.resize(total * 84);
     sp.resize(total * 7);
     sv.resize(total);
@@ -615,7 +642,7 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     }
     // coach.rs:329-331: train(samples, model_id, model_id + 1)
     azb_nnet* cand = nets[cur ^ 1].get();
-    int rc = azb_nnet_copy(cand, nets[cur].get());
+    int rc = agree(azb_nnet_copy(cand, nets[cur].get()));
     if (rc) return rc;
     // batch_size is the global batch: every rank contributes batch_size / world samples per step; the step count is the
     // same on all ranks (a pass = the global window once)
@@ -640,7 +667,7 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
         pv = wv.data();
       }
       float loss[2] = {0.0f, 0.0f};
-      rc = azb_nnet_train_begin(cand, pb, pp, pv, bs, loss);
+      rc = agree(azb_nnet_train_begin(cand, pb, pp, pv, bs, loss));  // (before the gradient all-reduce: nobody waits alone)
       if (rc) return rc;
       if (world > 1) {  // mean over ranks of the per-rank mean gradients = gradient of the mean loss over the global batch
         AZB_CUDA(cudaDeviceSynchronize());
@@ -655,9 +682,9 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
     }
     rep.train_steps = steps;
     rep.train_ms = wall_ms(t0);
-    if (files) {  // python_nnet.rs:76-79 save_checkpoint(model, model_id, checkpoint)
+    {  // python_nnet.rs:76-79 save_checkpoint(model, model_id, checkpoint)
       const std::string wpath = dir + "/" + std::to_string(model_id + 1) + ".azbw";
-      rc = azb_nnet_save(cand, wpath.c_str());
+      rc = agree(files ? azb_nnet_save(cand, wpath.c_str()) : AZB_OK);
       if (rc) return rc;
     }
 
@@ -672,9 +699,9 @@ int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb
       azb_arena_opts ao{};
       ao.k_open = lc.arena_k_open;
       ao.shared_trees = lc.arena_shared_trees;
-      ao.first_game_id = iteration * cfg.num_arena_games + 2 * pair_first;
-      rc = azb_arena_play_games_ex(&acfg, 2 * pairs, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), &ao, counts, nullptr,
-                                   nullptr, nullptr, nullptr, nullptr);
+      ao.first_game_id = it_id * cfg.num_arena_games + 2 * pair_first;
+      rc = agree(azb_arena_play_games_ex(&acfg, 2 * pairs, AZB_EVAL_NNET, AZB_EVAL_NNET, cand, nets[cur].get(), &ao, counts,
+                                         nullptr, nullptr, nullptr, nullptr, nullptr));
       if (rc) return rc;
       rc = sum_u64(counts, 3);
       if (rc) return rc;

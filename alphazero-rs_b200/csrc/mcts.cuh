@@ -56,7 +56,12 @@ struct TreeRec {
   uint32_t error;
   uint32_t slow;      // sticky: see WarpTree::slow
   uint32_t stat[8];
+  uint32_t tt_gen;    // generation of the tree's transposition table: entries carry tt_gen + 1 above their 49-bit key, so a
+                      // new game (AsyncMcts::default) bumps it instead of zero-filling the table (1 MB per tree at config 2)
+  uint32_t pad[3];
 };
+constexpr uint32_t kTtGenWrap = 32766u;  // 15 bits above the key; tt_gen + 1 stays in 1 .. 32767
+constexpr uint64_t kKeyMask = (1ull << 49) - 1ull;
 
 // One level of the current simulation's path (shared memory).  After the simulation's backup the
 // entries double as the PREDICTION for the next simulation of the same tree: consecutive
@@ -78,7 +83,8 @@ struct __align__(16) PathEnt {
 // Per-warp view of one tree.  Every member is warp-uniform except `stat` (lane k = stat k).
 struct WarpTree {
   uint4* blocks;   // slot id indexes this directly (16-byte slots, 8 per block)
-  uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}
+  uint4* table;    // HashEntry as uint4 {key.lo, key.hi, slot, meta}; key = tt_stamp | 49-bit state key
+  uint64_t tt_stamp;  // (tt_gen + 1) << 49: entries of another generation (or zero-filled ones) read as empty
   PathEnt* path;   // shared memory, kPathCap entries
   const uint4* win;  // shared memory, 8 entries: win_table()
   uint32_t pred_len;  // levels [0, pred_len) of `path` describe nodes the previous simulation walked
@@ -183,14 +189,14 @@ __device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask,
   uint32_t b = hash_bucket(key, bucket_mask);
   for (uint32_t probe = 0; probe <= bucket_mask; ++probe) {
     const uint64_t k = (static_cast<uint64_t>(e.y) << 32) | e.x;
-    const uint32_t hit = __ballot_sync(kFull, k == key) & 0xFFu;
+    const uint32_t hit = __ballot_sync(kFull, k == (key | t.tt_stamp)) & 0xFFu;
     if (hit) {
       const int l = __ffs(hit) - 1;
       slot = __shfl_sync(kFull, e.z, l);
       meta = __shfl_sync(kFull, e.w, l);
       return true;
     }
-    const uint32_t emp = __ballot_sync(kFull, k == 0ull) & 0xFFu;
+    const uint32_t emp = __ballot_sync(kFull, ((k ^ t.tt_stamp) >> 49) != 0ull) & 0xFFu;
     if (emp) {
       ins = b * 8u + (__ffs(emp) - 1);
       return false;
@@ -208,7 +214,7 @@ __device__ __forceinline__ bool tt_find(const WarpTree& t, uint32_t bucket_mask,
 __device__ __forceinline__ void tt_insert(const WarpTree& t, uint32_t ins, uint64_t key,
                                           uint32_t slot, uint32_t meta, int lane) {
   if (lane == 0)
-    t.table[ins] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), slot, meta);
+    t.table[ins] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>((key | t.tt_stamp) >> 32), slot, meta);
 }
 
 // ---- leaf evaluators fused into the search (NNet::predict, src/nnet.rs:40-44) --------------
@@ -349,11 +355,7 @@ __device__ __forceinline__ uint32_t* n_word_ptr(const WarpTree& t, uint32_t slot
 __device__ __forceinline__ BackupRegs backup_prepare(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
   const uint32_t sh = (slot & 1u) * 16u;
   const uint32_t old = *n_word_ptr(t, slot);
-#ifdef AZB_BACKUP_SEPARATE_N
-  uint64_t c = counter_pack(ld_w(t, slot), ld_n(t, slot)) + kVisit;
-#else
   uint64_t c = counter_pack(ld_w(t, slot), old >> sh) + kVisit;
-#endif
   c = counter_unvisit(c, v, quirks);
   BackupRegs r;
   r.w_new = static_cast<uint32_t>(c >> 32);
@@ -368,11 +370,6 @@ __device__ __forceinline__ void backup_commit(const WarpTree& t, uint32_t slot, 
   // out of L1 (measured: profiles/r1_v2_selfplay_ncu.md), and the next simulation re-reads it.
   // No other lane touches this block's header during a backup (path nodes sit in distinct blocks).
   *n_word_ptr(t, slot) = r.nword;
-}
-__device__ __forceinline__ uint32_t backup_node(const WarpTree& t, uint32_t slot, float v, uint32_t quirks) {
-  const BackupRegs r = backup_prepare(t, slot, v, quirks);
-  backup_commit(t, slot, r);
-  return r.n_new;
 }
 
 // ---- search_iteration (async_mcts.rs:219-371) --------------------------------

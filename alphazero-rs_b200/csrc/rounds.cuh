@@ -147,6 +147,15 @@ struct Control {
   int8_t* arena_result;      // [n_games] play_game's return value (arena.rs:51)
 };
 
+// Diagnostic (AZB200_ROUND_TIMES=1): %globaltimer at four points of every round — before k_compact (which = 0), before
+// k_round (1), after k_round (2), after the forward passes (3) — into times[round % cap][4].
+__global__ void k_stamp(unsigned long long* times, const unsigned int* round, uint32_t which, uint32_t cap) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const uint32_t r = which == 0u ? *round : *round - 1u;  // k_compact counts the round it starts
+  times[static_cast<size_t>(r % cap) * 4u + which] = t;
+}
+
 // ---- k_compact: recycle finished slots, hand out pending games, rebuild the dense active list -----------------
 // One thread per slot over as many CTAs as it takes (the single-CTA block scan this replaces took 13.8 us per round:
 // 8 x 20 barriers over strided loads of the slot records).  The order of the active list carries no meaning (a slot's
@@ -273,7 +282,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     if (!(rp.mode == kModeArena && rp.shared && gi != 0u))
       for (uint32_t k = 0; k < tps; ++k) {
         WarpTree tk = open_tree(pools, p, slot * tps + k);
-        clear_table(tk, p, lane);
+        fresh_table(tk, pools, p, slot * tps + k, lane);
         if (lane < 12) reinterpret_cast<uint32_t*>(&rec->tv[k])[lane] = 0u;
       }
     board = BB{0ull, 0ull};

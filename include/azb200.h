@@ -279,7 +279,8 @@ int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a,
  * Both crates are absent from /root/reference (Cargo.toml:13,24), so the byte layout is restated from
  * their published formats: parity unpinned by the reference, pinned by oracle/learn.hpp and an independent
  * Python parser in tests/.  Host-only code: these calls work without a CUDA device.
- * The reader accepts any 3-d board shape with 84 elements (the literal to_features writes [6,7,2], F11).
+ * The reader accepts the declared board shape [2,6,7] and the literal to_features shape [6,7,2] (F11), which it
+ * transposes into channel-first planes; any other shape is rejected.
  * ------------------------------------------------------------------------------------- */
 /* counts[n_iters] samples per history entry (oldest first); boards/pis/vs hold sum(counts) samples. */
 int azb_examples_write(const char* path, uint64_t n_iters, const uint64_t* counts, const float* boards,
@@ -347,7 +348,10 @@ typedef struct azb_learn_report {
   double selfplay_ms, train_ms, arena_ms;       /* host wall-clock of the three phases */
 } azb_learn_report;
 
-/* net_cfg: architecture and seed of model 0 (NNet::new(checkpoint), async_mcts.rs:125).  With save_files set, a
+/* Resume: a coach whose setup loaded `<n>.examples` numbers its iterations from n + 1 (game ids, shuffles and file names
+ * go on; the reference restarts at 0 and, seeding from entropy, plays new games — with this engine's fixed Philox streams a
+ * restart at 0 would replay the games the window already holds).  Weights restart from `0.azbw` (model ids restart).
+ * net_cfg: architecture and seed of model 0 (NNet::new(checkpoint), async_mcts.rs:125).  With save_files set, a
  * `0.azbw` already in checkpoint_directory is loaded instead of the random init, and every trained candidate is
  * written as `<model_id + 1>.azbw`.  reports[cap_reports] receives one entry per iteration; *final_net (optional)
  * receives the accepted model, owned by the caller afterwards (azb_nnet_destroy). */
@@ -370,6 +374,28 @@ typedef struct azb_dist {
 } azb_dist;
 int azb_coach_learn_dist(azb_coach* c, const azb_nnet_config* net_cfg, const azb_learn_config* lc, const azb_dist* dist,
                          azb_learn_report* reports, uint64_t cap_reports, uint64_t* n_reports, azb_nnet** final_net);
+/* The library's own communicator (NCCL, loaded with dlopen at first use: AZB200_NCCL_LIB, default libnccl.so.2) for hosts
+ * that bring none — a Rust host needs neither torch nor torchrun.  One process per GPU: rank 0 calls azb_dist_unique_id and
+ * hands the 128 bytes to the other ranks by whatever means the host has (a file, MPI, a socket); every rank calls
+ * azb_dist_init(id, rank, world, device); azb_dist_make fills an azb_dist whose callbacks run ncclAllReduce on that
+ * communicator (in place on the device gradient vector; the u64 counters staged through a device buffer), ready for
+ * azb_coach_learn_dist.  azb_dist_allreduce_f64 reduces a few host doubles (timings, counters) with the same communicator.
+ * The reference has no counterpart: it is single-process (rayon threads, crossbeam channels). */
+#define AZB_DIST_ID_BYTES 128
+enum { AZB_DIST_SUM = 0, AZB_DIST_MAX = 1, AZB_DIST_MIN = 2 };
+typedef struct azb_comm azb_comm;
+int azb_dist_unique_id(uint8_t out[AZB_DIST_ID_BYTES]);
+int azb_dist_init(const uint8_t id[AZB_DIST_ID_BYTES], uint32_t rank, uint32_t world, int32_t device, azb_comm** out);
+int azb_dist_destroy(azb_comm* c);
+int azb_dist_make(azb_comm* c, azb_dist* out);
+int azb_dist_allreduce_f64(azb_comm* c, double* values, uint64_t count, int32_t op);
+/* Self-play on several GPUs of one box through ONE call (the episode fan-out of coach.rs:241-272 over devices): a host
+ * thread per listed device sets up its own coach (and, for AZB_EVAL_NNET, its own replica of the network created from
+ * net_cfg), plays games [first_game_id + d * games_per_device, ...) and writes stats[d].  No collective on the path.
+ * wall_ms (optional) = host wall clock of the whole call.  net_cfg may be NULL for fused evaluators. */
+int azb_coach_self_play_multi(const azb_config* cfg, const azb_nnet_config* net_cfg, const int32_t* devices,
+                              uint32_t n_devices, uint64_t games_per_device, uint64_t first_game_id,
+                              azb_selfplay_stats* stats, double* wall_ms);
 /* The coach's sample history (struct Coach.history, coach.rs:19): entry counts, then the data. */
 int azb_coach_history_stat(azb_coach* c, uint64_t* n_iters, uint64_t* counts, uint64_t cap_iters, uint64_t* n_samples);
 int azb_coach_history_export(azb_coach* c, float* boards, float* pis, float* vs, uint64_t cap_samples);

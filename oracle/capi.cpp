@@ -84,6 +84,7 @@ struct azo_params {
   int32_t cpuct;
   uint32_t quirks;
   uint64_t seed;
+  uint64_t num_sim_threads;  // coach.rs:51 (1 = deterministic mode; K > 1 = waves of K, oracle/mcts.hpp)
 };
 
 static CoachParams cp_of(const azo_params* p) {
@@ -95,6 +96,7 @@ static CoachParams cp_of(const azo_params* p) {
   cp.cpuct = p->cpuct;
   cp.quirks = p->quirks;
   cp.seed = p->seed;
+  cp.num_sim_threads = p->num_sim_threads ? p->num_sim_threads : 1;
   return cp;
 }
 
@@ -194,6 +196,7 @@ void* azo_mcts_create(const int8_t* root43, const azo_params* p, int eval_kind, 
   C4 root = root43 ? from43(root43) : C4::get_init_board();
   h->mcts.reset(new AsyncMcts<C4>(root, p->mcts_reserve_size, p->num_sims, p->max_depth, 0,
                                   p->cpuct, p->quirks, h->ev.get()));
+  h->mcts->num_threads = p->num_sim_threads ? p->num_sim_threads : 1;
   return h;
   AZO_CATCH(nullptr)
 }
@@ -263,6 +266,7 @@ int azo_execute_episode(const azo_params* p, uint64_t episode_id, int eval_kind,
   std::unique_ptr<Evaluator> ev(make_eval(eval_kind, fn, user));
   AsyncMcts<C4> mcts(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims, cp.max_depth, 0,
                      cp.cpuct, cp.quirks, ev.get());
+  mcts.num_threads = cp.num_sim_threads;
   auto tr = execute_episode<C4>(cp, mcts, episode_id);
   size_t plies = tr.actions.size();
   for (size_t i = 0; i < plies; ++i) {
@@ -304,8 +308,10 @@ int azo_arena_play_games_cb(const azo_params* p, uint64_t num, int eval_a, void*
   CoachParams cp = cp_of(p);
   std::unique_ptr<Evaluator> ea(make_eval(eval_a, fn_a, user_a)), eb(make_eval(eval_b, fn_b, user_b));
   auto mk = [&](Evaluator* e) {
-    return std::make_unique<AsyncMcts<C4>>(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims,
-                                           cp.max_depth, 0, cp.cpuct, cp.quirks, e);
+    auto m = std::make_unique<AsyncMcts<C4>>(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims,
+                                             cp.max_depth, 0, cp.cpuct, cp.quirks, e);
+    m->num_threads = cp.num_sim_threads;
+    return m;
   };
   std::unique_ptr<AsyncMcts<C4>> ta, tb;
   if (shared_trees) { ta = mk(ea.get()); tb = mk(eb.get()); }
@@ -393,6 +399,7 @@ int azo_bench_selfplay(const azo_params* p, int eval_kind, uint64_t n_games, uin
           std::unique_ptr<Evaluator> ev(make_eval(eval_kind, nullptr, nullptr));
           AsyncMcts<C4> mcts(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims,
                              cp.max_depth, 0, cp.cpuct, cp.quirks, ev.get());
+          mcts.num_threads = cp.num_sim_threads;
           auto tr = execute_episode<C4>(cp, mcts, first_game_id + g);
           tot_sims += tr.stats.sims;
           tot_plies += tr.actions.size();
@@ -439,6 +446,7 @@ int azo_bench_selfplay_net(const azo_params* p, int blocks, const float* params,
           CpuNetEvaluator ev(&net);
           AsyncMcts<C4> mcts(C4::get_init_board(), cp.mcts_reserve_size, cp.num_sims, cp.max_depth, 0, cp.cpuct,
                              cp.quirks, &ev);
+          mcts.num_threads = cp.num_sim_threads;
           auto tr = execute_episode<C4>(cp, mcts, first_game_id + g, max_plies ? max_plies : static_cast<size_t>(-1));
           tot_sims += tr.stats.sims;
           tot_plies += tr.actions.size();

@@ -19,6 +19,7 @@ struct CoachParams {                 // the fields of struct Coach (coach.rs:18-
   size_t temp_threshold = 15;
   size_t num_sims = 25;
   size_t max_depth = 1000;
+  size_t num_sim_threads = 1;        // coach.rs:32,51
   int32_t cpuct = 1;
   uint32_t quirks = AZO_PROFILE_SANE;
   uint64_t seed = 1;

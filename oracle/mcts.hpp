@@ -191,9 +191,107 @@ class AsyncMcts {                      // async_mcts.rs:14-24
     stats.sims++;
   }
 
-  // search (:191-217) with num_threads = 1
+  // search (:191-217).  num_threads = 1: the deterministic mode every parity test pins.
+  // num_threads = K > 1 (tree-parallel search with virtual loss, :196-214 + node.rs:77-92,359-365): the reference runs K
+  // OS threads whose interleaving is up to the scheduler, so its result is not reproducible; here the K threads run in
+  // ONE fixed interleaving, wave by wave — the K selections of a wave one after the other (each sees the virtual losses
+  // and the locks of the earlier ones), then the wave's evaluations, then the K backups in thread order.  That is a
+  // schedule the reference can produce, and it is what the device does (csrc/mcts.cuh, wave mode), bit for bit.
+  size_t num_threads = 1;
   void search(size_t root_idx) {
-    for (size_t sim_id = 0; sim_id < num_sims; ++sim_id) search_iteration(root_idx);
+    if (num_threads <= 1) {
+      for (size_t sim_id = 0; sim_id < num_sims; ++sim_id) search_iteration(root_idx);
+      return;
+    }
+    if (num_sims % num_threads != 0) throw std::runtime_error("num_sims % num_threads != 0 (async_mcts.rs:192)");
+    for (size_t sim_id = 0; sim_id < num_sims; sim_id += num_threads) search_wave(root_idx, num_threads);
+  }
+
+  struct InFlight {
+    size_t cur = 0;                 // where the walk stopped (resolved node index)
+    std::vector<size_t> path;      // node_path
+    float v = 0.0f;                 // value to back up (known at once, or after the wave's evaluations)
+    int wait_for = -1;              // >= 0: the value is -(network value) of that in-flight simulation's leaf
+    bool evaluate = false;          // this simulation owns a pending evaluation of `cur`
+  };
+
+  // One thread's walk of a wave: async_mcts.rs:236-356 with the repairs of App. C, visit() = N + 1 and VL + 1 on every node
+  // of the path; placeholders that another in-flight simulation holds are Locked and skipped on the retry (:253-257,
+  // node.rs:359-365).  Repairs that only matter with K > 1:
+  //   F17: no selectable child (every child Locked; node.rs:367 unwrap panics) -> the walk ends at this node with v = 0;
+  //   F18: a node whose evaluation is still pending in this wave is reached through a link or a duplicate (the reference
+  //        reads its missing policy and panics, :254 -> node.rs:354) -> the walk ends there and shares that evaluation.
+  void select_wave(size_t root_idx, std::vector<InFlight>& fl, size_t t) {
+    InFlight& me = fl[t];
+    size_t cur = root_idx, depth = 0;
+    for (;;) {
+      Node<G>* n = nodes->get(cur);
+      const size_t rcur = *nodes->resolve(cur);
+      stats.levels++;
+      if (depth > max_depth) { n->visit(); me.v = n->mu.s->eval_heuristic(); break; }
+      if (n->e != 0.0f) { n->visit(); stats.terminal_hits++; me.v = n->e; break; }
+      if (!n->mu.p) {
+        n->visit();
+        int owner = -1;
+        for (size_t k = 0; k < t; ++k)
+          if (fl[k].evaluate && fl[k].cur == rcur) owner = static_cast<int>(k);
+        if (owner >= 0) me.wait_for = owner;   // F18
+        else me.evaluate = true;               // F1: a root that was never evaluated
+        cur = rcur;
+        break;
+      }
+      n->visit();
+      size_t c = nodes->best_child(cur, cpuct, false);
+      if (nodes->state(c) == NodeState::Locked) {              // :253-257: retry without the Locked children
+        bool any = false;
+        for (size_t ch : n->children) any = any || nodes->state(ch) != NodeState::Locked;
+        if (!any) { me.v = 0.0f; cur = rcur; break; }          // F17
+        c = nodes->best_child(cur, cpuct, true);
+      }
+      if (nodes->state(c) == NodeState::PlaceHolder) {
+        if (!nodes->lock(c)) throw std::runtime_error("lock failed on an unlocked placeholder");
+        me.path.push_back(cur);
+        uint8_t a = nodes->raw(c)->a;
+        auto nx = n->mu.s->get_next_state(1, a);
+        G s2 = nx.first.get_canonical_form(nx.second);
+        cur = c;
+        auto up = nodes->upgrade(cur, s2);
+        if (!up) throw std::runtime_error("Upgraded invalid node! (:291)");
+        if (!*up) { stats.dup_links++; cur = *nodes->resolve(cur); continue; }
+        stats.expansions++;
+        Node<G>* m = nodes->get(cur);
+        m->visit();
+        if (m->e != 0.0f) { nodes->unlock(cur); stats.terminal_hits++; me.v = m->e; break; }
+        me.evaluate = true;                                    // stays Locked until the wave's evaluation phase
+        break;
+      }
+      me.path.push_back(cur);
+      cur = c;
+      depth += 1;
+    }
+    me.cur = *nodes->resolve(cur);
+  }
+
+  void search_wave(size_t root_idx, size_t K) {
+    std::vector<InFlight> fl(K);
+    for (size_t t = 0; t < K; ++t) select_wave(root_idx, fl, t);
+    for (size_t t = 0; t < K; ++t)
+      if (fl[t].evaluate) fl[t].v = -evaluate(fl[t].cur);      // set_policy + unlock inside
+    for (size_t t = 0; t < K; ++t)
+      if (fl[t].wait_for >= 0) fl[t].v = fl[static_cast<size_t>(fl[t].wait_for)].v;
+    for (size_t t = 0; t < K; ++t) {
+      size_t cur = fl[t].cur;
+      float sign = 1.0f;
+      const size_t root_res = *nodes->resolve(root_idx);
+      for (;;) {
+        nodes->get(cur)->unvisit(sign * fl[t].v, quirks);
+        if (!(quirks & AZO_Q2_BACKUP_NO_ALTERNATE)) sign = -sign;
+        if (*nodes->resolve(cur) == root_res) break;
+        cur = fl[t].path.back();
+        fl[t].path.pop_back();
+      }
+      stats.sims++;
+    }
   }
 
   // F12: a state absent from the tree becomes a new root (push + upgrade).

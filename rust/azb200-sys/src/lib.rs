@@ -147,7 +147,8 @@ pub struct azb_learn_report {
     pub arena_ms: f64,
 }
 
-/// The caller's communicator for `azb_coach_learn_dist` (the library owns none): both callbacks return 0 on success.
+/// The communicator `azb_coach_learn_dist` reduces with: the caller's own callbacks, or the library's NCCL communicator
+/// (`azb_dist_init` + `azb_dist_make`).  Both callbacks return 0 on success.
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct azb_dist {
@@ -170,6 +171,14 @@ pub struct azb_nnet {
 pub struct azb_mcts {
     _opaque: [u8; 0],
 }
+#[repr(C)]
+pub struct azb_comm {
+    _opaque: [u8; 0],
+}
+pub const AZB_DIST_ID_BYTES: usize = 128;
+pub const AZB_DIST_SUM: i32 = 0;
+pub const AZB_DIST_MAX: i32 = 1;
+pub const AZB_DIST_MIN: i32 = 2;
 
 extern "C" {
     pub fn azb_last_error() -> *const c_char;
@@ -219,6 +228,14 @@ extern "C" {
     // arena, src/arena.rs:7-99
     pub fn azb_arena_play_games(cfg: *const azb_config, num: u64, eval_a: i32, eval_b: i32, net_a: *mut azb_nnet, net_b: *mut azb_nnet, k_open: u32, out_counts: *mut u64, results: *mut i8, stats: *mut azb_selfplay_stats) -> c_int;
     pub fn azb_arena_play_games_ex(cfg: *const azb_config, num: u64, eval_a: i32, eval_b: i32, net_a: *mut azb_nnet, net_b: *mut azb_nnet, opts: *const azb_arena_opts, out_counts: *mut u64, results: *mut i8, actions: *mut u8, root_counts: *mut u16, plies: *mut u32, stats: *mut azb_selfplay_stats) -> c_int;
+
+    // the library's own NCCL communicator and the multi-GPU fan-out (no counterpart in the reference: SURVEY 2.2)
+    pub fn azb_dist_unique_id(out: *mut u8) -> c_int;
+    pub fn azb_dist_init(id: *const u8, rank: u32, world: u32, device: i32, out: *mut *mut azb_comm) -> c_int;
+    pub fn azb_dist_destroy(c: *mut azb_comm) -> c_int;
+    pub fn azb_dist_make(c: *mut azb_comm, out: *mut azb_dist) -> c_int;
+    pub fn azb_dist_allreduce_f64(c: *mut azb_comm, values: *mut f64, count: u64, op: i32) -> c_int;
+    pub fn azb_coach_self_play_multi(cfg: *const azb_config, net_cfg: *const azb_nnet_config, devices: *const i32, n_devices: u32, games_per_device: u64, first_game_id: u64, stats: *mut azb_selfplay_stats, wall_ms: *mut f64) -> c_int;
 
     // on-disk formats: coach.rs:55-81,159-167 and the weight checkpoints
     pub fn azb_examples_write(path: *const c_char, n_iters: u64, counts: *const u64, boards: *const f32, pis: *const f32, vs: *const f32) -> c_int;

@@ -69,44 +69,44 @@ impl std::fmt::Display for ConnectFourGame {
 
 impl ConnectFourGame {
     /// Game::get_init_board — connect_four_game.rs:82-84
-    pub fn get_init_board() -> Result<Self> {
+    pub fn try_get_init_board() -> Result<Self> {
         let mut st = sys::azb_c4_state { s: [[0; 7]; 6], me: 1 };
         check(unsafe { sys::azb_c4_init(&mut st, 1) })?;
         Ok(ConnectFourGame(st))
     }
     /// Game::get_feature_shape — :86-88
-    pub fn get_feature_shape() -> Vec<usize> {
+    pub fn feature_shape() -> Vec<usize> {
         let mut out = [0usize; 3];
         unsafe { sys::azb_c4_feature_shape(out.as_mut_ptr()) };
         out.to_vec()
     }
     /// Game::get_next_state(player, action) -> (state, -player) — :90-102
-    pub fn get_next_state(&self, player: i8, action: u8) -> Result<(Self, i8)> {
+    pub fn try_get_next_state(&self, player: i8, action: u8) -> Result<(Self, i8)> {
         let mut out = self.0;
         let mut next = 0i8;
         check(unsafe { sys::azb_c4_next_state(&self.0, &player, &action, 1, &mut out, &mut next) })?;
         Ok((ConnectFourGame(out), next))
     }
     /// Game::get_valid_moves — :104-109 (the player argument is ignored there too)
-    pub fn get_valid_moves(&self, _player: i8) -> Result<Array<u8, Ix1>> {
+    pub fn try_get_valid_moves(&self, _player: i8) -> Result<Array<u8, Ix1>> {
         let mut out = [0u8; sys::AZB_C4_ACTIONS];
         check(unsafe { sys::azb_c4_valid_moves(&self.0, 1, out.as_mut_ptr()) })?;
         Ok(Array::from(out.to_vec()))
     }
     /// Game::get_game_ended(player) — :111-196; `quirks` bit Q1 selects the literal scan ranges
-    pub fn get_game_ended(&self, player: i8, quirks: u32) -> Result<f32> {
+    pub fn try_get_game_ended(&self, player: i8, quirks: u32) -> Result<f32> {
         let mut out = 0f32;
         check(unsafe { sys::azb_c4_game_ended(&self.0, &player, 1, quirks, &mut out) })?;
         Ok(out)
     }
     /// Game::get_canonical_form(player) — :198-203 (repaired: cells * player)
-    pub fn get_canonical_form(&self, player: i8) -> Result<Self> {
+    pub fn try_get_canonical_form(&self, player: i8) -> Result<Self> {
         let mut out = self.0;
         check(unsafe { sys::azb_c4_canonical_form(&self.0, &player, 1, &mut out) })?;
         Ok(ConnectFourGame(out))
     }
     /// Game::get_symmetries(pi) — :205-211: identity and the column mirror
-    pub fn get_symmetries(&self, pi: ArrayView1<f32>) -> Result<Vec<(Self, Policy)>> {
+    pub fn try_get_symmetries(&self, pi: ArrayView1<f32>) -> Result<Vec<(Self, Policy)>> {
         assert_eq!(pi.len(), sys::AZB_C4_ACTIONS);
         let pi_in: Vec<f32> = pi.iter().cloned().collect();
         let mut states = [self.0; 2];
@@ -117,13 +117,13 @@ impl ConnectFourGame {
             .collect())
     }
     /// Game::eval_heuristic — :214-216
-    pub fn eval_heuristic(&self) -> Result<f32> {
+    pub fn try_eval_heuristic(&self) -> Result<f32> {
         let mut out = 0f32;
         check(unsafe { sys::azb_c4_eval_heuristic(&self.0, 1, &mut out) })?;
         Ok(out)
     }
     /// Game::to_features — :219-237 (repaired: [2,6,7], channel 0 = cells of `me`)
-    pub fn to_features(&self) -> Result<ArrayD<F>> {
+    pub fn try_to_features(&self) -> Result<ArrayD<F>> {
         let mut out = vec![0f32; sys::AZB_C4_FEATURES];
         check(unsafe { sys::azb_c4_to_features(&self.0, 1, out.as_mut_ptr()) })?;
         Ok(ArrayD::from_shape_vec(IxDyn(&[2, 6, 7]), out).unwrap())
@@ -143,6 +143,70 @@ impl ConnectFourGame {
 }
 
 // -------------------------------------------------------------------------------------------------
+// The reference's plugin traits, signature for signature (src/game.rs:10-28, src/nnet.rs:35-45), so that code written
+// against `alphazero_rs::game::Game` / `alphazero_rs::nnet::NNet` compiles against this crate by changing the `use` line.
+// The reference's own path panics on failure (`unwrap`, `assert!`); so do these trait methods — the `try_*` inherent
+// methods return `Result` for callers that want the status code.
+// -------------------------------------------------------------------------------------------------
+pub type PolicyView<'a> = ArrayView1<'a, f32>; // src/nnet.rs:18
+pub type BatchedBoardFeaturesView<'a> = ArrayViewD<'a, F>; // src/nnet.rs:13
+pub type BatchedPolicy = Array2<f32>; // src/nnet.rs:15
+pub type BatchedValue = Array1<f32>; // src/nnet.rs:20
+pub type ArcSOATrainingSamples = (ndarray::ArcArray<F, IxDyn>, ndarray::ArcArray<f32, ndarray::Ix2>, ndarray::ArcArray<f32, Ix1>); // src/nnet.rs:29-33
+
+pub trait Game: std::fmt::Display + Sized + Send + Clone + std::hash::Hash + Eq {
+    fn get_init_board() -> Self;
+    fn get_feature_shape() -> Vec<usize>;
+    fn get_next_state(&self, player: i8, action: u8) -> (Self, i8);
+    fn get_valid_moves(&self, player: i8) -> Array<u8, Ix1>;
+    fn get_game_ended(&self, player: i8) -> f32;
+    fn get_canonical_form(&self, player: i8) -> Self;
+    fn get_symmetries(&self, pi: PolicyView) -> Vec<(Self, Policy)>;
+    fn eval_heuristic(&self) -> f32;
+    fn to_features(&self) -> ArrayD<F>;
+}
+
+pub trait NNet {
+    fn new<P: AsRef<Path>>(checkpoint: P) -> Self;
+    fn train(&mut self, examples: ArcSOATrainingSamples, previous_model_id: usize, model_id: usize);
+    fn predict(&self, board: BatchedBoardFeaturesView, model_id: usize) -> (BatchedPolicy, BatchedValue);
+}
+
+/// Quirk profile the trait methods run under (`get_game_ended`'s scan ranges, Q1).  The trait has no room for it, so it
+/// is process-wide like the reference's compile-time constants; default = `AZB_PROFILE_SANE`.
+pub static GAME_QUIRKS: std::sync::atomic::AtomicU32 = std::sync::atomic::AtomicU32::new(sys::AZB_PROFILE_SANE);
+
+impl Game for ConnectFourGame {
+    fn get_init_board() -> Self {
+        ConnectFourGame::try_get_init_board().expect("azb_c4_init")
+    }
+    fn get_feature_shape() -> Vec<usize> {
+        ConnectFourGame::feature_shape()
+    }
+    fn get_next_state(&self, player: i8, action: u8) -> (Self, i8) {
+        self.try_get_next_state(player, action).expect("get_next_state (the reference underflows and panics on a full column)")
+    }
+    fn get_valid_moves(&self, player: i8) -> Array<u8, Ix1> {
+        self.try_get_valid_moves(player).expect("get_valid_moves")
+    }
+    fn get_game_ended(&self, player: i8) -> f32 {
+        self.try_get_game_ended(player, GAME_QUIRKS.load(std::sync::atomic::Ordering::Relaxed)).expect("get_game_ended")
+    }
+    fn get_canonical_form(&self, player: i8) -> Self {
+        self.try_get_canonical_form(player).expect("get_canonical_form")
+    }
+    fn get_symmetries(&self, pi: PolicyView) -> Vec<(Self, Policy)> {
+        self.try_get_symmetries(pi).expect("get_symmetries")
+    }
+    fn eval_heuristic(&self) -> f32 {
+        self.try_eval_heuristic().expect("eval_heuristic")
+    }
+    fn to_features(&self) -> ArrayD<F> {
+        self.try_to_features().expect("to_features")
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // NNet (src/nnet.rs:35-45)
 // -------------------------------------------------------------------------------------------------
 pub struct B200Net {
@@ -155,7 +219,7 @@ unsafe impl Send for B200Net {}
 impl B200Net {
     /// NNet::new(checkpoint): ResNet-6x128, bf16 tensor-core tower, He-normal init; `<checkpoint>/0.azbw` is loaded
     /// when it exists.
-    pub fn new<P: AsRef<Path>>(checkpoint: P) -> Result<Self> {
+    pub fn try_new<P: AsRef<Path>>(checkpoint: P) -> Result<Self> {
         Self::with_config(checkpoint, sys::azb_nnet_config { device: 0, blocks: 6, precision: sys::AZB_NNET_BF16_TC, reserved: 0, seed: 7 })
     }
     pub fn with_config<P: AsRef<Path>>(checkpoint: P, cfg: sys::azb_nnet_config) -> Result<Self> {
@@ -180,7 +244,7 @@ impl B200Net {
     }
     /// NNet::train(examples, previous_model_id, model_id): one Adam step on the batch; the trained weights are saved
     /// as `<checkpoint>/<model_id>.azbw` (python_nnet.rs:76-79).  Returns (policy loss, value loss).
-    pub fn train(&mut self, examples: &SOATrainingSamples, _previous_model_id: usize, model_id: usize) -> Result<(f32, f32)> {
+    pub fn try_train(&mut self, examples: &SOATrainingSamples, _previous_model_id: usize, model_id: usize) -> Result<(f32, f32)> {
         let (boards, pis, vs) = examples;
         let n = vs.len();
         assert!(boards.len() == n * sys::AZB_C4_FEATURES && pis.len() == n * sys::AZB_C4_ACTIONS);
@@ -195,7 +259,7 @@ impl B200Net {
         Ok((loss[0], loss[1]))
     }
     /// NNet::predict(board[B,2,6,7], model_id) -> (pi[B,7], v[B])
-    pub fn predict(&self, board: ArrayViewD<F>, model_id: usize) -> Result<(Array2<f32>, Array1<f32>)> {
+    pub fn try_predict(&self, board: ArrayViewD<F>, model_id: usize) -> Result<(Array2<f32>, Array1<f32>)> {
         let n = board.len() / sys::AZB_C4_FEATURES;
         let b = board.as_standard_layout();
         let mut pi = Array2::<f32>::zeros((n, sys::AZB_C4_ACTIONS));
@@ -213,6 +277,52 @@ impl B200Net {
 impl Drop for B200Net {
     fn drop(&mut self) {
         unsafe { sys::azb_nnet_destroy(self.h) };
+    }
+}
+
+impl NNet for B200Net {
+    /// src/nnet.rs:36
+    fn new<P: AsRef<Path>>(checkpoint: P) -> Self {
+        B200Net::try_new(checkpoint).expect("NNet::new")
+    }
+    /// src/nnet.rs:38 — one Adam step on the batch, weights saved as `<checkpoint>/<model_id>.azbw`
+    fn train(&mut self, examples: ArcSOATrainingSamples, previous_model_id: usize, model_id: usize) {
+        let owned: SOATrainingSamples = (examples.0.to_owned(), examples.1.to_owned(), examples.2.to_owned());
+        self.try_train(&owned, previous_model_id, model_id).expect("NNet::train");
+    }
+    /// src/nnet.rs:40-44
+    fn predict(&self, board: BatchedBoardFeaturesView, model_id: usize) -> (BatchedPolicy, BatchedValue) {
+        self.try_predict(board, model_id).expect("NNet::predict")
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// AsyncMcts (src/async_mcts.rs; private in the reference, which builds the arena players from it: coach.rs:333-372)
+// -------------------------------------------------------------------------------------------------
+/// One persistent search tree on the device with a fused evaluator (`AZB_EVAL_UNIFORM` = the example's stub network,
+/// examples/connect_four.rs:26-42).  Trees that search with a network live inside `Coach` / `arena::play_games_mcts`.
+pub struct AsyncMcts {
+    h: *mut sys::azb_mcts,
+}
+impl AsyncMcts {
+    /// AsyncMcts::default (async_mcts.rs:27-48) from a filled `azb_config` (num_sims, cpuct, max_depth, evaluator, ...).
+    pub fn from_config(cfg: &sys::azb_config) -> Result<Self> {
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::azb_mcts_create(cfg, 1, &mut h) })?;
+        Ok(AsyncMcts { h })
+    }
+    /// get_action_prob(s, temp, ...) — async_mcts.rs:74-115: num_sims simulations from the canonical state, then the
+    /// visit-count policy.
+    pub fn get_action_prob(&self, s: &ConnectFourGame, temp: f32) -> Result<Policy> {
+        let mut counts = [0u16; sys::AZB_C4_ACTIONS];
+        let mut pi = [0f32; sys::AZB_C4_ACTIONS];
+        check(unsafe { sys::azb_mcts_get_action_prob(self.h, &s.0, temp, counts.as_mut_ptr(), pi.as_mut_ptr()) })?;
+        Ok(Array::from(pi.to_vec()))
+    }
+}
+impl Drop for AsyncMcts {
+    fn drop(&mut self) {
+        unsafe { sys::azb_mcts_destroy(self.h) };
     }
 }
 
@@ -350,14 +460,60 @@ pub mod arena {
         Draw,
     } // src/arena.rs:54-59
 
-    /// arena::play_games(num, [player_a, player_b], None, false) — src/arena.rs:62-99 — with the two MCTS players of
-    /// coach.rs:333-375 (temp 0).  num/2 games per seat order; the counts are player A's.
-    pub fn play_games(cfg: &sys::azb_config, num: usize, net_a: &B200Net, net_b: &B200Net, k_open: u32)
-                      -> Result<std::collections::HashMap<GameResult, usize>> {
+    /// arena::play_game(player_actions, board, verbose) — src/arena.rs:7-52, closure for closure: the two players are
+    /// host closures over a canonical board, every `Game` call is one call of the bitboard kernel.  This is the literal
+    /// API for callers that bring their own players; the gating match of Coach::learn runs on the device instead
+    /// (`play_games_mcts`).
+    pub fn play_game<G: Game>(player_actions: &[&dyn Fn(&G) -> u8], board: &Option<G>, verbose: bool) -> i8 {
+        assert!(player_actions.len() == 2);
+        let mut cur_player: i8 = 1;
+        let mut board: G = board.clone().unwrap_or_else(G::get_init_board);
+        let mut iteration = 0;
+        while board.get_game_ended(cur_player) == 0.0 {
+            iteration += 1;
+            if verbose {
+                println!("Turn {}, Player {}\n{}", iteration, cur_player, board);
+            }
+            let canonical_board = board.get_canonical_form(cur_player);
+            let action = player_actions[if cur_player == 1 { 0 } else { 1 }](&canonical_board);
+            let valids = canonical_board.get_valid_moves(1);
+            assert!(valids[action as usize] > 0, "Action {} is not valid! valids = {}", action, valids);
+            let (new_board, new_cur_player) = board.get_next_state(cur_player, action);
+            board = new_board;
+            cur_player = new_cur_player;
+        }
+        // arena.rs:51: a value close to 0 rounds to a draw
+        cur_player * f32::round(board.get_game_ended(cur_player)) as i8
+    }
+
+    /// arena::play_games(num, player_actions, board, verbose) — src/arena.rs:62-99: both seat orders, num / 2 games each,
+    /// tallied for the FIRST closure (Heap's permutations of two elements: [0, 1] then [1, 0]).
+    pub fn play_games<G: Game>(num: usize, player_actions: Vec<&dyn Fn(&G) -> u8>, board: Option<G>, verbose: bool)
+                               -> std::collections::HashMap<GameResult, usize> {
+        assert!(player_actions.len() == 2);
+        let mut all: std::collections::HashMap<GameResult, usize> = std::collections::HashMap::new();
+        for ordering in 0..2 {
+            let seated: Vec<&dyn Fn(&G) -> u8> =
+                if ordering == 0 { vec![player_actions[0], player_actions[1]] } else { vec![player_actions[1], player_actions[0]] };
+            let (win_cond, lose_cond) = if ordering == 0 { (1, -1) } else { (-1, 1) };
+            for _ in 0..(num / 2) {
+                let r = play_game(&seated, &board, verbose);
+                let key = if r == win_cond { GameResult::Win } else if r == lose_cond { GameResult::Loss } else { GameResult::Draw };
+                *all.entry(key).or_insert(0) += 1;
+            }
+        }
+        all
+    }
+
+    /// The match of coach.rs:333-375 (two MCTS players, temp 0, arg-max with ties to the highest action) entirely on the
+    /// device.  `opts.shared_trees = 1` is the reference's layout (pmcts / nmcts created once, games one after the other).
+    pub fn play_games_mcts(cfg: &sys::azb_config, num: usize, net_a: &B200Net, net_b: &B200Net, opts: sys::azb_arena_opts)
+                           -> Result<std::collections::HashMap<GameResult, usize>> {
         let mut counts = [0u64; 3];
         check(unsafe {
-            sys::azb_arena_play_games(cfg, num as u64, sys::AZB_EVAL_NNET, sys::AZB_EVAL_NNET, net_a.as_raw(), net_b.as_raw(),
-                                      k_open, counts.as_mut_ptr(), ptr::null_mut(), ptr::null_mut())
+            sys::azb_arena_play_games_ex(cfg, num as u64, sys::AZB_EVAL_NNET, sys::AZB_EVAL_NNET, net_a.as_raw(), net_b.as_raw(),
+                                         &opts, counts.as_mut_ptr(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut(),
+                                         ptr::null_mut(), ptr::null_mut())
         })?;
         let mut out = std::collections::HashMap::new();
         out.insert(GameResult::Win, counts[0] as usize);

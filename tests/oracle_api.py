@@ -17,13 +17,13 @@ PREDICT_FN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_f
 class Params(C.Structure):
     _fields_ = [("mcts_reserve_size", C.c_uint64), ("temp_threshold", C.c_uint64),
                 ("num_sims", C.c_uint64), ("max_depth", C.c_uint64), ("cpuct", C.c_int32),
-                ("quirks", C.c_uint32), ("seed", C.c_uint64)]
+                ("quirks", C.c_uint32), ("seed", C.c_uint64), ("num_sim_threads", C.c_uint64)]
 
 
-def params(num_sims=25, quirks=0, seed=1, temp_threshold=15, max_depth=1000, cpuct=1, reserve=None):
+def params(num_sims=25, quirks=0, seed=1, temp_threshold=15, max_depth=1000, cpuct=1, reserve=None, num_sim_threads=1):
     if reserve is None:
         reserve = max(4096, int(num_sims) * 8 * 64)
-    return Params(reserve, temp_threshold, num_sims, max_depth, cpuct, quirks, seed)
+    return Params(reserve, temp_threshold, num_sims, max_depth, cpuct, quirks, seed, num_sim_threads)
 
 
 L = C.CDLL(LIB_PATH)

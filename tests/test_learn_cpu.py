@@ -98,13 +98,28 @@ def test_examples_reader_edge_cases(azb, tmp_path):
     path = tmp_path / "0.examples"
     azb.examples_write(path, [2], boards, pis, vs)
     blob = path.read_bytes()
-    # the literal Game::to_features writes [6,7,2] (F11): any 3-d shape of 84 elements is accepted
+    # the literal Game::to_features writes [6,7,2] (H,W,C — F11) where the declared shape is [2,6,7]: such a file is what a
+    # real reference run would leave behind.  The reader transposes it into the engine's channel-first planes (it used to
+    # copy the 84 floats verbatim, interleaving the two planes per cell — ADVICE r1).
+    hwc = np.ascontiguousarray(boards.reshape(2, 2, 6, 7).transpose(0, 2, 3, 1))  # the same samples, channel-last
     lit = bytearray(blob)
-    off = 8 + 8 + 1 + 8
-    lit[off:off + 24] = struct.pack("<3Q", 6, 7, 2)
+    for i in range(2):
+        off = 8 + 8 + i * 426 + 1 + 8
+        lit[off:off + 24] = struct.pack("<3Q", 6, 7, 2)
+        lit[off + 24 + 8:off + 24 + 8 + 336] = hwc[i].tobytes()
     (tmp_path / "1.examples").write_bytes(bytes(lit))
     c, b, p, v = azb.examples_read(tmp_path / "1.examples")
-    assert c.tolist() == [2] and (b.reshape(2, -1) == boards.reshape(2, -1)).all()
+    assert c.tolist() == [2] and np.array_equal(b.reshape(2, 2, 6, 7), boards.reshape(2, 2, 6, 7))
+    assert np.array_equal(p, pis) and np.array_equal(v, vs)
+    # any other shape is not a connect-four sample, even when it has 84 elements
+    for dims in ((7, 6, 2), (2, 7, 6), (1, 1, 84), (3, 4, 7)):
+        odd = bytearray(blob)
+        off = 8 + 8 + 1 + 8
+        odd[off:off + 24] = struct.pack("<3Q", *dims)
+        (tmp_path / "2.examples").write_bytes(bytes(odd))
+        with pytest.raises(azb.AzbError) as e:
+            azb.examples_read(tmp_path / "2.examples")
+        assert e.value.code == azb.ERR_INVALID
     for bad in (blob[:-1], blob + b"\0", blob[:8] + struct.pack("<Q", 3) + blob[16:], b"", blob[:100]):
         (tmp_path / "2.examples").write_bytes(bad)
         with pytest.raises(azb.AzbError) as e:

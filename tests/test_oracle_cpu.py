@@ -107,3 +107,39 @@ def test_oracle_episode_fixture(oracle):
         assert ep["vs"].tolist() == e["vs"]
         assert [int(x) for x in ep["stats"]] == e["stats"]
         assert np.float32(ep["final_r"]) == np.float32(e["final_r"]) and ep["final_player"] == e["final_player"]
+
+
+def test_cpu_network_matches_torch_restatement(azb, oracle):
+    """oracle/nnet_cpu.hpp (the plain C++ fp32 forward behind the CPU-baseline legs of BASELINE configs 1 and 3) against an
+    independent torch float64 restatement of the same architecture on the same random parameters: 1e-4, the tolerance the
+    north star states for fp32.  azb.param_layout is host-only Python (no device call)."""
+    import torch
+    import torch.nn.functional as F
+    blocks = 2
+    L = azb.param_layout(blocks)
+    rng = np.random.default_rng(5)
+    params = (rng.standard_normal(L["total"]) * 0.05).astype(np.float32)
+    boards = (rng.random((6, 2, 6, 7)) < 0.3).astype(np.float32)
+    boards[:, 1] *= 1.0 - boards[:, 0]
+
+    def get(name):
+        o, shape = L[name]
+        return torch.from_numpy(params[o:o + int(np.prod(shape))].reshape(shape).copy()).double()
+
+    x = torch.from_numpy(boards).double()
+    x = F.relu(F.conv2d(x, get("stem_w").reshape(3, 3, 2, 128).permute(3, 2, 0, 1), get("stem_b"), padding=1))
+    tw, tb = get("tower_w"), get("tower_b")
+    for b in range(blocks):
+        y = F.relu(F.conv2d(x, tw[2 * b].reshape(3, 3, 128, 128).permute(3, 2, 0, 1), tb[2 * b], padding=1))
+        y = F.conv2d(y, tw[2 * b + 1].reshape(3, 3, 128, 128).permute(3, 2, 0, 1), tb[2 * b + 1], padding=1)
+        x = F.relu(x + y)
+    pol = F.relu(torch.einsum("bchw,cp->bphw", x, get("pol_w")) + get("pol_b").view(1, 2, 1, 1)).reshape(len(boards), 84)
+    rpi = torch.softmax(pol @ get("pol_fc_w") + get("pol_fc_b"), dim=1).numpy()
+    val = F.relu(torch.einsum("bchw,c->bhw", x, get("val_w")) + get("val_b")).reshape(len(boards), 42)
+    rv = torch.tanh(F.relu(val @ get("val_fc1_w") + get("val_fc1_b")) @ get("val_fc2_w") + get("val_fc2_b")).numpy()
+    pi, v = oracle.cpu_net_predict(params, blocks, boards)
+    assert np.abs(pi - rpi).max() < 1e-4 and np.abs(v - rv).max() < 1e-4
+    assert np.abs(pi - pi[0]).max() > 1e-4  # different positions, different outputs
+    # the timing leg built on it runs and counts what it did
+    r = oracle.bench_selfplay_net(params, blocks, 2, 2, num_sims=6, max_plies=2, seed=3)
+    assert r["sims"] == 2 * 2 * 6 and r["plies"] == 4 and r["evals"] > 0

@@ -60,3 +60,50 @@ def test_safe_wrapper_uses_only_declared_symbols():
     src = open(os.path.join(ROOT, "rust", "azb200", "src", "lib.rs")).read()
     used = set(re.findall(r"sys::(azb_[a-z0-9_]+)\s*\(", src))
     assert used and used <= set(rust_functions())
+
+
+def test_integration_excerpt_matches_crate():
+    """INTEGRATION.md shows struct and fn declarations a maintainer may copy: every one of them must be the crate's own
+    text (a struct 16 bytes short would make the library write past it — ADVICE r1).  scripts/gen_integration.py rewrites
+    the block."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_integration", os.path.join(ROOT, "scripts", "gen_integration.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    a = md.index("<!-- BEGIN sys-excerpt -->") + len("<!-- BEGIN sys-excerpt -->\n")
+    b = md.index("\n<!-- END sys-excerpt -->")
+    assert md[a:b] == gen.excerpt(), "INTEGRATION.md drifted from rust/azb200-sys: run python scripts/gen_integration.py"
+    # and no other Rust struct declaration hides elsewhere in the document
+    for name, body in re.findall(r"pub struct (azb_[a-z0-9_]+) \{(.*?)\n\}", md, flags=re.S):
+        crate = re.search(r"pub struct %s \{(.*?)\n\}" % name, RS, flags=re.S)
+        assert crate and crate.group(1) == body, name
+
+
+def test_wrapper_implements_the_reference_traits():
+    """rust/azb200 restates `trait Game` (src/game.rs:10-28) and `trait NNet` (src/nnet.rs:35-45) and implements them for
+    ConnectFourGame / B200Net: every method of the two traits appears in the matching `impl ... for ...` block with the
+    trait's own signature (text compare, whitespace-insensitive)."""
+    src = open(os.path.join(ROOT, "rust", "azb200", "src", "lib.rs")).read()
+
+    def block(header):
+        i = src.index(header)
+        depth, j = 0, src.index("{", i)
+        for k in range(j, len(src)):
+            depth += src[k] == "{"
+            depth -= src[k] == "}"
+            if depth == 0:
+                return src[j + 1:k]
+        raise AssertionError(header)
+
+    def sigs(text):
+        return {re.sub(r"\s+", " ", m).strip() for m in re.findall(r"fn [a-z_]+(?:<[^>]*>)?\([^)]*\)(?: -> [^;{]+)?", text)}
+
+    for trait, impl in (("pub trait Game:", "impl Game for ConnectFourGame"), ("pub trait NNet", "impl NNet for B200Net")):
+        want, have = sigs(block(trait)), sigs(block(impl))
+        assert want and want == have, (trait, sorted(want ^ have))
+    game = sigs(block("pub trait Game:"))
+    assert len(game) == 9 and "fn get_next_state(&self, player: i8, action: u8) -> (Self, i8)" in game
+    # the closure API of src/arena.rs:7-11,62-67
+    assert re.search(r"pub fn play_game<G: Game>\(player_actions: &\[&dyn Fn\(&G\) -> u8\], board: &Option<G>, verbose: bool\) -> i8", src)
+    assert re.search(r"pub fn play_games<G: Game>\(num: usize, player_actions: Vec<&dyn Fn\(&G\) -> u8>, board: Option<G>, verbose: bool\)", src)
