@@ -81,10 +81,11 @@ uint32_t pow2_ceil(uint64_t x) {
 
 int validate(const azb_config* cfg) {
   if (!cfg) return fail(AZB_ERR_INVALID, "config is NULL");
-  if (cfg->num_sim_threads != 1)
-    return fail(AZB_ERR_UNSUPPORTED,
-                "num_sim_threads must be 1 (deterministic mode: one simulation in flight per tree)");
+  if (cfg->num_sim_threads < 1 || cfg->num_sim_threads > static_cast<uint64_t>(kMaxWave))
+    return fail(AZB_ERR_UNSUPPORTED, "num_sim_threads must be 1 (deterministic mode) .. 8 (waves of K simulations per tree)");
   if (cfg->num_sims == 0 || cfg->num_sims > 60000) return fail(AZB_ERR_INVALID, "num_sims out of range");
+  if (cfg->num_sims % cfg->num_sim_threads != 0)
+    return fail(AZB_ERR_INVALID, "num_sims must be a multiple of num_sim_threads (async_mcts.rs:192 assert)");
   if (cfg->evaluator < AZB_EVAL_UNIFORM || cfg->evaluator > AZB_EVAL_NNET)
     return fail(AZB_ERR_INVALID, "evaluator must be AZB_EVAL_UNIFORM, AZB_EVAL_HASH or AZB_EVAL_NNET");
   if (cfg->mcts_reserve_size < 16) return fail(AZB_ERR_INVALID, "mcts_reserve_size too small");
@@ -108,6 +109,7 @@ SearchParams make_params(const azb_config& c, uint64_t searches_per_tree) {
   p.cpuct_f = static_cast<float>(c.cpuct);
   p.quirks = c.quirks;
   p.temp_threshold = static_cast<uint32_t>(std::min<uint64_t>(c.temp_threshold, 0x7FFFFFFF));
+  p.num_threads = static_cast<uint32_t>(c.num_sim_threads);
   p.seed = c.seed;
   return p;
 }
@@ -621,11 +623,13 @@ struct RoundEngine {
     AZB_CUDA(cudaMemsetAsync(cb.keys.p, 0, 2 * n * 8));  // a new call: the networks may have changed
     return AZB_OK;
   }
-  int alloc(uint32_t slots) {
+  uint32_t leaf_cap = 0;  // rows of a model's leaf batch per round: slots * num_sim_threads
+  int alloc(uint32_t slots, uint32_t leaves_per_slot = 1) {
     n_slots = slots;
+    leaf_cap = slots * std::max(1u, leaves_per_slot);
     // leaf de-duplication table (rounds.cuh LeafBufs): 4 entries per slot and model; AZB200_LEAF_DEDUP=0 turns it off
     static const bool dedup = !(std::getenv("AZB200_LEAF_DEDUP") && std::atoi(std::getenv("AZB200_LEAF_DEDUP")) == 0);
-    dedup_mask = dedup ? pow2_ceil(static_cast<uint64_t>(slots) * 4u) - 1u : 0u;
+    dedup_mask = dedup ? pow2_ceil(static_cast<uint64_t>(leaf_cap) * 4u) - 1u : 0u;
     if (dedup) {
       AZB_CUDA(dedup_keys.ensure(4 * (static_cast<size_t>(dedup_mask) + 1) * 8));  // 2 round parities x 2 models
       AZB_CUDA(dedup_idx.ensure(4 * (static_cast<size_t>(dedup_mask) + 1) * 4));
@@ -634,10 +638,10 @@ struct RoundEngine {
     AZB_CUDA(recs.ensure(static_cast<size_t>(slots) * sizeof(GameRec)));
     AZB_CUDA(active.ensure(static_cast<size_t>(slots) * 4));
     AZB_CUDA(ctl_words.ensure(64));
-    AZB_CUDA(leaf_state.ensure(static_cast<size_t>(slots) * 2 * 16));
+    AZB_CUDA(leaf_state.ensure(static_cast<size_t>(leaf_cap) * 2 * 16));
     AZB_CUDA(leaf_count.ensure(8));
-    AZB_CUDA(leaf_pi.ensure(static_cast<size_t>(slots) * 2 * 32));
-    AZB_CUDA(leaf_v.ensure(static_cast<size_t>(slots) * 2 * 4));
+    AZB_CUDA(leaf_pi.ensure(static_cast<size_t>(leaf_cap) * 2 * 32));
+    AZB_CUDA(leaf_v.ensure(static_cast<size_t>(leaf_cap) * 2 * 4));
     AZB_CUDA(cudaMemset(recs.p, 0, static_cast<size_t>(slots) * sizeof(GameRec)));  // phase = Empty
     AZB_CUDA(cudaMemset(ctl_words.p, 0, 64));
     AZB_CUDA(cudaMemset(leaf_count.p, 0, 8));
@@ -723,8 +727,8 @@ struct RoundEngine {
         for (int k = 0; k < 2; ++k) {
           if (!nets[k] || rp.ev_kind[k] < AZB_EVAL_NNET) continue;
           if (k == 1 && rp.mode != kModeArena) continue;
-          int rc = nnet_forward(nets[k], lf.state + static_cast<size_t>(k) * rp.n_slots, lf.count + k, rp.n_slots,
-                                lf.pi + static_cast<size_t>(k) * rp.n_slots * 8, lf.v + static_cast<size_t>(k) * rp.n_slots, stream);
+          int rc = nnet_forward(nets[k], lf.state + static_cast<size_t>(k) * rp.leaf_cap, lf.count + k, rp.leaf_cap,
+                                lf.pi + static_cast<size_t>(k) * rp.leaf_cap * 8, lf.v + static_cast<size_t>(k) * rp.leaf_cap, stream);
           if (rc) return rc;
         }
       }
@@ -1228,7 +1232,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     c->nn_positions = 0;
     c->nn_cache_hits = 0;
   } else {
-    rc = c->engine.alloc(static_cast<uint32_t>(n_trees));
+    rc = c->engine.alloc(static_cast<uint32_t>(n_trees), p.num_threads);
     if (rc) return rc;
     RoundParams rp{};
     rp.p = p;
@@ -1237,6 +1241,7 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rp.plies_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? 0u : (c->cfg.plies_per_launch ? c->cfg.plies_per_launch : 2u);
     rp.sims_per_launch = c->cfg.evaluator >= AZB_EVAL_NNET ? round_sim_budget() : 0u;
     rp.n_slots = static_cast<uint32_t>(n_trees);
+    rp.leaf_cap = c->engine.leaf_cap;
     rp.n_games = static_cast<uint32_t>(G);
     rp.first_game_id = first_game_id;
     azb_nnet* nets[2] = {c->net, nullptr};
@@ -1804,7 +1809,7 @@ int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a,
   rc = gs.alloc(G, false);
   if (rc) return rc;
   RoundEngine eng;
-  rc = eng.alloc(static_cast<uint32_t>(n_slots));
+  rc = eng.alloc(static_cast<uint32_t>(n_slots), p.num_threads);
   if (rc) return rc;
   RoundParams rp{};
   rp.p = p;
@@ -1815,6 +1820,7 @@ int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a,
   rp.plies_per_launch = any_net ? 0u : (cfg->plies_per_launch ? cfg->plies_per_launch : 2u);
   rp.sims_per_launch = any_net ? round_sim_budget(true) : 0u;
   rp.n_slots = static_cast<uint32_t>(n_slots);
+  rp.leaf_cap = eng.leaf_cap;
   rp.n_games = static_cast<uint32_t>(G);
   rp.half = static_cast<uint32_t>(half);
   rp.k_open = k_open;

@@ -45,7 +45,7 @@ struct SearchParams {
   float cpuct_f;
   uint32_t quirks;
   uint32_t temp_threshold;
-  uint32_t pad;
+  uint32_t num_threads;  // num_sim_threads (coach.rs:51): 1 = deterministic mode; K > 1 = waves of K simulations (wave_*)
   uint64_t seed;
 };
 
@@ -375,7 +375,7 @@ __device__ __forceinline__ void backup_commit(const WarpTree& t, uint32_t slot, 
 // ---- search_iteration (async_mcts.rs:219-371) --------------------------------
 // A simulation either completes, or — when the leaf must be evaluated by the batched network
 // (evaluator kind AZB_EVAL_NNET) — suspends after storing what is needed to finish it later.
-enum : uint32_t { kPendNone = 0, kPendRoot = 1, kPendExpand = 2 };
+enum : uint32_t { kPendNone = 0, kPendRoot = 1, kPendExpand = 2, kPendWave = 3 };
 struct Pending {
   uint32_t kind;      // kPend*
   uint32_t my_slot;   // expansion: the placeholder being upgraded
@@ -749,10 +749,248 @@ __device__ __forceinline__ bool one_sim(WarpTree& t, const SearchParams& p, int 
   return one_sim_impl<false>(t, p, ev_kind, root, root_slot, root_meta, lane, pd, leaf);
 }
 
+// ---- tree-parallel search with virtual loss: num_sim_threads = K > 1 (async_mcts.rs:191-217, node.rs:77-92,359-365) ----
+// The reference runs K OS threads per tree whose interleaving is the scheduler's, so its result is not reproducible.
+// Here (and in the CPU oracle that the tests compare with, bit for bit) the K threads run in ONE fixed interleaving, wave by wave: the K walks of a
+// wave one after the other — each sees the virtual losses (visit() = N + 1, VL + 1 on every node of a path) and the locks
+// of the earlier ones —, then the wave's evaluations (inline, or K leaves per tree in one network batch: a K-th of the
+// rounds), then the K backups in thread order.  Nothing is written to the tree's counters during the walks: the
+// virtual counter of a node is its counter at rest + (in-flight walks through it) * 0x10001, looked up in the wave's
+// path table in shared memory.  Repairs that only matter here: F17 every child Locked (node.rs:367 unwraps None) -> the
+// walk ends at the node with v = 0; F18 a node whose evaluation is pending in this wave reached through a link / a
+// duplicate (the reference reads its missing policy, node.rs:354) -> the walk ends there and shares that evaluation.
+constexpr int kMaxWave = 8;
+enum : uint32_t { kWvEval = 1u, kWvShare = 2u, kWvRoot = 4u };
+struct __align__(16) WaveSim {  // 256 bytes; kMaxWave of them fit the warp's path area in shared memory
+  uint32_t plen;    // path[0 .. plen) = the nodes walked through (resolved owner slots), path[plen] = where the walk stopped
+  uint32_t flags;   // kWvEval: owns a pending evaluation of path[plen]; kWvShare: shares simulation `share`'s; kWvRoot: F1
+  uint32_t share;
+  float v;          // the value backed up at path[plen]
+  uint32_t my_slot, new_meta, vm, leaf_ref;  // the pending expansion; leaf_ref: its row in the network batch (rounds)
+  uint64_t key;
+  uint64_t cur, opp;  // the position to evaluate
+  uint32_t levels, pad;
+  uint32_t path[kPathCap];
+};
+static_assert(sizeof(WaveSim) == 256, "WaveSim layout");
+static_assert(sizeof(WaveSim) * kMaxWave <= sizeof(PathEnt) * kPathCap, "the wave table lives in the path area");
+
+// One walk of a wave (simulation `tix`).  Inline evaluators finish the expansion at once
+// (the node still counts as Locked until the wave ends); AZB_EVAL_NNET leaves the new node without policy.
+__device__ __forceinline__ void wave_select(WarpTree& t, const SearchParams& p, int ev_kind, BB root, uint32_t root_slot,
+                                            uint32_t root_meta, WaveSim* ws, uint32_t tix, int lane) {
+  const float neg_inf = __uint_as_float(0xFF800000u);
+  const uint32_t la = lane & 7u;
+  const bool grp0 = lane < 8;
+  uint32_t cur_slot = root_slot, cur_meta = root_meta, par_n = ld_n(t, root_slot);
+  uint32_t depth = 0, plen = 0, levels = 0, flags = 0, share = 0;
+  uint32_t my_slot = 0, new_meta = 0, vm = 0;
+  uint64_t key = 0;
+  float v = 0.0f;
+  BB pos = root;
+  // in-flight walks k < tix whose node at path index `idx` is `slot`
+  auto inflight_at = [&](uint32_t idx, uint32_t slot) -> uint32_t {
+    uint32_t n = 0;
+    for (uint32_t k = 0; k < tix; ++k) n += (ws[k].plen >= idx && ws[k].path[idx] == slot) ? 1u : 0u;
+    return n;
+  };
+  for (;;) {
+    levels++;
+    if (levels > 4u * kPathCap) { t.error = kErrInternal; break; }
+    if (depth > p.max_depth) break;                     // :241-244 (+F6): v = eval_heuristic() == 0
+    if (cur_meta >= kMaxBlockId) {                      // :246-249 (+F6)
+      v = terminal_e(cur_meta & 3u);
+      t.stat += static_cast<uint32_t>(lane == kStatTerminal);
+      break;
+    }
+    {  // F18 / F1: a node without a usable policy
+      uint32_t owner = 0xFFFFFFFFu;
+      for (uint32_t k = 0; k < tix; ++k)
+        if ((ws[k].flags & kWvEval) && ws[k].path[ws[k].plen] == cur_slot) owner = k;
+      if (owner != 0xFFFFFFFFu) { flags = kWvShare; share = owner; break; }
+      if (!(block_flags(t, cur_meta) & kFlagHasPolicy)) {
+        flags = kWvEval | kWvRoot;
+        my_slot = cur_slot;
+        new_meta = cur_meta;
+        key = state_key(pos);
+        break;
+      }
+    }
+    // ---- best_child with the virtual counters (node.rs:343-370) ----
+    const uint32_t blk = cur_meta;
+    const uint4* bp = t.blocks + static_cast<size_t>(blk) * 8u;
+    const uint4 w = bp[la];
+    uint32_t nn = reinterpret_cast<const uint16_t*>(bp + 7)[la];
+    bool ok = grp0 && la < 7u && w.w != kMetaInvalid;
+    uint32_t wv = w.x, rslot = blk * 8u + la;
+    if (ok && w.w == kMetaLink) {  // resolve(): statistics come from the owner (node.rs:179-201)
+      rslot = w.x;
+      wv = ld_w(t, rslot);
+      nn = ld_n(t, rslot);
+    }
+    const uint32_t vl_c = ok ? inflight_at(plen + 1u, rslot) : 0u;
+    uint32_t locked = 0u;  // the RAW child slot is the pending expansion of an earlier walk (NodeState::Locked)
+    for (uint32_t k = 0; k < tix; ++k)
+      locked |= ((ws[k].flags & kWvEval) && !(ws[k].flags & kWvRoot) && ws[k].my_slot == blk * 8u + la) ? 1u : 0u;
+    const uint32_t vl_x = inflight_at(plen, cur_slot);
+    const float sq = AZB_FSQRT(AZB_FADD(static_cast<float>((par_n + vl_x + 1u) & 0xFFFFu), kEps));  // N after this visit()
+    const uint64_t vc = counter_pack(wv, nn) + static_cast<uint64_t>(vl_c) * kVisit;
+    float u = ok ? puct_u(vc, __uint_as_float(w.z), sq, p.cpuct_f) : neg_inf;
+    float mx = redux_max_f32(u);
+    uint32_t ball = __ballot_sync(kFull, ok && u == mx);
+    if (ball == 0u) { t.error = kErrInternal; break; }
+    uint32_t a = bfind_u32(ball);
+    if (__shfl_sync(kFull, locked, a)) {  // :253-257: retry without the Locked children
+      ok = ok && !locked;
+      u = ok ? u : neg_inf;
+      mx = redux_max_f32(u);
+      ball = __ballot_sync(kFull, ok && u == mx);
+      if (ball == 0u) break;  // F17: v = 0 at this node
+      a = bfind_u32(ball);
+    }
+    const uint32_t ch_meta = __shfl_sync(kFull, w.w, a);
+    if (lane == 0) ws[tix].path[plen] = cur_slot;  // node_path.push (:270 / F3)
+    plen++;
+    pos = play_canonical(pos, static_cast<int>(a));
+    if (ch_meta != kMetaPlaceholder) {  // Exists: descend (:269-274 + F2); a finished game is noticed at the loop's top
+      if (ch_meta == kMetaLink) {
+        cur_slot = __shfl_sync(kFull, w.x, a);
+        cur_meta = __shfl_sync(kFull, w.y, a);
+      } else {
+        cur_slot = blk * 8u + a;
+        cur_meta = ch_meta;
+      }
+      par_n = __shfl_sync(kFull, nn, a);
+      depth++;
+      continue;
+    }
+    // ---- the chosen child is a placeholder: lock + upgrade (:260-299, node.rs:272-326) ----
+    my_slot = blk * 8u + a;
+    key = state_key(pos);
+    const uint4 e_home = tt_load_home(t, p.bucket_mask, key, lane);
+    const int code = game_ended_code_warp(t, pos, lane);
+    vm = valid_mask(pos.cur | pos.opp);
+    uint32_t o_slot, o_meta, ins;
+    if (tt_find(t, p.bucket_mask, key, e_home, lane, o_slot, o_meta, ins)) {  // Some(false): a link; go on from the owner
+      if (lane == static_cast<int>(a)) t.blocks[my_slot] = make_uint4(o_slot, o_meta, w.z, kMetaLink);
+      t.stat += static_cast<uint32_t>(lane == kStatDupLinks);
+      __syncwarp();
+      cur_slot = o_slot;
+      cur_meta = o_meta;
+      par_n = ld_n(t, o_slot);
+      continue;  // (depth not incremented, async_mcts.rs:293-299)
+    }
+    if (ins == 0xFFFFFFFFu) { t.error = kErrTable; break; }
+    cur_slot = my_slot;
+    if (code) {  // repair F5: a finished game, the net is skipped
+      new_meta = kMetaTerminal | static_cast<uint32_t>(code);
+      v = terminal_e(static_cast<uint32_t>(code));
+      if (lane == static_cast<int>(a)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+      tt_insert(t, ins, key, my_slot, new_meta, lane);
+      t.n_owners++;
+      t.stat += static_cast<uint32_t>(lane == kStatTerminal || lane == kStatExpansions);
+      __syncwarp();
+      break;
+    }
+    if (t.n_blocks >= p.cap_blocks) { t.error = kErrBlocks; break; }
+    new_meta = t.n_blocks++;
+    flags = kWvEval;
+    float pi = 0.0f, val = 0.0f;
+    uint32_t bflags = 0u;
+    if (ev_kind < AZB_EVAL_NNET) {  // inline evaluators know the policy now; nobody reads it before the wave ends
+      evaluate_masked(t, ev_kind, pos, vm, lane, pi, val);
+      v = -val;
+      bflags = kFlagHasPolicy;
+      t.stat += static_cast<uint32_t>(lane == kStatEvals);
+    }
+    write_child_block(t, new_meta, vm, pi, bflags, lane);
+    if (lane == static_cast<int>(a)) reinterpret_cast<uint32_t*>(t.blocks + my_slot)[3] = new_meta;
+    tt_insert(t, ins, key, my_slot, new_meta, lane);
+    t.n_owners++;
+    t.stat += static_cast<uint32_t>(lane == kStatExpansions);
+    __syncwarp();
+    break;
+  }
+  if (lane == 0) {
+    WaveSim& me = ws[tix];
+    me.path[plen] = cur_slot;
+    me.plen = plen;
+    me.flags = flags;
+    me.share = share;
+    me.v = v;
+    me.my_slot = my_slot;
+    me.new_meta = new_meta;
+    me.vm = vm;
+    me.leaf_ref = 0u;
+    me.key = key;
+    me.cur = pos.cur;
+    me.opp = pos.opp;
+    me.levels = levels;
+  }
+  __syncwarp();
+}
+
+// The network's answer (or the inline evaluator's, for an F1 root) for the pending evaluation of walk `k`: mask +
+// normalise, set_policy, unlock (async_mcts.rs:317-353).  Lane a holds the raw pi[a].
+__device__ __forceinline__ void wave_set_policy(WarpTree& t, const SearchParams& p, WaveSim* ws, uint32_t k, float pi, float val,
+                                                int lane) {
+  const uint32_t blk = ws[k].new_meta;
+  uint4* bp = t.blocks + static_cast<size_t>(blk) * 8u;
+  const uint32_t m = lane < 7 ? bp[lane].w : kMetaInvalid;
+  const uint32_t vm = __ballot_sync(kFull, m != kMetaInvalid) & 0x7Fu;
+  pi = mask_normalise(pi, vm, lane);
+  if (lane < 7) reinterpret_cast<float*>(bp + lane)[2] = pi;
+  if (lane == 7) reinterpret_cast<uint32_t*>(bp + 7)[3] |= kFlagHasPolicy << 16;
+  if (lane == 0) ws[k].v = -val;
+  t.stat += static_cast<uint32_t>(lane == kStatEvals);
+  __syncwarp();
+}
+
+// The K backups of a wave, in thread order (:361-370): visit() + unvisit() folded per path node, as in backup_path.
+__device__ __forceinline__ void wave_backup(WarpTree& t, const SearchParams& p, WaveSim* ws, uint32_t K, int lane) {
+  const bool alternate = !(p.quirks & AZB_Q2_BACKUP_NO_ALTERNATE);
+  __syncwarp();
+  for (uint32_t k = 0; k < K; ++k) {
+    const uint32_t plen = ws[k].plen;
+    const float v = (ws[k].flags & kWvShare) ? ws[ws[k].share].v : ws[k].v;
+    for (uint32_t base = 0; base <= plen; base += 32u) {
+      const uint32_t l = base + lane;
+      if (l <= plen) {
+        const bool neg = alternate && ((plen - l) & 1u);
+        const BackupRegs r = backup_prepare(t, ws[k].path[l], __fmul_rn(neg ? -1.0f : 1.0f, v), p.quirks);
+        backup_commit(t, ws[k].path[l], r);
+      }
+    }
+    t.stat += static_cast<uint32_t>(lane == kStatSims) + (lane == kStatLevels ? ws[k].levels : 0u);
+    __syncwarp();  // the next walk's path may share nodes with this one
+  }
+  t.pred_len = 0u;
+}
+
+// One wave with an inline evaluator, start to end.
+__device__ __forceinline__ void wave_inline(WarpTree& t, const SearchParams& p, int ev_kind, BB root, uint32_t root_slot,
+                                            uint32_t root_meta, uint32_t K, int lane) {
+  WaveSim* ws = reinterpret_cast<WaveSim*>(t.path);
+  for (uint32_t k = 0; k < K && !t.error; ++k) wave_select(t, p, ev_kind, root, root_slot, root_meta, ws, k, lane);
+  if (t.error) return;
+  for (uint32_t k = 0; k < K; ++k)
+    if ((ws[k].flags & (kWvEval | kWvRoot)) == (kWvEval | kWvRoot)) {  // F1: the root's own evaluation
+      float pi, val;
+      evaluate_inline(ev_kind, BB{ws[k].cur, ws[k].opp}, lane, pi, val);
+      wave_set_policy(t, p, ws, k, pi, val, lane);
+    }
+  wave_backup(t, p, ws, K, lane);
+}
+
 // search (:191-217) with num_threads = 1 and a fused evaluator: nsims simulations from `root`.
 __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
                                          uint32_t root_slot, uint32_t root_meta, uint32_t nsims,
                                          int lane) {
+  if (p.num_threads > 1u) {  // tree-parallel mode: waves of K simulations (num_sims % K == 0 is checked at setup, :192)
+    for (uint32_t sim = 0; sim < nsims && !t.error; sim += p.num_threads)
+      wave_inline(t, p, ev_kind, root, root_slot, root_meta, p.num_threads, lane);
+    return;
+  }
   uint32_t sim = 0;
   // Repair F1: an existing, non-terminal node that was never evaluated (a stand-alone root at
   // its first visit) is evaluated when first reached; this consumes one simulation.  Only a

@@ -119,6 +119,7 @@ __device__ __forceinline__ void cache_insert(const LeafBufs& leaf, uint32_t side
   if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(leaf.ckeys + at) = skey | kCacheReady;
 }
 constexpr uint32_t kLeafIndirect = 0x80000000u;  // GameRec.leaf_idx: low bits index didx[] instead of the batch
+constexpr uint32_t kLeafDone = 0x7FFFFFFFu;      // WaveSim.leaf_ref: answered from the cache, nothing to fetch
 
 struct RoundParams {
   SearchParams p;
@@ -128,6 +129,7 @@ struct RoundParams {
   uint32_t sims_per_launch;  // network rounds: a slot that needs no evaluation (endgame: terminal hits
                              // only) yields after this many simulations, so a round never waits on it
   uint32_t n_slots, n_games;
+  uint32_t leaf_cap;  // rows of a model's leaf batch: n_slots * num_sim_threads (a wave suspends with up to K leaves)
   uint32_t half;    // arena: games [0, half) seat A first, [half, 2*half) seat B first (arena.rs:74-83)
   uint32_t k_open;  // arena: random opening plies
   uint32_t shared;  // arena: 1 = the reference's layout (coach.rs:333-354): ONE tree pair for the whole match, games
@@ -241,6 +243,55 @@ __device__ __forceinline__ void store_tree_vars(const WarpTree& t, TreeVars& tv,
   if (lane < 8) tv.stat[lane] = t.stat;
 }
 
+// ---- one leaf's way through the batched evaluator ---------------------------------------------------------------
+// leaf_submit: claim the position for this round (or find the slot that already has), take a dense batch row; returns
+// the reference the slot keeps until it resumes (a row index, or kLeafIndirect | de-duplication entry).  Lane 0 works.
+__device__ __forceinline__ uint32_t leaf_submit(const LeafBufs& leaf, uint32_t side, uint32_t leaf_cap, BB leaf_pos, int lane) {
+  uint32_t ref = 0;
+  if (lane == 0) {
+    bool owner = true;
+    uint32_t at = 0;
+    if (leaf.dmask) {  // claim the position for this round, or find the slot that already has
+      const uint64_t skey = state_key(leaf_pos);
+      const unsigned long long key = skey | (static_cast<unsigned long long>(leaf.stamp) << 49);
+      const uint32_t base = (leaf.dpar * 2u + static_cast<uint32_t>(side)) * (leaf.dmask + 1u);
+      uint32_t h = static_cast<uint32_t>((skey * 0x9E3779B97F4A7C15ull) >> 40) & leaf.dmask;
+      for (;;) {
+        at = base + h;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(leaf.dkeys + at);
+        if ((cur >> 49) != leaf.stamp) {  // empty or left over from an earlier round
+          const unsigned long long old = atomicCAS(leaf.dkeys + at, cur, key);
+          if (old == cur) break;          // claimed
+          cur = old;
+          if ((cur >> 49) != leaf.stamp) continue;
+        }
+        if (cur == key) { owner = false; break; }
+        h = (h + 1u) & leaf.dmask;  // (the table has 4 entries per leaf the round can hold: it never fills)
+      }
+    }
+    if (owner) {
+      ref = atomicAdd(leaf.count + side, 1u);
+      leaf.state[static_cast<size_t>(side) * leaf_cap + ref] =
+          make_uint4(static_cast<uint32_t>(leaf_pos.cur), static_cast<uint32_t>(leaf_pos.cur >> 32),
+                     static_cast<uint32_t>(leaf_pos.opp), static_cast<uint32_t>(leaf_pos.opp >> 32));
+      if (leaf.dmask) leaf.didx[at] = ref;  // read by the duplicates in the next round's kernel
+    } else {
+      ref = kLeafIndirect | at;
+    }
+  }
+  return __shfl_sync(kFull, ref, 0);
+}
+// leaf_fetch: the network's answer for a submitted leaf (lane a: raw pi[a]); the owner of the row feeds the call's cache.
+__device__ __forceinline__ void leaf_fetch(const LeafBufs& leaf, uint32_t side, uint32_t leaf_cap, uint32_t ref, uint64_t skey,
+                                           int lane, float& pi, float& val) {
+  uint32_t li = ref;
+  if (li & kLeafIndirect) li = leaf.didx[li & ~kLeafIndirect];  // a duplicate: the row of the slot that owns the position
+  const size_t row = static_cast<size_t>(side) * leaf_cap + li;
+  pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
+  val = leaf.v[row];
+  if (leaf.cmask && !(ref & kLeafIndirect)) cache_insert(leaf, side, skey, pi, val, lane);
+}
+
 // ---- k_round ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
 k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, GameBufs g) {
@@ -296,16 +347,29 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
   load_tree_vars(t, rec->tv[side], lane);
   uint32_t err = 0;
 
-  if (phase == kPhasePending) {  // the network's answer for the suspended simulation is in
+  if (phase == kPhasePending && rec->pd.kind == kPendWave) {  // the answers for a suspended wave's leaves are in
+    WaveSim* ws = reinterpret_cast<WaveSim*>(t.path);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(rec->path);
+      uint4* dst = reinterpret_cast<uint4*>(t.path);
+      for (uint32_t i = lane; i < p.num_threads * (sizeof(WaveSim) / 16u); i += 32u) dst[i] = src[i];
+    }
+    __syncwarp();
+    for (uint32_t k = 0; k < p.num_threads; ++k)
+      if ((ws[k].flags & kWvEval) && ws[k].leaf_ref != kLeafDone) {
+        float pi, val;
+        leaf_fetch(leaf, side, rp.leaf_cap, ws[k].leaf_ref, ws[k].key, lane, pi, val);
+        wave_set_policy(t, p, ws, k, pi, val, lane);
+      }
+    wave_backup(t, p, ws, p.num_threads, lane);
+    sims_done += p.num_threads;
+    phase = kPhaseSearch;
+  } else if (phase == kPhasePending) {  // the network's answer for the suspended simulation is in
     Pending pd = rec->pd;
     for (uint32_t i = lane; i <= pd.plen && i < kPathCap; i += 32u) t.path[i] = rec->path[i];
     __syncwarp();
-    uint32_t li = rec->leaf_idx;
-    if (li & kLeafIndirect) li = leaf.didx[li & ~kLeafIndirect];  // a duplicate: the row of the slot that owns the position
-    const size_t row = static_cast<size_t>(side) * rp.n_slots + li;
-    const float pi = lane < 7 ? leaf.pi[row * 8u + lane] : 0.0f;
-    const float val = leaf.v[row];
-    if (leaf.cmask && !(rec->leaf_idx & kLeafIndirect)) cache_insert(leaf, side, pd.key, pi, val, lane);
+    float pi, val;
+    leaf_fetch(leaf, side, rp.leaf_cap, rec->leaf_idx, pd.key, lane, pi, val);
     if (pd.kind == kPendRoot) finish_root_eval(t, p, root_slot, root_meta, pi, val, lane);
     else finish_expand(t, p, pd, pi, val, lane, /*normalised=*/false, /*predict=*/true);
     sims_done++;
@@ -358,6 +422,61 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     bool suspended = false, yielded = false;
     Pending pd;
     BB leaf_pos;
+    if (p.num_threads > 1u) {
+      // ---- tree-parallel mode: waves of K walks (mcts.cuh wave_*); a wave suspends with up to K leaves ----
+      WaveSim* ws = reinterpret_cast<WaveSim*>(t.path);
+      bool waiting = false;
+      while (sims_done < p.num_sims && !t.error) {
+        if (sims_left == 0u) { yielded = true; break; }
+        sims_left = sims_left > p.num_threads ? sims_left - p.num_threads : 0u;
+        for (uint32_t k = 0; k < p.num_threads && !t.error; ++k) wave_select(t, p, ev, board, root_slot, root_meta, ws, k, lane);
+        if (t.error) break;
+        uint32_t n_wait = 0;
+        for (uint32_t k = 0; k < p.num_threads; ++k) {
+          if (!(ws[k].flags & kWvEval)) continue;
+          const bool root_eval = (ws[k].flags & kWvRoot) != 0u;
+          const BB lp{ws[k].cur, ws[k].opp};
+          if (ev < AZB_EVAL_NNET) {
+            if (root_eval) {  // F1 with an inline evaluator (new nodes were evaluated in the walk)
+              float pi, val;
+              evaluate_inline(ev, lp, lane, pi, val);
+              wave_set_policy(t, p, ws, k, pi, val, lane);
+            }
+            continue;
+          }
+          uint32_t ce = 0xFFFFFFFFu;
+          if (leaf.cmask) ce = cache_find(leaf, side, ws[k].key, lane);
+          if (ce != 0xFFFFFFFFu) {  // a position this model has already evaluated in this call
+            const float pi = lane < 7 ? __ldcg(leaf.cvals + static_cast<size_t>(ce) * 8u + lane) : 0.0f;
+            const float val = __ldcg(leaf.cvals + static_cast<size_t>(ce) * 8u + 7u);
+            wave_set_policy(t, p, ws, k, pi, val, lane);
+            if (lane == 0) {
+              atomicAdd(leaf.cache_hits, 1ull);
+              ws[k].leaf_ref = kLeafDone;
+            }
+          } else {
+            const uint32_t ref = leaf_submit(leaf, side, rp.leaf_cap, lp, lane);
+            if (lane == 0) ws[k].leaf_ref = ref;
+            n_wait++;
+          }
+          __syncwarp();
+        }
+        if (n_wait) { waiting = true; break; }
+        wave_backup(t, p, ws, p.num_threads, lane);
+        sims_done += p.num_threads;
+      }
+      if (t.error) { err = t.error; break; }
+      if (yielded) break;
+      if (waiting) {  // the wave's state (its K walks) waits in the slot record for the network's answers
+        const uint4* src = reinterpret_cast<const uint4*>(t.path);
+        uint4* dst = reinterpret_cast<uint4*>(rec->path);
+        for (uint32_t i = lane; i < p.num_threads * (sizeof(WaveSim) / 16u); i += 32u) dst[i] = src[i];
+        if (lane == 0) rec->pd.kind = kPendWave;
+        phase = kPhasePending;
+        break;
+      }
+      goto make_move;
+    }
   search_more:
     suspended = false;
     while (sims_done < p.num_sims && !t.error) {
@@ -396,37 +515,8 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
       }
     }
     if (suspended) {  // hand the leaf to the batched evaluator of this side's model
+      const uint32_t ref = leaf_submit(leaf, side, rp.leaf_cap, leaf_pos, lane);
       if (lane == 0) {
-        uint32_t ref = 0;
-        bool owner = true;
-        uint32_t at = 0;
-        if (leaf.dmask) {  // claim the position for this round, or find the slot that already has
-          const uint64_t skey = state_key(leaf_pos);
-          const unsigned long long key = skey | (static_cast<unsigned long long>(leaf.stamp) << 49);
-          const uint32_t base = (leaf.dpar * 2u + static_cast<uint32_t>(side)) * (leaf.dmask + 1u);
-          uint32_t h = static_cast<uint32_t>((skey * 0x9E3779B97F4A7C15ull) >> 40) & leaf.dmask;
-          for (;;) {
-            at = base + h;
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(leaf.dkeys + at);
-            if ((cur >> 49) != leaf.stamp) {  // empty or left over from an earlier round
-              const unsigned long long old = atomicCAS(leaf.dkeys + at, cur, key);
-              if (old == cur) break;          // claimed
-              cur = old;
-              if ((cur >> 49) != leaf.stamp) continue;
-            }
-            if (cur == key) { owner = false; break; }
-            h = (h + 1u) & leaf.dmask;  // (the table has 4 entries per slot: it never fills)
-          }
-        }
-        if (owner) {
-          ref = atomicAdd(leaf.count + side, 1u);
-          leaf.state[static_cast<size_t>(side) * rp.n_slots + ref] =
-              make_uint4(static_cast<uint32_t>(leaf_pos.cur), static_cast<uint32_t>(leaf_pos.cur >> 32),
-                         static_cast<uint32_t>(leaf_pos.opp), static_cast<uint32_t>(leaf_pos.opp >> 32));
-          if (leaf.dmask) leaf.didx[at] = ref;  // read by the duplicates in the next round's kernel
-        } else {
-          ref = kLeafIndirect | at;
-        }
         rec->pd = pd;
         rec->leaf_idx = ref;
       }
@@ -436,6 +526,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
       break;
     }
     // ---- the move ----
+  make_move:
     if (rp.mode == kModeArena) {
       // coach.rs:356-371: argmax of get_action_prob(s, temp = 0) — a one-hot on the most visited
       // child, ties to the highest action

@@ -108,7 +108,11 @@ typedef struct azb_config {
   uint64_t num_iters;
   uint64_t num_eps;
   uint64_t num_sims;
-  uint64_t num_sim_threads; /* must be 1: deterministic mode, one simulation in flight per tree */
+  uint64_t num_sim_threads; /* 1 = deterministic mode (one simulation in flight per tree; every bit-exact parity claim);
+                             * K = 2..8 = tree-parallel search with virtual loss (async_mcts.rs:191-217): waves of K
+                             * simulations per tree in one fixed interleaving, reproduced bit for bit by the oracle's wave
+                             * mode; with the network evaluator a wave sends up to K leaves per tree into a round's batch.
+                             * num_sims must be a multiple of it (async_mcts.rs:192) */
   uint64_t max_depth;
   int32_t cpuct;
   /* engine additions */

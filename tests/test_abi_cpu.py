@@ -51,8 +51,11 @@ def test_host_only_calls(azb):
 
 def test_invalid_config_rejected(azb):
     with pytest.raises(azb.AzbError) as e:
-        azb.AsyncMcts(1, num_sim_threads=4)
+        azb.AsyncMcts(1, num_sims=32, num_sim_threads=16)  # waves hold at most 8 walks
     assert e.value.code == azb.ERR_UNSUPPORTED
+    with pytest.raises(azb.AzbError) as e:
+        azb.AsyncMcts(1, num_sims=25, num_sim_threads=4)   # async_mcts.rs:192: num_sims % num_threads == 0
+    assert e.value.code == azb.ERR_INVALID
     with pytest.raises(azb.AzbError) as e:
         azb.Coach(num_sims=0)
     assert e.value.code == azb.ERR_INVALID
