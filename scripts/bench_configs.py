@@ -18,15 +18,16 @@ if "micro" in which:
     t0 = time.perf_counter(); m.get_action_prob(root, 1.0); dt = time.perf_counter() - t0
     print(json.dumps({"workload": "micro: 800 sims from the empty board x 4096 trees (second search on the same trees)",
                       "wall_ms": 1e3 * dt, "sims_per_sec": n * sims / dt}))
+K = int(os.environ.get("AZB200_BENCH_THREADS", "1"))  # num_sim_threads: waves of K simulations per tree
 if "config3" in which:
     net = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
-    coach = azb.Coach(nnet=net, num_sims=400, seed=0xA1FA0, evaluator=azb.EVAL_NNET)
+    coach = azb.Coach(nnet=net, num_sims=400, seed=0xA1FA0, evaluator=azb.EVAL_NNET, num_sim_threads=K)
     st = coach.self_play(8192, 0)
     s = st["device_ms"] * 1e-3
-    print(json.dumps({"workload": "config3: 8192 games x 400 sims, ResNet-6x128 bf16 leaf evaluator", "device_s": s,
+    print(json.dumps({"workload": "config3: 8192 games x 400 sims, ResNet-6x128 bf16 leaf evaluator", "num_sim_threads": K, "device_s": s,
                       "sims_per_sec": st["sims"] / s, "games_per_sec": st["games"] / s, "leaf_evals_per_sec": st["evals"] / s,
                       "nn_positions": st["nn_positions"], "nn_cache_hits": st["nn_cache_hits"],
-                      "nn_tflops_whole_run": st["nn_positions"] * FLOP(6) / s / 1e12, "rounds": st["launches"] // 3, "plies": st["plies"]}))
+                      "nn_tflops_whole_run": st["nn_positions"] * FLOP(6) / s / 1e12, "kernel_launches": st["launches"], "plies": st["plies"]}))
 if "config4" in which:
     a = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
     b = azb.NNet(seed=8, blocks=6, precision=azb.NNET_BF16_TC)

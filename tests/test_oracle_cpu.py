@@ -100,7 +100,8 @@ def test_oracle_episode_fixture(oracle):
     fx = json.load(open(os.path.join(HERE, "golden", "oracle_episodes.json")))
     for e in fx["episodes"]:
         ep = oracle.execute_episode(num_sims=e["num_sims"], quirks=e["quirks"], seed=e["seed"],
-                                    episode_id=e["episode_id"], evaluator=e["evaluator"])
+                                    episode_id=e["episode_id"], evaluator=e["evaluator"],
+                                    num_sim_threads=e.get("num_sim_threads", 1))
         n = ep["plies"]
         assert ep["actions"][:n].tolist() == e["actions"]
         assert ep["counts"][:n].tolist() == e["counts"]
@@ -143,3 +144,24 @@ def test_cpu_network_matches_torch_restatement(azb, oracle):
     # the timing leg built on it runs and counts what it did
     r = oracle.bench_selfplay_net(params, blocks, 2, 2, num_sims=6, max_plies=2, seed=3)
     assert r["sims"] == 2 * 2 * 6 and r["plies"] == 4 and r["evals"] > 0
+
+
+def test_wave_mode_invariants(oracle):
+    """Tree-parallel search (num_sim_threads = K, oracle/mcts.hpp search_wave): every wave leaves no virtual loss behind
+    (VL field 0, N = visits), the root is visited once per simulation, K = 1 is the deterministic search itself, and
+    num_sims % K != 0 is refused (async_mcts.rs:192)."""
+    root = oracle.init_board(1)
+    for k in (1, 2, 4, 8):
+        m = oracle.Mcts(num_sims=64, quirks=0, evaluator=oracle.EVAL_HASH, num_sim_threads=k)
+        counts, _ = m.get_action_prob(root, 1.0)
+        c = m.counter_of(root)
+        assert c & 0xFFFF == 0 and (c >> 16) & 0xFFFF == 64          # VL back to 0, N(root) = 64 visits
+        keys, counters, e, p, hp = m.dump()
+        assert (counters & np.uint64(0xFFFF) == 0).all()
+        assert int(counts.sum()) <= 64 - 1
+        if k == 1:
+            ref = oracle.Mcts(num_sims=64, quirks=0, evaluator=oracle.EVAL_HASH)
+            rc, _ = ref.get_action_prob(root, 1.0)
+            assert counts.tolist() == rc.tolist()
+    with pytest.raises(RuntimeError):
+        oracle.Mcts(num_sims=10, quirks=0, evaluator=0, num_sim_threads=4).get_action_prob(root, 1.0)

@@ -74,7 +74,8 @@ def test_sampled_800_sims(azb, oracle, schedule):
 def test_oracle_fixture_on_device(azb, schedule):
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_episodes.json")))
     for e in fx["episodes"]:
-        coach = azb.Coach(num_sims=e["num_sims"], quirks=e["quirks"], seed=e["seed"], evaluator=e["evaluator"], schedule=schedule)
+        coach = azb.Coach(num_sims=e["num_sims"], quirks=e["quirks"], seed=e["seed"], evaluator=e["evaluator"], schedule=schedule,
+                          num_sim_threads=e.get("num_sim_threads", 1))
         st = coach.self_play(1, e["episode_id"])
         tr = coach.traces()
         n = int(tr["plies"][0])

@@ -92,3 +92,28 @@ def test_adam_step_and_training_lowers_the_loss(azb, oracle):
     pi, v = net.predict(boards)
     assert np.allclose(pi.sum(1), 1.0, atol=1e-5) and np.isfinite(v).all()
     assert np.mean((v - vs) ** 2) < 1.2 * losses[-1]
+
+
+def test_default_step_size_is_justified(azb, oracle):
+    """The reference's Adam runs at 1e-3 (connect_four_net.py:21) on a network with BatchNorm in front of every ReLU.  This
+    network has none (folded away for inference): at 1e-3 the two-channel policy head dies within ~100 steps and the policy
+    loss parks at ln 7 = 1.946 (uniform), at 1e-4 (azb_learn_config_default) the same batches train.  This is the evidence
+    for the stated deviation; it fails if a future normalisation makes 1e-3 trainable (then the default should move back)."""
+    feats = random_features(oracle, 60, seed=11)[:512]
+    rng = np.random.default_rng(4)
+    # a learnable target: the policy prefers the centre-most legal column of the position, the value its stone balance
+    pis = np.zeros((len(feats), 7), np.float32)
+    for i, f in enumerate(feats):
+        free = [c for c in (3, 2, 4, 1, 5, 0, 6) if f[:, 0, c].sum() == 0]
+        pis[i, free[0] if free else 3] = 1.0
+    vs = np.tanh(feats[:, 0].sum((1, 2)) - feats[:, 1].sum((1, 2))).astype(np.float32)
+    final = {}
+    for lr in (1e-3, 1e-4):
+        net = azb.NNet(seed=7, blocks=6, precision=azb.NNET_BF16_TC)
+        losses = []
+        for step in range(160):
+            idx = rng.permutation(len(feats))[:256]
+            losses.append(net.train((feats[idx], pis[idx], vs[idx]), lr=lr))
+        final[lr] = float(np.mean([l[0] for l in losses[-10:]]))
+    assert final[1e-4] < 1.2, final          # trains
+    assert final[1e-3] > 1.8, final          # parks at ~ln 7: the head is dead
