@@ -115,5 +115,7 @@ def test_default_step_size_is_justified(azb, oracle):
             idx = rng.permutation(len(feats))[:256]
             losses.append(net.train((feats[idx], pis[idx], vs[idx]), lr=lr))
         final[lr] = float(np.mean([l[0] for l in losses[-10:]]))
-    assert final[1e-4] < 1.2, final          # trains
-    assert final[1e-3] > 1.8, final          # parks at ~ln 7: the head is dead
+    # measured on B200: 1e-4 -> 0.0014 (the 512 positions are learnt), 1e-3 -> 1.71 (the policy head is dead: the loss sits at the
+    # entropy of the targets' marginal, a little under ln 7 = 1.946)
+    assert final[1e-4] < 0.2, final
+    assert final[1e-3] > 1.2, final
