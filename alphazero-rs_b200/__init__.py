@@ -272,6 +272,10 @@ def _load():
         "azb_coach_setup": [C.POINTER(Config), C.POINTER(vp)],
         "azb_coach_destroy": [vp],
         "azb_coach_self_play": [vp, u64, u64, C.POINTER(SelfPlayStats)],
+        "azb_coach_self_play_begin": [vp, u64, u64],
+        "azb_coach_self_play_end": [vp, C.POINTER(SelfPlayStats)],
+        "azb_coach_span_mark": [vp],
+        "azb_coach_span_ms": [vp, vp, C.POINTER(C.c_double)],
         "azb_coach_traces": [vp, vp, vp, vp, vp, vp],
         "azb_coach_num_samples": [vp, C.POINTER(u64)],
         "azb_coach_ply_times": [vp, vp],
@@ -571,6 +575,27 @@ class Coach:
         _check(lib.azb_coach_self_play(self._h, n_games, first_game_id, C.byref(st)))
         self.n_games = n_games
         return st.as_dict()
+
+    def self_play_begin(self, n_games, first_game_id=0):
+        """Launch a self-play call and return (azb_coach_self_play_begin); self_play_end() collects it.  Two coaches used in
+        turn overlap one batch's tail with the next batch's head."""
+        _check(lib.azb_coach_self_play_begin(self._h, n_games, first_game_id))
+        self._begun = n_games
+
+    def self_play_end(self):
+        st = SelfPlayStats()
+        _check(lib.azb_coach_self_play_end(self._h, C.byref(st)))
+        self.n_games = self._begun
+        return st.as_dict()
+
+    def span_mark(self):
+        _check(lib.azb_coach_span_mark(self._h))
+
+    def span_ms(self, last):
+        """Device milliseconds (CUDA events) from this coach's span_mark() to the end of `last`'s most recent call."""
+        ms = C.c_double()
+        _check(lib.azb_coach_span_ms(self._h, last._h, C.byref(ms)))
+        return ms.value
 
     def execute_episode(self, episode_id=0):
         """One game; returns its SOA samples like the reference's VecDeque<TrainingSample>."""

@@ -169,17 +169,20 @@ static cudaError_t search_carveout(K kernel) {
   cudaFuncAttributes fa{};
   cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
   if (e != cudaSuccess) return e;
-  const size_t want = 7 * (fa.sharedSizeBytes + 1024);
+  const size_t want = kCtasPerSm * (fa.sharedSizeBytes + 1024);
   const int pct = static_cast<int>((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 static int resident_trees(int device, uint32_t* out) {
   int per_sm = 0, sms = 0;
-  AZB_CUDA(search_carveout(k_selfplay));
-  AZB_CUDA(search_carveout(k_round));
-  AZB_CUDA(search_carveout(k_mcts_search));
-  AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay, kWarpsPerCta * 32, 0));
+  AZB_CUDA(search_carveout(k_selfplay<false>));
+  AZB_CUDA(search_carveout(k_selfplay<true>));
+  AZB_CUDA(search_carveout(k_round<false>));
+  AZB_CUDA(search_carveout(k_round<true>));
+  AZB_CUDA(search_carveout(k_mcts_search<false>));
+  AZB_CUDA(search_carveout(k_mcts_search<true>));
+  AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_selfplay<false>, kWarpsPerCta * 32, 0));
   AZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   *out = static_cast<uint32_t>(per_sm * sms * kWarpsPerCta);
   return AZB_OK;
@@ -544,7 +547,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
 struct GameStore {
   DevBuf plies, final_r, final_player, error, actions, counts, sample_state, sample_pi, stats, arena_result, ply_ns;
   GameBufs g{};
-  int alloc(uint64_t G, bool samples) {
+  int alloc(uint64_t G, bool samples, cudaStream_t st = nullptr) {
     AZB_CUDA(plies.ensure(G * 4));
     AZB_CUDA(final_r.ensure(G * 4));
     AZB_CUDA(final_player.ensure(G));
@@ -557,12 +560,12 @@ struct GameStore {
     }
     AZB_CUDA(stats.ensure(G * 32));
     AZB_CUDA(arena_result.ensure(G));
-    AZB_CUDA(cudaMemset(actions.p, 0xFF, G * kTraceStride));
-    AZB_CUDA(cudaMemset(counts.p, 0, G * kTraceStride * 7 * 2));
-    AZB_CUDA(cudaMemset(plies.p, 0, G * 4));
-    AZB_CUDA(cudaMemset(error.p, 0, G * 4));
-    AZB_CUDA(cudaMemset(stats.p, 0, G * 32));
-    AZB_CUDA(cudaMemset(arena_result.p, 0, G));
+    AZB_CUDA(cudaMemsetAsync(actions.p, 0xFF, G * kTraceStride, st));
+    AZB_CUDA(cudaMemsetAsync(counts.p, 0, G * kTraceStride * 7 * 2, st));
+    AZB_CUDA(cudaMemsetAsync(plies.p, 0, G * 4, st));
+    AZB_CUDA(cudaMemsetAsync(error.p, 0, G * 4, st));
+    AZB_CUDA(cudaMemsetAsync(stats.p, 0, G * 32, st));
+    AZB_CUDA(cudaMemsetAsync(arena_result.p, 0, G, st));
     g.plies = plies.as<uint32_t>();
     g.final_r = final_r.as<float>();
     g.final_player = final_player.as<int8_t>();
@@ -575,7 +578,7 @@ struct GameStore {
     g.ply_ns = nullptr;
     if (std::getenv("AZB200_PLY_TIMES")) {  // diagnostic: per-ply completion times
       AZB_CUDA(ply_ns.ensure(G * kTraceStride * 8));
-      AZB_CUDA(cudaMemset(ply_ns.p, 0, G * kTraceStride * 8));
+      AZB_CUDA(cudaMemsetAsync(ply_ns.p, 0, G * kTraceStride * 8, st));
       g.ply_ns = ply_ns.as<unsigned long long>();
     }
     return AZB_OK;
@@ -720,7 +723,8 @@ struct RoundEngine {
       if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 0u, kTimesCap);
       k_compact<<<(rp.n_slots + 255u) / 256u, 256, 0, stream>>>(rp, recs.as<GameRec>(), c, lf);
       if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 1u, kTimesCap);
-      k_round<<<grid, kWarpsPerCta * 32, 0, stream>>>(rp, pools, recs.as<GameRec>(), c, lf, gs.g);
+      if (rp.p.num_threads > 1u) k_round<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(rp, pools, recs.as<GameRec>(), c, lf, gs.g);
+      else k_round<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(rp, pools, recs.as<GameRec>(), c, lf, gs.g);
       if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 2u, kTimesCap);
       AZB_CUDA(cudaGetLastError());
       if (any_net) {
@@ -876,6 +880,18 @@ struct azb_coach {
   // last self-play call
   uint64_t n_games = 0, n_samples = 0, launches = 0, nn_positions = 0, nn_cache_hits = 0;
   DevBuf next_game, offsets, out_boards, out_pis, out_vs;
+  // azb_coach_self_play_begin / _end: the persistent kernel runs on the coach's own non-blocking stream, so that two
+  // coaches used in turn overlap one batch's tail with the next batch's head
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, span0 = nullptr;
+  bool pending = false;
+  uint64_t pending_games = 0, pending_trees = 0;
+  ~azb_coach() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (span0) cudaEventDestroy(span0);
+    if (stream) cudaStreamDestroy(stream);
+  }
   std::vector<uint32_t> h_plies;
 };
 
@@ -1080,8 +1096,12 @@ int azb_mcts_get_action_prob(azb_mcts* m, const azb_c4_state* states, float temp
   AZB_CUDA(cudaMemset(m->d_counts.p, 0, n * 7 * sizeof(uint16_t)));
   AZB_CUDA(cudaMemset(m->d_pi.p, 0, n * 7 * sizeof(float)));
   const unsigned grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  k_mcts_search<<<grid, kWarpsPerCta * 32>>>(m->cfg.evaluator, m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
-                                             m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
+  if (m->pool.p.num_threads > 1u)
+    k_mcts_search<true><<<grid, kWarpsPerCta * 32>>>(m->cfg.evaluator, m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
+                                                     m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
+  else
+    k_mcts_search<false><<<grid, kWarpsPerCta * 32>>>(m->cfg.evaluator, m->pool.p, m->pool.pools, m->d_states.as<BB>(), temp,
+                                                      m->d_counts.as<uint16_t>(), m->d_pi.as<float>(), n);
   AZB_CUDA(cudaGetLastError());
   AZB_CUDA(cudaDeviceSynchronize());
   AZB_CUDA(cudaMemcpy(counts, m->d_counts.p, n * 7 * sizeof(uint16_t), cudaMemcpyDeviceToHost));
@@ -1174,8 +1194,15 @@ int azb_coach_destroy(azb_coach* c) {
   return AZB_OK;
 }
 
-int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, azb_selfplay_stats* stats) {
+// azb_coach_self_play in two halves.  _begin sizes the pools, clears the per-game buffers and LAUNCHES the call (the
+// persistent kernel of the fused evaluators goes to the coach's own non-blocking stream and _begin returns at once; the
+// lock-step rounds of the network evaluator run to completion inside _begin); _end waits, checks the games' error words
+// and fills the statistics.  Two coaches used in turn — begin(A), begin(B), end(A), export(A), begin(A), end(B), ... —
+// keep the device full across batches: a batch ends with its longest game (42 plies on one warp while the mean game
+// has 28), and the warps its finished games vacate are taken by the next batch's CTAs instead of idling.
+int azb_coach_self_play_begin(azb_coach* c, uint64_t n_games, uint64_t first_game_id) {
   if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (c->pending) return fail(AZB_ERR_INVALID, "a self-play call is already in flight on this coach (azb_coach_self_play_end first)");
   if (n_games == 0 || n_games > (1u << 26)) return fail(AZB_ERR_INVALID, "n_games out of range");
   HostTimer tm("self_play");
   AZB_CUDA(cudaSetDevice(c->cfg.device));
@@ -1200,15 +1227,9 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   if (!c->pool_ready || c->pool.n_trees != n_trees || std::memcmp(&c->pool.p, &p, sizeof(p)) != 0) {
     rc = c->pool.alloc(p, static_cast<uint32_t>(n_trees));
     if (rc) return rc;
+    AZB_CUDA(cudaDeviceSynchronize());  // (the pool's clears ran on the legacy stream; the kernel may go to the coach's)
     c->pool_ready = true;
   }
-  const uint64_t G = n_games;
-  rc = c->gs.alloc(G, true);
-  if (rc) return rc;
-  GameBufs g = c->gs.g;
-  tm.lap("pool + game buffers");
-  c->n_games = 0;
-  c->n_samples = 0;
   if (c->cfg.evaluator >= AZB_EVAL_NNET && !c->net)
     return fail(AZB_ERR_INVALID, "evaluator NNET needs azb_coach_set_nnet first");
   // schedule: 1 = one persistent kernel, a warp plays a whole game (fused evaluators only);
@@ -1216,17 +1237,30 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   uint32_t schedule = c->cfg.schedule;
   if (c->cfg.evaluator >= AZB_EVAL_NNET) schedule = 2;
   else if (schedule == 0) schedule = 1;  // measured: re-dealing live games buys nothing at 7 warps/scheduler
-
-  cudaEvent_t e0, e1;
-  AZB_CUDA(cudaEventCreate(&e0));
-  AZB_CUDA(cudaEventCreate(&e1));
-  AZB_CUDA(cudaEventRecord(e0));
+  if (!c->stream) {
+    AZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    AZB_CUDA(cudaEventCreate(&c->ev0));
+    AZB_CUDA(cudaEventCreate(&c->ev1));
+  }
+  cudaStream_t st = schedule == 1 ? c->stream : nullptr;
+  const uint64_t G = n_games;
+  rc = c->gs.alloc(G, true, st);
+  if (rc) return rc;
+  GameBufs g = c->gs.g;
+  tm.lap("pool + game buffers");
+  c->n_games = 0;
+  c->n_samples = 0;
+  AZB_CUDA(cudaEventRecord(c->ev0, st));
   if (schedule == 1) {
     AZB_CUDA(c->next_game.ensure(4));
-    AZB_CUDA(cudaMemset(c->next_game.p, 0, 4));
+    AZB_CUDA(cudaMemsetAsync(c->next_game.p, 0, 4, st));
     const unsigned grid = static_cast<unsigned>((n_trees + kWarpsPerCta - 1) / kWarpsPerCta);
-    k_selfplay<<<grid, kWarpsPerCta * 32>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
-                                            static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
+    if (p.num_threads > 1u)
+      k_selfplay<true><<<grid, kWarpsPerCta * 32, 0, st>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
+                                                           static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
+    else
+      k_selfplay<false><<<grid, kWarpsPerCta * 32, 0, st>>>(c->cfg.evaluator, p, c->pool.pools, g, static_cast<uint32_t>(n_trees),
+                                                            static_cast<uint32_t>(G), first_game_id, c->next_game.as<unsigned int>());
     AZB_CUDA(cudaGetLastError());
     c->launches = 1;
     c->nn_positions = 0;
@@ -1248,14 +1282,25 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
     rc = c->engine.run(rp, c->pool.pools, c->gs, nets, &c->launches, &c->nn_positions, &c->nn_cache_hits);
     if (rc) return rc;
   }
-  AZB_CUDA(cudaEventRecord(e1));
+  AZB_CUDA(cudaEventRecord(c->ev1, st));
   tm.lap("launch");
-  AZB_CUDA(cudaEventSynchronize(e1));
+  c->pending = true;
+  c->pending_games = G;
+  c->pending_trees = n_trees;
+  return AZB_OK;
+}
+
+int azb_coach_self_play_end(azb_coach* c, azb_selfplay_stats* stats) {
+  if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
+  if (!c->pending) return fail(AZB_ERR_INVALID, "no self-play call in flight (azb_coach_self_play_begin first)");
+  HostTimer tm("self_play_end");
+  AZB_CUDA(cudaSetDevice(c->cfg.device));
+  c->pending = false;
+  const uint64_t G = c->pending_games;
+  AZB_CUDA(cudaEventSynchronize(c->ev1));
   tm.lap("kernel wait");
   float ms = 0.0f;
-  AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  AZB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
 
   c->h_plies.resize(G);
   std::vector<uint32_t> h_err(G), h_stats(G * 8);
@@ -1280,13 +1325,42 @@ int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, 
   s.samples = s.plies * 2;
   s.device_ms = ms;
   s.launches = c->launches;
-  s.trees_resident = n_trees;
+  s.trees_resident = c->pending_trees;
   s.nn_positions = c->nn_positions;
   s.nn_cache_hits = c->nn_cache_hits;
   c->n_games = G;
   c->n_samples = s.samples;
   if (stats) *stats = s;
   return AZB_OK;
+}
+
+// Device time across pipelined calls: azb_coach_span_mark(first) records an event on that coach's stream before its next
+// _begin; azb_coach_span_ms(first, last) = from that mark to the end of `last`'s most recent call (after its _end).
+int azb_coach_span_mark(azb_coach* c) {
+  if (!c) return fail(AZB_ERR_INVALID, "NULL argument");
+  AZB_CUDA(cudaSetDevice(c->cfg.device));
+  if (!c->stream) {
+    AZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    AZB_CUDA(cudaEventCreate(&c->ev0));
+    AZB_CUDA(cudaEventCreate(&c->ev1));
+  }
+  if (!c->span0) AZB_CUDA(cudaEventCreate(&c->span0));
+  AZB_CUDA(cudaEventRecord(c->span0, c->stream));
+  return AZB_OK;
+}
+int azb_coach_span_ms(azb_coach* first, azb_coach* last, double* ms) {
+  if (!first || !last || !ms || !first->span0 || !last->ev1) return fail(AZB_ERR_INVALID, "NULL argument / no mark");
+  float f = 0.0f;
+  AZB_CUDA(cudaEventSynchronize(last->ev1));
+  AZB_CUDA(cudaEventElapsedTime(&f, first->span0, last->ev1));
+  *ms = f;
+  return AZB_OK;
+}
+
+int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id, azb_selfplay_stats* stats) {
+  const int rc = azb_coach_self_play_begin(c, n_games, first_game_id);
+  if (rc) return rc;
+  return azb_coach_self_play_end(c, stats);
 }
 
 int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint32_t* plies, float* final_r,

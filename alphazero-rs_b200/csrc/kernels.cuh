@@ -6,7 +6,14 @@
 
 namespace azb {
 
-constexpr int kWarpsPerCta = 4;
+// Warps (= trees) per CTA of the search kernels.  A CTA's slot on its SM is free again only when ALL its warps are done, so
+// with back-to-back batches on two streams (azb_coach_self_play_begin / _end) small CTAs hand finished games' warp slots
+// to the next batch sooner.
+#ifndef AZB_WARPS_PER_CTA
+#define AZB_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = AZB_WARPS_PER_CTA;
+constexpr int kCtasPerSm = 28 / kWarpsPerCta;  // 28 resident warps per SM at 72 registers
 constexpr int kMaxPlies = 42;   // the board has 42 cells
 constexpr int kTraceStride = 64;
 
@@ -52,6 +59,7 @@ __device__ __forceinline__ void fresh_table(WarpTree& t, const Pools& pools, con
 }
 
 // ---- AsyncMcts::get_action_prob for n_trees persistent trees (test hook) --------------------
+template <bool WAVE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_mcts_search(int ev_kind, SearchParams p, Pools pools, const BB* __restrict__ states, float temp,
               uint16_t* __restrict__ counts, float* __restrict__ pi_out, uint32_t n_trees) {
@@ -68,7 +76,7 @@ k_mcts_search(int ev_kind, SearchParams p, Pools pools, const BB* __restrict__ s
   const BB s = states[tree];
   uint32_t rs = 0, rm = 0;
   if (make_root(t, p, s, lane, rs, rm)) {  // lookup_state_id (:81), F12 on a miss
-    run_sims(t, p, ev_kind, s, rs, rm, p.num_sims, lane);
+    run_sims<WAVE>(t, p, ev_kind, s, rs, rm, p.num_sims, lane);
     if (!t.error) {
       const uint32_t cnt = root_child_count(t, rm, lane);
       const float pi = counts_to_pi(cnt, temp, lane);
@@ -142,7 +150,8 @@ struct GameBufs {
   unsigned long long* ply_ns;  // [n_games][64] %globaltimer at the end of each ply (diagnostic), or nullptr
 };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
+template <bool WAVE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n_games,
            uint64_t first_game_id, unsigned int* next_game) {
   const uint32_t tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -168,7 +177,7 @@ k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_tree
       uint32_t rs = 0, rm = 0;
       if (!make_root(t, p, board, lane, rs, rm)) break;          // get_action_prob :81 (+F12)
       if (step * p.num_sims >= kSafeVisits) t.slow = 1u;
-      run_sims(t, p, ev_kind, board, rs, rm, p.num_sims, lane);     // :82
+      run_sims<WAVE>(t, p, ev_kind, board, rs, rm, p.num_sims, lane);  // :82
       if (t.error) break;
       const uint32_t cnt = root_child_count(t, rm, lane);
       const float pi = counts_to_pi(cnt, temp, lane);

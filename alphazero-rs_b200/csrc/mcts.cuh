@@ -983,10 +983,13 @@ __device__ __forceinline__ void wave_inline(WarpTree& t, const SearchParams& p, 
 }
 
 // search (:191-217) with num_threads = 1 and a fused evaluator: nsims simulations from `root`.
+// WAVE is a compile-time switch: the deterministic kernels carry none of the wave code (inlined into them it cost the
+// persistent kernel 12 % at BASELINE config 2 without a single spill — code size / layout of the hot loop).
+template <bool WAVE>
 __device__ __forceinline__ void run_sims(WarpTree& t, const SearchParams& p, int ev_kind, BB root,
                                          uint32_t root_slot, uint32_t root_meta, uint32_t nsims,
                                          int lane) {
-  if (p.num_threads > 1u) {  // tree-parallel mode: waves of K simulations (num_sims % K == 0 is checked at setup, :192)
+  if constexpr (WAVE) {  // tree-parallel mode: waves of K simulations (num_sims % K == 0 is checked at setup, :192)
     for (uint32_t sim = 0; sim < nsims && !t.error; sim += p.num_threads)
       wave_inline(t, p, ev_kind, root, root_slot, root_meta, p.num_threads, lane);
     return;

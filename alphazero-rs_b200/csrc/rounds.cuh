@@ -293,7 +293,8 @@ __device__ __forceinline__ void leaf_fetch(const LeafBufs& leaf, uint32_t side, 
 }
 
 // ---- k_round ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7)
+template <bool WAVE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, GameBufs g) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -347,7 +348,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
   load_tree_vars(t, rec->tv[side], lane);
   uint32_t err = 0;
 
-  if (phase == kPhasePending && rec->pd.kind == kPendWave) {  // the answers for a suspended wave's leaves are in
+  if (WAVE && phase == kPhasePending && rec->pd.kind == kPendWave) {  // the answers for a suspended wave's leaves are in
     WaveSim* ws = reinterpret_cast<WaveSim*>(t.path);
     {
       const uint4* src = reinterpret_cast<const uint4*>(rec->path);
@@ -422,7 +423,7 @@ k_round(RoundParams rp, Pools pools, GameRec* recs, Control ctl, LeafBufs leaf, 
     bool suspended = false, yielded = false;
     Pending pd;
     BB leaf_pos;
-    if (p.num_threads > 1u) {
+    if constexpr (WAVE) {
       // ---- tree-parallel mode: waves of K walks (mcts.cuh wave_*); a wave suspends with up to K leaves ----
       WaveSim* ws = reinterpret_cast<WaveSim*>(t.path);
       bool waiting = false;

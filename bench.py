@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (default: config 2)")
     ap.add_argument("--sims", type=int, default=NUM_SIMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one step at a time (no overlap of consecutive batches)")
     ap.add_argument("--no-secondary", action="store_true", help="headline line only (config 2): skip configs 1, 3, 4, 5")
     ap.add_argument("--parity-games", type=int, default=16, help="games of the last timed step replayed by the oracle")
     args = ap.parse_args()
@@ -377,51 +378,79 @@ def main():
         return azb.sharding.reduce_scalar(dist, x, op, device="cuda" if dist is not None else None)
 
     import numpy as np
-    coach = azb.Coach(num_sims=args.sims, seed=SEED, quirks=azb.PROFILE_SANE, evaluator=azb.EVAL_UNIFORM,
-                      temp_threshold=15, cpuct=1, max_depth=1000, mcts_reserve_size=1000000, device=local_rank)
+    # Steps are enqueued TWO DEEP on two coaches (each with its own trees, buffers and CUDA stream): begin(k + 1) is called
+    # before end(k), so the warps that batch k's finished games vacate are taken by batch k + 1's games instead of idling
+    # until batch k's longest game ends (a batch of 4096 games ends with its 42-ply stragglers while the mean game has 28
+    # plies).  Every step is still one batch of 4096 games played to completion by its own launch; at most one SM-ful of
+    # games (28 warps per SM) is in flight at any time.  The CPU arm has no such barrier either (its threads take the
+    # next game when one ends).  --no-pipeline runs the steps one after the other (round 1's loop).
+    mk = lambda: azb.Coach(num_sims=args.sims, seed=SEED, quirks=azb.PROFILE_SANE, evaluator=azb.EVAL_UNIFORM,
+                           temp_threshold=15, cpuct=1, max_depth=1000, mcts_reserve_size=1000000, device=local_rank)
+    depth = 1 if args.no_pipeline else 2
+    coaches = [mk() for _ in range(depth)]
+    coach = coaches[0]
     G = args.games
     cap = G * 84  # 42 plies x 2 symmetries: the most samples a game can produce
-    pinned = [azb.PinnedArray((cap, 2, 6, 7)), azb.PinnedArray((cap, 7)), azb.PinnedArray((cap,))]
-    out = tuple(p.array for p in pinned)
+    pinned = [[azb.PinnedArray((cap, 2, 6, 7)), azb.PinnedArray((cap, 7)), azb.PinnedArray((cap,))] for _ in range(depth)]
+    outs = [tuple(p.array for p in ps) for ps in pinned]
+    first_of = lambda k: azb.sharding.shard(k, rank, world, G)[0]  # global game ids: disjoint per rank and per step
 
-    def step(k):
-        """One pass of the hot path through the public API, host buffers out."""
-        first, _ = azb.sharding.shard(k, rank, world, G)  # global game ids: disjoint per rank and per step
+    def run_steps(k0, n, export):
+        """n steps (k0 ...) through the public API, `depth` in flight.  export: the SOA samples of every step are copied into
+        page-locked host buffers.  Returns (per-step stats, samples exported, wall seconds, device-span ms)."""
+        stats, n_samples = [], 0
+        coaches[0].span_mark()
         t0 = time.perf_counter()
-        st = coach.self_play(G, first)
-        _, _, vs = coach.export_samples(out)
-        t1 = time.perf_counter()
-        return st, t1 - t0, len(vs)
+        for j in range(min(depth - 1, n)):
+            coaches[j % depth].self_play_begin(G, first_of(k0 + j))
+        for j in range(n):
+            nxt = j + depth - 1
+            if nxt < n:
+                coaches[nxt % depth].self_play_begin(G, first_of(k0 + nxt))
+            c = coaches[j % depth]
+            stats.append(c.self_play_end())
+            if export:
+                _, _, vs = c.export_samples(outs[j % depth])
+                n_samples += len(vs)
+        wall = time.perf_counter() - t0
+        span = coaches[0].span_ms(coaches[(n - 1) % depth])
+        return stats, n_samples, wall, span
 
     sampler = ClockSampler(local_rank)
-    for k in range(args.warmup):
-        step(k)
+    run_steps(0, args.warmup, True)
+    # one batch alone (no overlap): the latency of a single 4096-game call
+    st1 = coaches[0].self_play(G, first_of(args.warmup))
+    single_batch_ms = st1["device_ms"]
     barrier()
     if rank == 0:
         sampler.window_open()
-    dev_ms = wall = 0.0
+    # (1) device-timed: inputs resident, nothing copied out between steps, CUDA events from the first launch to the last end
+    k_dev = args.warmup + 1
+    stats_dev, _, _, span_ms = run_steps(k_dev, args.steps, False)
+    barrier()
+    # (2) end to end: the same K steps with every step's samples exported to host memory, wall clock
+    k_e2e = k_dev + args.steps
+    stats_e2e, n_samples, wall, _ = run_steps(k_e2e, args.steps, True)
+    barrier()
+    sampler.window_close()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = span_ms
     tot = {}
-    n_samples = 0
-    per_step = []
-    launches = 0
-    for k in range(args.steps):
-        st, w, ns = step(args.warmup + k)
-        dev_ms += st["device_ms"]; wall += w; n_samples += ns
-        launches += st["launches"] + 1  # the library's own count of the self-play launches + k_export_samples
-        per_step.append((round(st["device_ms"], 2), round(1e3 * w, 2)))
+    for st in stats_dev:
         for key, v in st.items():
             if key not in ("device_ms", "blocks_used_max", "owners_max"):
                 tot[key] = tot.get(key, 0) + v
         tot["blocks_used_max"] = max(tot.get("blocks_used_max", 0), st["blocks_used_max"])
-    barrier()
-    sampler.window_close()
-    clocks = sampler.stop() if rank == 0 else None
+    sims_e2e = sum(st["sims"] for st in stats_e2e)
+    launches = sum(st["launches"] for st in stats_dev) + sum(st["launches"] + 1 for st in stats_e2e)
+    per_step = [round(st["device_ms"], 2) for st in stats_dev]
+    coach = coaches[(args.steps - 1) % depth]  # holds the last timed step's games
     # parity of what was just timed: games of the LAST timed step (this rank's) replayed by the oracle, bit for bit
     parity_checked = 0
     if rank == 0 and args.parity_games > 0:
         ge.build_oracle()
         import oracle_api as orc
-        last_first, _ = azb.sharding.shard(args.warmup + args.steps - 1, rank, world, G)
+        last_first = first_of(k_e2e + args.steps - 1)
         parity_checked = replay_parity(orc, coach.traces(), G, args.parity_games, first=last_first, num_sims=args.sims,
                                        quirks=0, seed=SEED, evaluator=orc.EVAL_UNIFORM)
 
@@ -431,6 +460,7 @@ def main():
     games_all = reduce(tot["games"], "SUM")
     levels_all = reduce(tot["levels"], "SUM")
     exp_all = reduce(tot["expansions"], "SUM")
+    sims_e2e_all = reduce(sims_e2e, "SUM")
     secondary = {}
     if not args.no_secondary and world > 1:  # collective sections: every rank takes part
         import tempfile
@@ -450,7 +480,7 @@ def main():
         return
 
     value = sims_all / (dev_ms_max * 1e-3)
-    e2e = sims_all / wall_max
+    e2e = sims_e2e_all / wall_max
     L, X = levels_all / sims_all, exp_all / sims_all
     bps = algorithmic_bytes_per_sim(L, X)
     peak, peak_src = peaks()
@@ -471,17 +501,26 @@ def main():
                    "games_per_sec": games_all / (dev_ms_max * 1e-3), "plies_per_game": tot["plies"] / tot["games"],
                    "levels_per_sim": L, "expansions_per_sim": X, "bytes_per_sim": bps,
                    "blocks_used_max": tot["blocks_used_max"],
-                   "l2": "tree pools (~20 GB per GPU) are far larger than L2; no flush needed",
+                   "l2": "tree pools (~20 GB per coach) are far larger than L2; no flush needed",
+                   "pipelining": ("none: one step at a time" if depth == 1 else
+                                  "steps enqueued 2 deep on two coaches with their own trees and CUDA streams "
+                                  "(azb_coach_self_play_begin / _end): the next batch's games take the warps the current batch's "
+                                  "finished games vacate; every step is one batch of 4096 games played to completion by its own launch"),
+                   "single_batch_ms": single_batch_ms,
+                   "launch_ms_mean": sum(per_step) / max(1, len(per_step)),
                    "parallelism": f"{world} GPU(s), independent games per GPU, no collective on the path" +
                                   ("; ranks synchronised through the library's own NCCL communicator (no torch)" if comm is not None else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_selfplay<UNIFORM>",
-                     "launch_ms": dev_ms / args.steps},
+                     "launch_ms": dev_ms / args.steps,
+                     "how": "algorithmic bytes of the timed region / its device span (CUDA events from the first launch to the last "
+                            "launch's end); consecutive launches overlap on the device, so a per-launch duration (launch_ms_mean in "
+                            "config) would count the shared time twice"},
         "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "bytes_how": "computed from the sizes of the arrays the call copies (samples x 92 f32 + per-game plies / errors / "
                              "statistics; config struct + game ids in), not measured on the bus",
                 "ms_per_step": 1e3 * wall_max / args.steps,
-                "per_step_ms_device_and_wall": per_step},
+                "per_launch_device_ms": per_step},
         "gpu_launches": launches,
         "gpu_launches_how": "the library's own launch counter per self-play call (azb_selfplay_stats.launches: one persistent "
                             "k_selfplay) + one k_export_samples per step, rank 0",
@@ -493,9 +532,11 @@ def main():
         import tempfile
         ge.build_oracle()
         import oracle_api as orc
-        coach.close()
-        for p_ in pinned:
-            p_.close()
+        for c_ in coaches:
+            c_.close()
+        for ps in pinned:
+            for p_ in ps:
+                p_.close()
         net = None
         # the leaf evaluator's dense forward pass, the only tensor-core work of the path, timed with CUDA events inside the library
         try:

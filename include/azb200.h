@@ -158,6 +158,19 @@ typedef struct azb_selfplay_stats {
  * root_counts[n_games][64][7], plies[n_games], final_r[n_games], final_player[n_games]. */
 int azb_coach_self_play(azb_coach* c, uint64_t n_games, uint64_t first_game_id,
                         azb_selfplay_stats* stats);
+/* The same call in two halves: _begin launches (the persistent kernel of the fused evaluators runs on the coach's own
+ * stream and _begin returns at once; network rounds complete inside _begin), _end waits and fills the statistics.  Used in
+ * turn on two coaches — begin(A), begin(B), end(A), export(A), begin(A), end(B), ... — consecutive batches overlap on the
+ * device: the warps that a batch's finished games vacate are taken by the next batch instead of idling until the batch's
+ * longest game ends (the reference's rayon pool has no such barrier either: a worker that finishes an episode takes the
+ * next one, coach.rs:241-272).  A coach holds one call in flight; its results (traces, samples) are those of the last
+ * _end. */
+int azb_coach_self_play_begin(azb_coach* c, uint64_t n_games, uint64_t first_game_id);
+int azb_coach_self_play_end(azb_coach* c, azb_selfplay_stats* stats);
+/* Device time across pipelined calls (CUDA events): _span_mark(first) records an event on that coach's stream before its
+ * next _begin; _span_ms(first, last, &ms) = from that mark to the end of `last`'s most recent call. */
+int azb_coach_span_mark(azb_coach* c);
+int azb_coach_span_ms(azb_coach* first, azb_coach* last, double* ms);
 int azb_coach_traces(azb_coach* c, uint8_t* actions, uint16_t* root_counts, uint32_t* plies,
                      float* final_r, int8_t* final_player);
 /* Diagnostic (persistent schedule, env AZB200_PLY_TIMES=1): ns[n_games][64] = %globaltimer at the end

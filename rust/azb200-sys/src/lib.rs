@@ -202,6 +202,10 @@ extern "C" {
     pub fn azb_coach_setup(cfg: *const azb_config, out: *mut *mut azb_coach) -> c_int;
     pub fn azb_coach_destroy(c: *mut azb_coach) -> c_int;
     pub fn azb_coach_self_play(c: *mut azb_coach, n_games: u64, first_game_id: u64, stats: *mut azb_selfplay_stats) -> c_int;
+    pub fn azb_coach_self_play_begin(c: *mut azb_coach, n_games: u64, first_game_id: u64) -> c_int;
+    pub fn azb_coach_self_play_end(c: *mut azb_coach, stats: *mut azb_selfplay_stats) -> c_int;
+    pub fn azb_coach_span_mark(c: *mut azb_coach) -> c_int;
+    pub fn azb_coach_span_ms(first: *mut azb_coach, last: *mut azb_coach, ms: *mut f64) -> c_int;
     pub fn azb_coach_traces(c: *mut azb_coach, actions: *mut u8, root_counts: *mut u16, plies: *mut u32, final_r: *mut f32, final_player: *mut i8) -> c_int;
     pub fn azb_coach_ply_times(c: *mut azb_coach, ns: *mut u64) -> c_int;
     pub fn azb_coach_num_samples(c: *mut azb_coach, n: *mut u64) -> c_int;

@@ -108,3 +108,34 @@ def test_full_size_properties(azb, schedule):
     st2 = coach.self_play(4096, 0)
     tr2 = coach.traces()
     assert np.array_equal(tr["actions"], tr2["actions"]) and st2["levels"] == st["levels"]
+
+
+def test_pipelined_calls_equal_blocking_calls(azb, oracle):
+    """azb_coach_self_play_begin / _end on two coaches used in turn (consecutive batches overlap on the device) give, batch by
+    batch, what the blocking call gives; one batch is replayed by the oracle."""
+    G, sims = 96, 60
+    cs = [azb.Coach(num_sims=sims, seed=21, evaluator=azb.EVAL_HASH) for _ in range(2)]
+    ref = azb.Coach(num_sims=sims, seed=21, evaluator=azb.EVAL_HASH)
+    cs[0].self_play_begin(G, 0)
+    for k in range(4):
+        if k + 1 < 4:
+            cs[(k + 1) % 2].self_play_begin(G, (k + 1) * G)
+        st = cs[k % 2].self_play_end()
+        tr = cs[k % 2].traces()
+        b, p, v = cs[k % 2].export_samples()
+        rst = ref.self_play(G, k * G)
+        rtr = ref.traces()
+        rb, rp, rv = ref.export_samples()
+        for key in ("plies", "sims", "levels", "expansions", "terminal_hits", "dup_links", "evals"):
+            assert st[key] == rst[key], (k, key)
+        assert np.array_equal(tr["actions"], rtr["actions"]) and np.array_equal(tr["counts"], rtr["counts"])
+        assert np.array_equal(b, rb) and np.array_equal(p, rp) and np.array_equal(v, rv)
+    o = oracle.execute_episode(num_sims=sims, seed=21, episode_id=3 * G + 5, evaluator=oracle.EVAL_HASH)
+    n = o["plies"]
+    assert tr["plies"][5] == n and tr["actions"][5, :n].tolist() == o["actions"][:n].tolist()
+    with pytest.raises(azb.AzbError):
+        cs[0].self_play_end()  # nothing in flight
+    cs[0].self_play_begin(G, 0)
+    with pytest.raises(azb.AzbError):
+        cs[0].self_play_begin(G, G)  # one call in flight per coach
+    cs[0].self_play_end()
