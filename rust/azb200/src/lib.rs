@@ -405,6 +405,25 @@ impl Coach {
         debug_assert_eq!(written as usize, ns);
         Ok(((boards, pis, vs), st))
     }
+    /// The fan-out in two halves (`azb_coach_self_play_begin` / `_end`): `begin` launches and returns, `end` waits and hands the
+    /// samples out.  Two coaches used in turn overlap consecutive batches on the device (a rayon pool has no barrier between
+    /// episodes either, coach.rs:241-272).
+    pub fn execute_episodes_begin(&mut self, n: usize, first_episode_id: u64) -> Result<()> {
+        check(unsafe { sys::azb_coach_self_play_begin(self.h, n as u64, first_episode_id) })
+    }
+    pub fn execute_episodes_end(&mut self) -> Result<(SOATrainingSamples, sys::azb_selfplay_stats)> {
+        let mut st = sys::azb_selfplay_stats::default();
+        check(unsafe { sys::azb_coach_self_play_end(self.h, &mut st) })?;
+        let ns = st.samples as usize;
+        let mut boards = ArrayD::<F>::zeros(IxDyn(&[ns, 2, 6, 7]));
+        let mut pis = Array2::<f32>::zeros((ns, sys::AZB_C4_ACTIONS));
+        let mut vs = Array1::<f32>::zeros(ns);
+        let mut written = 0u64;
+        check(unsafe {
+            sys::azb_coach_export_samples(self.h, boards.as_mut_ptr(), pis.as_mut_ptr(), vs.as_mut_ptr(), ns as u64, &mut written)
+        })?;
+        Ok(((boards, pis, vs), st))
+    }
     /// Coach::execute_episode(mcts, episode_id, rng) — coach.rs:104-109.
     pub fn execute_episode(&mut self, episode_id: u64) -> Result<SOATrainingSamples> {
         Ok(self.execute_episodes(1, episode_id)?.0)
