@@ -260,6 +260,7 @@ def _load():
     vp, sz, u64, u32, f32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_float
     sigs = {
         "azb_device_count": [],
+        "azb_release_caches": [],
         "azb_c4_init": [vp, sz],
         "azb_c4_feature_shape": [vp],
         "azb_c4_next_state": [vp, vp, vp, sz, vp, vp],
@@ -358,6 +359,11 @@ def _check(rc):
 
 def device_count():
     return lib.azb_device_count()
+
+
+def release_caches():
+    """Free the calling thread's evaluation cache (~2.7 GB of device memory kept between network runs)."""
+    _check(lib.azb_release_caches())
 
 
 class PinnedArray:

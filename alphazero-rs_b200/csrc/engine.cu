@@ -73,6 +73,19 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// A pair of CUDA events that cannot leak on an early return.
+struct EventPair {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t create() {
+    cudaError_t e = cudaEventCreate(&e0);
+    return e != cudaSuccess ? e : cudaEventCreate(&e1);
+  }
+  ~EventPair() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
 uint32_t pow2_ceil(uint64_t x) {
   uint64_t p = 1;
   while (p < x) p <<= 1;
@@ -165,19 +178,19 @@ int capacity_error(uint32_t code) {
 // The search lives on L1 hits of the hot tree top: keep the unified L1/shared array as L1 and ask for
 // just enough shared memory for the CTAs the launch bounds allow (static smem + 1 KB reserved each).
 template <typename K>
-static cudaError_t search_carveout(K kernel) {
+static cudaError_t search_carveout(K kernel, int ctas_per_sm = kCtasPerSm) {
   cudaFuncAttributes fa{};
   cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
   if (e != cudaSuccess) return e;
-  const size_t want = kCtasPerSm * (fa.sharedSizeBytes + 1024);
+  const size_t want = ctas_per_sm * (fa.sharedSizeBytes + 1024);
   const int pct = static_cast<int>((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 static int resident_trees(int device, uint32_t* out) {
   int per_sm = 0, sms = 0;
-  AZB_CUDA(search_carveout(k_selfplay<false>));
-  AZB_CUDA(search_carveout(k_selfplay<true>));
+  AZB_CUDA(search_carveout(k_selfplay<false>, kPlayCtasPerSm));
+  AZB_CUDA(search_carveout(k_selfplay<true>, kPlayCtasPerSm));
   AZB_CUDA(search_carveout(k_round<false>));
   AZB_CUDA(search_carveout(k_round<true>));
   AZB_CUDA(search_carveout(k_mcts_search<false>));
@@ -901,6 +914,22 @@ extern "C" {
 
 const char* azb_last_error(void) { return g_err.c_str(); }
 
+// The evaluation cache of the network rounds (2 x 2^25 entries, ~2.7 GB) belongs to the calling thread and is re-used by every
+// run of that thread; this gives it back to the device (the next network run allocates it again).
+int azb_release_caches(void) {
+  RoundEngine::CacheBufs& cb = RoundEngine::thread_cache();
+  if (cb.device >= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(cb.device);
+    cb.keys.release();
+    cb.vals.release();
+    cudaSetDevice(dev);
+    cb.device = -1;
+  }
+  return AZB_OK;
+}
+
 int azb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -1533,20 +1562,17 @@ int azb_nnet_benchmark(azb_nnet* n, uint64_t batch, uint32_t iters, double* ms_p
     int rc = nnet_forward(n, n->d_states.as<uint4>(), nullptr, B, n->d_pi.as<float>(), n->d_v.as<float>(), 0);
     if (rc) return rc;
   }
-  cudaEvent_t e0, e1;
-  AZB_CUDA(cudaEventCreate(&e0));
-  AZB_CUDA(cudaEventCreate(&e1));
-  AZB_CUDA(cudaEventRecord(e0));
+  EventPair ev;
+  AZB_CUDA(ev.create());
+  AZB_CUDA(cudaEventRecord(ev.e0));
   for (uint32_t i = 0; i < iters; ++i) {
     int rc = nnet_forward(n, n->d_states.as<uint4>(), nullptr, B, n->d_pi.as<float>(), n->d_v.as<float>(), 0);
     if (rc) return rc;
   }
-  AZB_CUDA(cudaEventRecord(e1));
-  AZB_CUDA(cudaEventSynchronize(e1));
+  AZB_CUDA(cudaEventRecord(ev.e1));
+  AZB_CUDA(cudaEventSynchronize(ev.e1));
   float ms = 0.0f;
-  AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  AZB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
   *ms_per_pass = ms / iters;
   return AZB_OK;
 }
@@ -1901,20 +1927,17 @@ int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a,
   rp.shared = shared ? 1u : 0u;
   rp.first_game_id = o.first_game_id;
   azb_nnet* nets[2] = {net_a, net_b};
-  cudaEvent_t e0, e1;
-  AZB_CUDA(cudaEventCreate(&e0));
-  AZB_CUDA(cudaEventCreate(&e1));
-  AZB_CUDA(cudaEventRecord(e0));
+  EventPair ev;
+  AZB_CUDA(ev.create());
+  AZB_CUDA(cudaEventRecord(ev.e0));
   uint64_t launches = 0;
   uint64_t nn_positions = 0, nn_cache_hits = 0;
   rc = eng.run(rp, pool.pools, gs, nets, &launches, &nn_positions, &nn_cache_hits);
   if (rc) return rc;
-  AZB_CUDA(cudaEventRecord(e1));
-  AZB_CUDA(cudaEventSynchronize(e1));
+  AZB_CUDA(cudaEventRecord(ev.e1));
+  AZB_CUDA(cudaEventSynchronize(ev.e1));
   float ms = 0.0f;
-  AZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  AZB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
   std::vector<int8_t> res(G);
   std::vector<uint32_t> h_err(G), h_stats(G * 8), h_plies(G);
   AZB_CUDA(cudaMemcpy(res.data(), gs.arena_result.p, G, cudaMemcpyDeviceToHost));

@@ -13,7 +13,15 @@ namespace azb {
 #define AZB_WARPS_PER_CTA 4
 #endif
 constexpr int kWarpsPerCta = AZB_WARPS_PER_CTA;
-constexpr int kCtasPerSm = 28 / kWarpsPerCta;  // 28 resident warps per SM at 72 registers
+// Resident warps per SM: 28 at 72 registers, 32 at 64, 36 at 56.  The persistent self-play kernel runs at 32: with
+// consecutive batches overlapped the device is full, and four more warps per SM hide more latency than the 8 registers
+// cost (measured, 8 batches three deep: 74.7 ms per batch at 32, 78.5 at 28, 83.4 at 36; one batch alone 108 vs 106 ms).
+// The round kernel keeps 28 (it already spills at 72).
+#ifndef AZB_WARPS_PER_SM
+#define AZB_WARPS_PER_SM 32
+#endif
+constexpr int kCtasPerSm = 28 / kWarpsPerCta;                    // k_round, k_mcts_search
+constexpr int kPlayCtasPerSm = AZB_WARPS_PER_SM / kWarpsPerCta;  // k_selfplay
 constexpr int kMaxPlies = 42;   // the board has 42 cells
 constexpr int kTraceStride = 64;
 
@@ -151,7 +159,7 @@ struct GameBufs {
 };
 
 template <bool WAVE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kPlayCtasPerSm)
 k_selfplay(int ev_kind, SearchParams p, Pools pools, GameBufs g, uint32_t n_trees, uint32_t n_games,
            uint64_t first_game_id, unsigned int* next_game) {
   const uint32_t tree = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -331,6 +331,7 @@ def main():
     ap.add_argument("--sims", type=int, default=NUM_SIMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="one step at a time (no overlap of consecutive batches)")
+    ap.add_argument("--depth", type=int, default=3, help="steps in flight (coaches with their own trees and streams)")
     ap.add_argument("--no-secondary", action="store_true", help="headline line only (config 2): skip configs 1, 3, 4, 5")
     ap.add_argument("--parity-games", type=int, default=16, help="games of the last timed step replayed by the oracle")
     args = ap.parse_args()
@@ -378,15 +379,15 @@ def main():
         return azb.sharding.reduce_scalar(dist, x, op, device="cuda" if dist is not None else None)
 
     import numpy as np
-    # Steps are enqueued TWO DEEP on two coaches (each with its own trees, buffers and CUDA stream): begin(k + 1) is called
-    # before end(k), so the warps that batch k's finished games vacate are taken by batch k + 1's games instead of idling
+    # Steps are enqueued `depth` (3) DEEP on as many coaches (each with its own trees, buffers and CUDA stream): begin(k + 2) is
+    # called before end(k), so the warps that batch k's finished games vacate are taken by batch k + 1's games instead of idling
     # until batch k's longest game ends (a batch of 4096 games ends with its 42-ply stragglers while the mean game has 28
     # plies).  Every step is still one batch of 4096 games played to completion by its own launch; at most one SM-ful of
     # games (28 warps per SM) is in flight at any time.  The CPU arm has no such barrier either (its threads take the
     # next game when one ends).  --no-pipeline runs the steps one after the other (round 1's loop).
     mk = lambda: azb.Coach(num_sims=args.sims, seed=SEED, quirks=azb.PROFILE_SANE, evaluator=azb.EVAL_UNIFORM,
                            temp_threshold=15, cpuct=1, max_depth=1000, mcts_reserve_size=1000000, device=local_rank)
-    depth = 1 if args.no_pipeline else 2
+    depth = 1 if args.no_pipeline else max(1, args.depth)
     coaches = [mk() for _ in range(depth)]
     coach = coaches[0]
     G = args.games
@@ -503,7 +504,7 @@ def main():
                    "blocks_used_max": tot["blocks_used_max"],
                    "l2": "tree pools (~20 GB per coach) are far larger than L2; no flush needed",
                    "pipelining": ("none: one step at a time" if depth == 1 else
-                                  "steps enqueued 2 deep on two coaches with their own trees and CUDA streams "
+                                  f"steps enqueued {depth} deep on {depth} coaches with their own trees and CUDA streams "
                                   "(azb_coach_self_play_begin / _end): the next batch's games take the warps the current batch's "
                                   "finished games vacate; every step is one batch of 4096 games played to completion by its own launch"),
                    "single_batch_ms": single_batch_ms,

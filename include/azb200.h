@@ -42,6 +42,9 @@ typedef enum azb_status {
 #define AZB_EVAL_NNET 2    /* batched leaf evaluation by an azb_nnet (lock-step rounds) */
 
 const char* azb_last_error(void);
+/* Give the calling thread's evaluation cache (network rounds: 2 x 2^25 entries, ~2.7 GB of device memory, kept between
+ * calls) back to the device; the next network run allocates it again. */
+int azb_release_caches(void);
 /* Number of visible CUDA devices (0 when there is none; never fails). */
 int azb_device_count(void);
 

@@ -183,6 +183,7 @@ pub const AZB_DIST_MIN: i32 = 2;
 extern "C" {
     pub fn azb_last_error() -> *const c_char;
     pub fn azb_device_count() -> c_int;
+    pub fn azb_release_caches() -> c_int;
     pub fn azb_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn azb_host_free(p: *mut c_void) -> c_int;
 
