@@ -292,8 +292,6 @@ struct azb_nnet {
       for (int c = 0; c < kTcWeightCopies; ++c)
         AZB_CUDA(cudaMemcpy(d_wtiles.as<uint8_t>() + c * wtile_copy_bytes, tiles.data(), wtile_copy_bytes, cudaMemcpyHostToDevice));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<kTcCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-      AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
@@ -317,32 +315,6 @@ struct azb_nnet {
 };
 
 namespace {
-// TMA descriptor of an activation buffer for im2col loads: NHWC tensor {C=128, W=7, H=6, N}, 3x3 window
-// with padding 1 (pixel box corners -1 / -1), 64 channels x 128 pixels per copy, SWIZZLE_128B.
-int encode_act_map(CUtensorMap* map, void* ptr, size_t bytes) {
-  typedef CUresult (*EncodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeIm2col encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    AZB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeIm2col is not available in this driver");
-    encode = reinterpret_cast<EncodeIm2col>(fn);
-  }
-  const cuuint64_t n_pos = bytes / (static_cast<size_t>(kCells) * kNetC * 2);
-  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kNetC), 7, 6, n_pos};
-  const cuuint64_t strides[3] = {kNetC * 2, 7 * kNetC * 2, static_cast<cuuint64_t>(kCells) * kNetC * 2};  // bytes: W, H, N
-  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};  // {W, H}: padding 1, 3x3 window (CUTLASS fprop: -pad, pad - (R-1))
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, lower, upper, kTcBlockK, kTcTileM, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(AZB_ERR_CUDA, "cuTensorMapEncodeIm2col failed");
-  return AZB_OK;
-}
-
 // TMA descriptor of a PADDED activation buffer [rows][128] for k_conv3x3_tc3: plain 2-D tiles of 64 channels x
 // 160 rows (a 128-row tile and its halo), SWIZZLE_128B, out-of-range rows zero-filled.
 int encode_act_map_rows(CUtensorMap* map, void* ptr, size_t bytes) {
@@ -381,13 +353,14 @@ uint32_t round_sim_budget(bool arena = false) {
 // also turns it off when the driver refuses programmatic edges inside a capture)
 bool g_tc_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
 
-// Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout),
-// 2 = k_conv3x3_tc2 (CTA pair, TMA im2col per tap, dense layout), default 3 = k_conv3x3_tc3 (CTA pair, the
-// tile fetched once and reused by all taps, padded layout).
+// Which tensor-core tower runs (AZB200_TC_PAIR): 0 = k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout: the
+// independent implementation the bit-equality test compares with), default 3 = k_conv3x3_tc3 (CTA pair, the tile fetched
+// once and reused by all taps, padded layout).  (Round 1's intermediate kernels — the TMA-im2col pair kernel and the 4-CTA
+// weight multicast — were measured slower and are gone; profiles/r1_nnet_forward.md keeps their numbers.)
 int tc_mode() {
   static const int mode = [] {
     const char* e = std::getenv("AZB200_TC_PAIR");
-    return e && e[0] == '0' ? 0 : (e && e[0] == '2' ? 2 : 3);
+    return e && e[0] == '0' ? 0 : 3;
   }();
   return mode;
 }
@@ -413,9 +386,10 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     if (net->act_map_ptr[i] != net->d_act[i].p || net->act_map_bytes[i] != net->d_act[i].bytes) {
       // a fresh buffer: the padded layout's zero rows / columns are zeroed here once and never written again
       AZB_CUDA(cudaMemsetAsync(net->d_act[i].p, 0, net->d_act[i].bytes, st));
-      const int rc = mode == 3 ? encode_act_map_rows(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes)
-                               : encode_act_map(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
-      if (rc) return rc;
+      if (mode == 3) {
+        const int rc = encode_act_map_rows(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
+        if (rc) return rc;
+      }
       net->act_map_ptr[i] = net->d_act[i].p;
       net->act_map_bytes[i] = net->d_act[i].bytes;
     }
@@ -427,32 +401,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes, st>>>(
       prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x, lay);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
-  // Optional (AZB200_TC_CLUSTER=1): clusters of kTcCluster CTAs share the weight tiles by multicast.
-  // Measured slower on B200 (533 vs 592 TFLOP/s at batch 8192): the kernel is bound by the bytes it can
-  // keep in flight through its shared-memory stages (Little's law at ~2 us L2 latency), not by L2
-  // traffic, and the multicast slices occupy the same stages; kept for the next layout (A reuse).
-  static const bool no_cluster = std::getenv("AZB200_TC_CLUSTER") == nullptr;
-  // how many clusters are co-resident (GPC sizes need not be multiples of the cluster size)
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
-    cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3(148u / kTcCluster * kTcCluster);
-    qc.blockDim = dim3(kTcThreads);
-    qc.dynamicSmemBytes = kTcSmemBytes;
-    cudaLaunchAttribute qa{};
-    qa.id = cudaLaunchAttributeClusterDimension;
-    qa.val.clusterDim.x = kTcCluster;
-    qa.val.clusterDim.y = 1;
-    qa.val.clusterDim.z = 1;
-    qc.attrs = &qa;
-    qc.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc<kTcCluster>, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    max_clusters = n;
-  }
-  const bool clustered = !no_cluster && max_clusters > 0 && tiles >= 2u * kTcCluster;
-  const unsigned grid = clustered ? std::min<uint32_t>((tiles + kTcCluster - 1) / kTcCluster, static_cast<uint32_t>(max_clusters)) * kTcCluster
-                                  : std::min<uint32_t>(tiles, 148u);
+  const unsigned grid = std::min<uint32_t>(tiles, 148u);
   // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
   // single-CTA kernel with streamed weight tiles.
   const bool use_pair = mode != 0;
@@ -462,10 +411,10 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   if (max_pairs < 0) {
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(148u);
-    qc.blockDim = dim3(kT2Threads);
-    qc.dynamicSmemBytes = kT2SmemBytes;
+    qc.blockDim = dim3(kTcThreads);
+    qc.dynamicSmemBytes = kT3SmemBytes;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc2, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, k_conv3x3_tc3, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
     max_pairs = n;
     if (std::getenv("AZB200_TIMING")) std::fprintf(stderr, "[azb200 nnet] co-resident CTA pairs: %d\n", n);
   }
@@ -475,34 +424,18 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
       while (mi < 2 && net->d_act[mi].p != a.in) ++mi;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2u * std::min<uint32_t>(pair_tiles, static_cast<uint32_t>(max_pairs)));
-      cfg.blockDim = dim3(mode == 3 ? kTcThreads : kT2Threads);
-      cfg.dynamicSmemBytes = mode == 3 ? kT3SmemBytes : kT2SmemBytes;
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = kT3SmemBytes;
       cfg.stream = st;
       cudaLaunchAttribute pdl{};  // overlap this layer's prologue + weight preload with the previous kernel's tail
       pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
       pdl.val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = &pdl;
       cfg.numAttrs = use_pdl ? 1 : 0;
-      return mode == 3 ? cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, a, net->act_map[mi])
-                       : cudaLaunchKernelEx(&cfg, k_conv3x3_tc2, a, net->act_map[mi]);
+      return cudaLaunchKernelEx(&cfg, k_conv3x3_tc3, a, net->act_map[mi]);
     }
-    if (!clustered) {
-      k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
-      return cudaGetLastError();
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = kTcSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = kTcCluster;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_conv3x3_tc<kTcCluster>, a);
+    k_conv3x3_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    return cudaGetLastError();
   };
   static unsigned long long* d_dbg = nullptr;  // AZB200_TC_DEBUG=1: role timers of the first conv launch
   if (!d_dbg && std::getenv("AZB200_TC_DEBUG")) {

@@ -375,23 +375,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tc(ConvTcArgs g) {
 // warp 9: TMEM allocation (cta_group::2: the same warp in both CTAs), then lane 0 preloads the weights
 // and is the TMA producer.
 // ================================================================================================
-#ifndef AZB_T2_STAGES
-#define AZB_T2_STAGES 5
-#endif
-constexpr int kT2Stages = AZB_T2_STAGES;
-#ifndef AZB_T2_STREAMS
-#define AZB_T2_STREAMS 2
-#endif
-// MMA streams per pair: stream k (its own issuing thread, warp 8 + 2k of the leader) owns the tiles
-// i = k (mod streams) of the pair and two of the 2 x streams TMEM accumulators.  One thread spends
-// ~390 cycles per k-block on waits, 4 x UTCHMMA issue and the commit against 256 cycles of tensor work;
-// two threads on different schedulers overlap that.
-constexpr int kT2Streams = AZB_T2_STREAMS;
-constexpr int kT2Accs = 2 * kT2Streams;
-constexpr int kT2Threads = 320 + 64 * (kT2Streams - 1);
 constexpr uint32_t kT2WTile = 64 * 128;                    // one k-block of the CTA's 64 output channels
-constexpr uint32_t kT2WBytes = kTcKBlocks * kT2WTile;      // 147456
-constexpr uint32_t kT2SmemBytes = kT2WBytes + kT2Stages * kTcTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kT2WBytes = kTcKBlocks * kT2WTile;      // 147456: a CTA's resident half of a layer's weights
 constexpr int kT2PairRows = 2 * kTcTileM;
 constexpr uint32_t kIdescBf16M256N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 
@@ -426,229 +411,6 @@ __device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t ct
                "h"(cta_mask)
                : "memory");
 }
-// 128 consecutive base pixels starting at (w, h, n) of the bounding box, tap offset (off_w, off_h),
-// channels [c, c + 64): 16 KB into `dst`; completes on `mbar_cluster` (may live in the pair's leader).
-__device__ __forceinline__ void tma_im2col_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t mbar_cluster, int c, int w, int h,
-                                                int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
-k_conv3x3_tc2(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-B alignment
-  auto w_tile = [&](int kb) { return base + kb * kT2WTile; };
-  auto stage_a = [&](int s) { return base + kT2WBytes + s * kTcTileBytes; };
-  const uint32_t bars = base + kT2WBytes + kT2Stages * kTcTileBytes;
-  auto bar_full = [&](int s) { return bars + 8u * s; };              // leader: 1 arrival (its expect_tx) + 2 x 16 KB of TMA bytes
-  auto bar_empty = [&](int s) { return bars + 80u + 8u * s; };       // 1 arrival: the pair's MMAs have read the stage
-  auto bar_acc_full = [&](int a) { return bars + 120u + 8u * a; };   // 1 arrival: the tile's MMAs are done (kT2Accs of them)
-  auto bar_acc_empty = [&](int a) { return bars + 152u + 8u * a; };  // leader: 512 arrivals (both CTAs' 8 epilogue warps)
-  const uint32_t bar_w_full = bars + 184u;
-  const uint32_t bar_w_peer = bars + 192u;                           // leader: the peer's weights are resident
-  const uint32_t tmem_slot = bars + 200u;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
-  const uint32_t rows = n_pos * kCells;
-  const uint32_t n_tiles = (rows + kT2PairRows - 1) / kT2PairRows;  // pair tiles of 256 rows
-  // tiles of this pair (the same number in both CTAs of a pair); groups of kT2Streams consecutive ones advance together
-  const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;
-  // Each stream owns its own ring of A stages (stream 0: 3 of the 5, stream 1: 2): k-block kb of the stream's
-  // j-th tile is the stream's item j * 18 + kb, in slot base + item % depth with phase parity (item / depth) & 1.
-  // (A ring shared by both streams would let a stream wait on a slot whose previous phase — the other stream's
-  // item — has not completed yet; a parity wait two phases early returns at once.  TMA copies complete out of order.)
-  auto ring_base = [&](uint32_t stream) { return kT2Streams == 1 ? 0u : (stream == 0u ? 0u : static_cast<uint32_t>(kT2Stages + 1) / 2u); };
-  auto ring_depth = [&](uint32_t stream) {
-    return kT2Streams == 1 ? static_cast<uint32_t>(kT2Stages)
-                           : (stream == 0u ? static_cast<uint32_t>(kT2Stages + 1) / 2u : static_cast<uint32_t>(kT2Stages) / 2u);
-  };
-  auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kT2PairRows + rank * kTcTileM; };
-  const bool dbg_on = g.dbg != nullptr && blockIdx.x < 2;
-  unsigned long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
-  long long dbg_c = 0;
-#define AZB_DBG_T0() do { if (dbg_on) dbg_c = clock64(); } while (0)
-#define AZB_DBG_ADD(k) do { if (dbg_on) { const long long n_ = clock64(); dbg_t[k] += n_ - dbg_c; dbg_c = n_; } } while (0)
-  const long long dbg_start = dbg_on ? clock64() : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kT2Stages; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
-    }
-    for (int a = 0; a < kT2Accs; ++a) {
-      mbar_init(bar_acc_full(a), 1);
-      mbar_init(bar_acc_empty(a), 512);
-    }
-    mbar_init(bar_w_full, 1);
-    mbar_init(bar_w_peer, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
-  }
-  if (warp == 9) {  // kT2Accs accumulators x 128 fp32 columns, in both CTAs' TMEM
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u * kT2Accs) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely / multicasts into them
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as SMs free up (they set
-  // up barriers / TMEM and preload THEIR weights, which depend on nothing); everything that touches the
-  // activations first waits for the previous layer to have completed (griddepcontrol.wait below).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  if (warp < 8) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    // ===== epilogue, 8 warps: own TMEM lanes (the CTA's 128 rows) -> bias / residual / ReLU -> bf16 -> HBM.
-    // A warp reads the TMEM lane quarter warp % 4; warps 0-3 take output channels 0-63, warps 4-7 64-127 =====
-    const int q = warp & 3, half = warp >> 2;
-    for (uint32_t ti = 0; ti < iters; ++ti) {
-      const uint32_t a = ti % kT2Accs;
-      AZB_DBG_T0();
-      mbar_wait(bar_acc_full(a), (ti / kT2Accs) & 1u);
-      AZB_DBG_ADD(0);
-      tc_fence_after();
-      const uint32_t m = row0_of(ti) + q * 32 + lane;
-      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + ch * 32u, acc);
-        if (m < rows) {
-          const float* bias = g.bias + ch * 32;
-          uint32_t packed[16];
-          uint4 res[4];
-          if (g.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + ch * 32);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) res[jj] = rp[jj];
-          }
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            float x0 = __uint_as_float(acc[2 * jj]) + bias[2 * jj];
-            float x1 = __uint_as_float(acc[2 * jj + 1]) + bias[2 * jj + 1];
-            if (g.residual) {
-              const uint32_t rw = reinterpret_cast<const uint32_t*>(res)[jj];
-              x0 += __uint_as_float(rw << 16);
-              x1 += __uint_as_float(rw & 0xFFFF0000u);
-            }
-            x0 = fmaxf(x0, 0.0f);
-            x1 = fmaxf(x1, 0.0f);
-            const __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
-            packed[jj] = *reinterpret_cast<const uint32_t*>(&p2);
-          }
-          uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + ch * 32);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) op[jj] = make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive_cluster(bar_acc_empty(a), 0u);  // the leader issues the MMAs that overwrite accumulator a
-      AZB_DBG_ADD(1);
-    }
-    if (dbg_on && threadIdx.x == 128) { g.dbg[rank * 16 + 2] = dbg_t[0]; g.dbg[rank * 16 + 3] = dbg_t[1]; }
-  } else if (warp == 8 || (kT2Streams > 1 && warp == 10)) {
-    const uint32_t stream = warp == 8 ? 0u : 1u;
-    if (lane == 0 && iters > 0) {
-      AZB_DBG_T0();
-      mbar_wait(bar_w_full, 0u);  // my half of the weights is resident
-      if (rank == 1) {
-        if (stream == 0u) mbar_arrive_cluster(bar_w_peer, 0u);
-      } else {
-        // ===== MMA issuer of one stream of the pair: ONE thread, nothing but waits, MMAs and commits.
-        // The producer interleaves the streams' k-blocks: ring item (group * 18 + kb) * streams + stream =====
-        mbar_wait(bar_w_peer, 0u);
-        AZB_DBG_ADD(5);
-        for (uint32_t ti = stream; ti < iters; ti += kT2Streams) {
-          const uint32_t a = ti % kT2Accs;
-          AZB_DBG_T0();
-          mbar_wait(bar_acc_empty(a), ((ti / kT2Accs) & 1u) ^ 1u);
-          AZB_DBG_ADD(1);
-          for (int kb = 0; kb < kTcKBlocks; ++kb) {
-            const uint32_t it = (ti / kT2Streams) * kTcKBlocks + kb, depth = ring_depth(stream);
-            const int s = static_cast<int>(ring_base(stream) + it % depth);
-            AZB_DBG_T0();
-            mbar_wait(bar_full(s), (it / depth) & 1u);
-            AZB_DBG_ADD(0);
-            tc_fence_after();
-            AZB_DBG_ADD(2);
-            const uint64_t ad = umma_desc_sw128(stage_a(s)), bd = umma_desc_sw128(w_tile(kb));
-#pragma unroll
-            for (int k = 0; k < kTcBlockK / 16; ++k)
-              umma2_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
-            AZB_DBG_ADD(3);
-            umma2_commit_multicast(bar_empty(s), 3u);  // frees the stage in both CTAs
-            if (kb == kTcKBlocks - 1) umma2_commit_multicast(bar_acc_full(a), 3u);
-            AZB_DBG_ADD(4);
-          }
-        }
-        if (dbg_on && stream == 0u) for (int k = 0; k < 6; ++k) g.dbg[4 + k] = dbg_t[k];
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    if (lane == 0 && iters > 0) {
-      // ===== weight preload: this CTA's 64 output channels of all 18 k-blocks, once per launch =====
-      mbar_arrive_expect_tx(bar_w_full, kT2WBytes);
-      for (int kb = 0; kb < kTcKBlocks; ++kb)
-        tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w_full);
-      // ===== A producer: one im2col TMA per k-block and tile for this CTA's 128 rows; the tiles of a
-      // group (one per stream) advance together, k-block by k-block =====
-      asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
-      for (uint32_t i0 = 0; i0 < iters; i0 += kT2Streams) {
-        const int cnt = static_cast<int>(min(static_cast<uint32_t>(kT2Streams), iters - i0));
-        int n[kT2Streams], h[kT2Streams], w[kT2Streams];
-#pragma unroll
-        for (int st = 0; st < kT2Streams; ++st) {
-          const uint32_t row0 = row0_of(i0 + st);
-          const int cell = static_cast<int>(row0 % kCells);
-          n[st] = static_cast<int>(row0 / kCells);
-          h[st] = cell / 7 - 1;  // base pixel in bounding-box coordinates (lower corner -1)
-          w[st] = cell % 7 - 1;
-        }
-        for (int kb = 0; kb < kTcKBlocks; ++kb) {
-          const int tap = kb >> 1;
-#pragma unroll
-          for (int st = 0; st < kT2Streams; ++st) {
-            if (st >= cnt) break;
-            const uint32_t it = (i0 / kT2Streams) * kTcKBlocks + kb, depth = ring_depth(st);  // the stream's own item counter
-            const int s = static_cast<int>(ring_base(st) + it % depth);
-            AZB_DBG_T0();
-            mbar_wait(bar_empty(s), ((it / depth) & 1u) ^ 1u);
-            AZB_DBG_ADD(0);
-            if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2u * kTcTileBytes);  // both CTAs' copies land on this barrier
-            tma_im2col_pair(stage_a(s), &tmap_in, map_to_cta(bar_full(s), 0u), (kb & 1) * kTcBlockK, w[st], h[st], n[st],
-                            static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
-            AZB_DBG_ADD(1);
-          }
-        }
-      }
-      if (dbg_on) { g.dbg[rank * 16 + 0] = dbg_t[0]; g.dbg[rank * 16 + 1] = dbg_t[1]; }
-    }
-    __syncwarp();
-  }
-
-  if (dbg_on && threadIdx.x == 0) { g.dbg[rank * 16 + 11] = clock64() - dbg_start; g.dbg[rank * 16 + 12] = iters; }
-#undef AZB_DBG_T0
-#undef AZB_DBG_ADD
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair's MMAs / remote arrivals may still be in flight
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u * kT2Accs) : "memory");
-}
-
-// Where a (position, board row y, column x) lives in an activation buffer [row][128 channels]:
-//   dense  : row = pos * 42 + y * 7 + x                      (k_conv3x3_tc<1>, k_conv3x3_tc2)
-//   padded : row = pos * 56 + y * 8 + x, column 7 and board row 6 of every position are ZERO rows that
-//            nobody ever writes: a tap (dy, dx) of the 3x3 window is then the plain row shift dy * 8 + dx,
-//            zero padding included (k_conv3x3_tc3).
 struct ActLayout {
   uint32_t pos_rows, pitch;  // 42, 7 or 56, 8
   __host__ __device__ size_t row(uint32_t pos, int y, int x) const { return static_cast<size_t>(pos) * pos_rows + y * pitch + x; }

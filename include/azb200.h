@@ -194,7 +194,11 @@ int azb_coach_export_samples(azb_coach* c, float* boards, float* pis, float* vs,
  * policy head conv1x1(128->2)+ReLU+FC(84->7)+softmax, value head conv1x1(128->1)+ReLU+
  * FC(42->64)+ReLU+FC(64->1)+tanh; BatchNorm folded into the conv bias.
  * ------------------------------------------------------------------------------------- */
-#define AZB_NNET_BF16_TC 0 /* bf16 weights/activations, fp32 accumulate, tcgen05 tensor cores */
+#define AZB_NNET_BF16_TC 0 /* bf16 weights/activations, fp32 accumulate, tcgen05 tensor cores.  Stated tolerance against
+                             * the fp32 path of the same weights (13 layers of bf16 rounding): |pi - pi32| <= 5e-2 and
+                             * |v - v32| <= 5e-2 per element, mean absolute error <= 2e-3 (pi) / 4e-3 (v); every tower layer
+                             * is within 1 bf16 ulp of a float64 convolution of the same bf16 inputs
+                             * (tests/test_nnet_gpu.py, tests/test_train_blocks_gpu.py).  Results do not depend on the batch. */
 #define AZB_NNET_FP32 1    /* fp32 reference path on CUDA cores (pins the numerics) */
 typedef struct azb_nnet_config {
   int32_t device;

@@ -1,8 +1,4 @@
-# round-2 GPU job 16: full GPU suite + bench (3 deep, 32 warps per SM) + smoke
+# round-2 GPU job 10: config 3 in wave mode (K = 2, 4, 8), config 2 tail with waves
 mkdir -p gpurun_out
-T="--timeout=300 --timeout-method=thread"
-timeout 700 python -m pytest tests -m gpu -q $T > gpurun_out/j16_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/j16_tests.log
-tail -5 gpurun_out/j16_tests.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/j16_bench.log 2> gpurun_out/j16_bench.err; tail -c 400 gpurun_out/j16_bench.log; tail -5 gpurun_out/j16_bench.err
-timeout 200 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -c 500
+for K in 1 2 4 8; do AZB200_BENCH_THREADS=$K AZB200_ROUND_TIMES=1 timeout 120 python scripts/bench_configs.py config3 2>&1 | tail -12 | cut -c1-420; done > gpurun_out/j10_c3_waves.log 2>&1
+cat gpurun_out/j10_c3_waves.log
