@@ -16,11 +16,15 @@ constexpr int kWarpsPerCta = AZB_WARPS_PER_CTA;
 // Resident warps per SM: 28 at 72 registers, 32 at 64, 36 at 56.  The persistent self-play kernel runs at 32: with
 // consecutive batches overlapped the device is full, and four more warps per SM hide more latency than the 8 registers
 // cost (measured, 8 batches three deep: 74.7 ms per batch at 32, 78.5 at 28, 83.4 at 36; one batch alone 108 vs 106 ms).
-// The round kernel keeps 28 (it already spills at 72).
+// The round kernel keeps 28: config 3 measured 3.46-3.54 s at 28, 32, 36 and 40 alike (AZB_ROUND_WARPS_PER_SM; it spills
+// 192 bytes at 72 registers, 336 at 64) — a round is bounded by cold tree loads, not by resident warps.
 #ifndef AZB_WARPS_PER_SM
 #define AZB_WARPS_PER_SM 32
 #endif
-constexpr int kCtasPerSm = 28 / kWarpsPerCta;                    // k_round, k_mcts_search
+#ifndef AZB_ROUND_WARPS_PER_SM
+#define AZB_ROUND_WARPS_PER_SM 28
+#endif
+constexpr int kCtasPerSm = AZB_ROUND_WARPS_PER_SM / kWarpsPerCta;  // k_round, k_mcts_search
 constexpr int kPlayCtasPerSm = AZB_WARPS_PER_SM / kWarpsPerCta;  // k_selfplay
 constexpr int kMaxPlies = 42;   // the board has 42 cells
 constexpr int kTraceStride = 64;
