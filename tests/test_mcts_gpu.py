@@ -39,6 +39,25 @@ def test_root_search_matches_oracle(azb, oracle, quirks, evaluator, sims):
     compare_tree(m, o)
 
 
+@pytest.mark.parametrize("temp", [0.5, 2.0, 0.25])
+def test_generic_temperature_within_tolerance(azb, oracle, temp):
+    """get_action_prob with a temperature other than 0 / 1 (async_mcts.rs:108-113: counts^(1/temp), normalised).  The
+    coach only ever passes 1 or 0 (coach.rs:122-126); this form goes through powf on both sides (CUDA's vs libm's), so it
+    is pinned by tolerance, not by bits: 2e-6 relative on every probability, the counts themselves stay bit-exact, and the
+    vector against a float64 restatement from those counts."""
+    root = oracle.init_board(1)
+    m = azb.AsyncMcts(1, num_sims=200, quirks=0, evaluator=1, mcts_reserve_size=100000)
+    o = oracle.Mcts(num_sims=200, quirks=0, evaluator=1)
+    ca, pa = m.get_action_prob(root, temp)
+    cb, pb = o.get_action_prob(root, temp)
+    assert ca[0].tolist() == cb.tolist()
+    want = ca[0].astype(np.float64) ** (1.0 / temp)
+    want /= want.sum()
+    assert np.abs(pa[0] - pb).max() <= 2e-6 * max(1.0, float(pb.max()))
+    assert np.abs(pa[0] - want).max() <= 2e-6
+    assert abs(float(pa[0].sum()) - 1.0) < 1e-5
+
+
 def test_survey_golden_on_device(azb, oracle):
     import json, os
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_vectors.json")))
