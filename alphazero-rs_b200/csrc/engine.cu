@@ -444,7 +444,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   }
   for (int blk = 0; blk < net->L.R; ++blk) {
     ConvTcArgs a{};
-    a.dbg = blk == 0 ? d_dbg : nullptr;
+    a.dbg = nullptr;
     a.count = d_count;
     a.max_batch = max_batch;
     a.in = x; a.residual = nullptr; a.out = y;
@@ -453,7 +453,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     a.bias = prm + net->L.tower_b + (2 * blk) * kNetC;
     AZB_CUDA(launch_conv(a));
     a.in = y; a.residual = x; a.out = z;
-    a.dbg = nullptr;
+    a.dbg = blk == 0 ? d_dbg : nullptr;  // (the second launch: its predecessor is a convolution, as for 11 of the 12)
     a.w_tiles += static_cast<size_t>(kTcKBlocks) * kTcTileBytes;
     a.bias += kNetC;
     AZB_CUDA(launch_conv(a));
@@ -480,9 +480,10 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     if (printed++ == 4) {
       const char* names[16] = {"producer wait empty", "producer TMA issue", "epilogue wait acc_full", "epilogue work", "mma wait full",
                                "mma wait acc_empty", "mma fences", "mma issue (4 MMAs)", "mma commit", "mma wait weights",
-                               "relay fence+arrive", "kernel cycles", "tile iterations", "", "", ""};
+                               "epilogue done at", "kernel cycles", "tile iterations", "setup done at", "grid dependency met at",
+                               "first MMA at"};
       for (int r = 0; r < 2; ++r)
-        for (int k = 0; k < 13; ++k)
+        for (int k = 0; k < 16; ++k)
           if (h[r * 16 + k]) std::fprintf(stderr, "[azb200 tc2 rank %d] %-24s %llu\n", r, names[k], h[r * 16 + k]);
     }
   }

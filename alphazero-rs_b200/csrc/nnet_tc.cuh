@@ -386,6 +386,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 // shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+// one lane of a converged warp (the same lane every time it is called by the same warp)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0u;
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
@@ -439,7 +451,8 @@ constexpr int kT3StageRows = kTcTileM + 2 * kT3HaloRows;          // 160
 constexpr uint32_t kT3HalfBytes = kT3StageRows * 128;             // 20480: one channel half of a stage
 constexpr uint32_t kT3StageBytes = 2 * kT3HalfBytes;              // 40960
 constexpr int kT3Stages = 2;
-constexpr uint32_t kT3SmemBytes = kT2WBytes + kT3Stages * kT3StageBytes + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
+constexpr uint32_t kT3SmemBytes = kT2WBytes + kT3Stages * kT3StageBytes + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/ +
+                                  320 /*weight barriers, one per k-block and CTA*/;
 
 // UMMA descriptor of a 128-row K-major SWIZZLE_128B operand that starts at an arbitrary 128-byte row of a
 // 1024-byte aligned buffer: the base-offset field [49, 52) carries (start address >> 7) & 7.
@@ -489,9 +502,11 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   auto bar_full = [&](int s) { return bars + 8u * s; };              // leader: 1 arrival (its expect_tx) + 2 x 40 KB of TMA bytes
   auto bar_empty = [&](int s) { return bars + 16u + 8u * s; };       // 1 arrival: the pair's MMAs have read the stage
   auto bar_acc_full = [&](int a) { return bars + 32u + 8u * a; };    // 1 arrival: the tile's MMAs are done
-  auto bar_acc_empty = [&](int a) { return bars + 48u + 8u * a; };   // leader: 512 arrivals (both CTAs' 8 epilogue warps)
-  const uint32_t bar_w_full = bars + 64u;
-  const uint32_t bar_w_peer = bars + 72u;
+  auto bar_acc_empty = [&](int a) { return bars + 48u + 8u * a; };   // leader: 16 arrivals (one per epilogue warp of both CTAs)
+  // weights: one barrier per k-block (the first tile's MMAs start when the first 8 KB have landed, the other 136 KB
+  // arrive under them) and, on the leader, one more per k-block that the peer CTA's relay thread arrives on
+  auto bar_w = [&](int kb) { return bars + 768u + 8u * kb; };          // 1 arrival (expect_tx) + 8 KB of bulk-copy bytes
+  auto bar_w_peer = [&](int kb) { return bars + 768u + 144u + 8u * kb; };  // leader: 1 arrival from the peer's relay
   const uint32_t tmem_slot = bars + 80u;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));  // [128]
 
@@ -517,10 +532,12 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full(a), 1);
-      mbar_init(bar_acc_empty(a), 512);
+      mbar_init(bar_acc_empty(a), 16);
     }
-    mbar_init(bar_w_full, 1);
-    mbar_init(bar_w_peer, 1);
+    for (int kb = 0; kb < kTcKBlocks; ++kb) {
+      mbar_init(bar_w(kb), 1);
+      mbar_init(bar_w_peer(kb), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
   }
@@ -536,6 +553,7 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (dbg_on && threadIdx.x == 0) g.dbg[rank * 16 + 13] = clock64() - dbg_start;
 
   if (warp < 8) {
     // ===== epilogue, 8 warps: TMEM lane quarter warp % 4, output channels 64 * (warp / 4) .. + 63 =====
@@ -565,7 +583,10 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       uint32_t acc0[32], acc1[32];
       tmem_ld32x2(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + half * 64u, acc0, acc1);
       tc_fence_before();
-      mbar_arrive_cluster(bar_acc_empty(a), 0u);  // the accumulator is in registers: the next tile may overwrite it
+      __syncwarp();
+      // the accumulator is in registers: the next tile may overwrite it.  ONE arrival per warp: 512 per-thread arrivals
+      // on the leader's barrier (half of them remote) serialised into ~5 k cycles per tile once the MMA warp got faster
+      if (lane == 0) mbar_arrive_cluster(bar_acc_empty(a), 0u);
       if (real) {
         uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + half * 64);
 #pragma unroll
@@ -603,48 +624,74 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       }
       AZB_DBG_ADD(1);
     }
-    if (dbg_on && threadIdx.x == 128) { g.dbg[rank * 16 + 2] = dbg_t[0]; g.dbg[rank * 16 + 3] = dbg_t[1]; }
+    if (dbg_on && threadIdx.x == 128) {
+      g.dbg[rank * 16 + 2] = dbg_t[0];
+      g.dbg[rank * 16 + 3] = dbg_t[1];
+      g.dbg[rank * 16 + 10] = clock64() - dbg_start;
+    }
   } else if (warp == 8) {
-    if (lane == 0 && iters > 0) {
-      mbar_wait(bar_w_full, 0u);
-      if (rank == 1) {
-        mbar_arrive_cluster(bar_w_peer, 0u);
-      } else {
-        // ===== MMA issuer of the pair: per tile one wait, 18 k-blocks x 4 MMAs on shifted views of the stage, two commits =====
-        mbar_wait(bar_w_peer, 0u);
-        for (uint32_t ti = 0; ti < iters; ++ti) {
-          const uint32_t a = ti & 1u;
-          const int s = ti % kT3Stages;
-          AZB_DBG_T0();
-          mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
-          AZB_DBG_ADD(1);
-          mbar_wait(bar_full(s), (ti / kT3Stages) & 1u);
-          AZB_DBG_ADD(0);
-          tc_fence_after();
-#pragma unroll 1
-          for (int kb = 0; kb < kTcKBlocks; ++kb) {
-            const int tap = kb >> 1, shift = kT3HaloRows + (tap / 3 - 1) * 8 + (tap % 3 - 1);  // rows
-            const uint64_t ad = umma_desc_sw128_rows(stage_a(s, kb & 1) + shift * 128), bd = umma_desc_sw128(w_tile(kb));
+    if (iters > 0 && rank == 1) {
+      if (lane == 0) {
+        // relay: tell the leader's MMA warp, k-block by k-block, that this CTA's half of the weights has landed
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          mbar_wait(bar_w(kb), 0u);
+          mbar_arrive_cluster(bar_w_peer(kb), 0u);
+        }
+      }
+    } else if (iters > 0) {
+      // ===== MMA issuer of the pair: per tile one wait, 18 k-blocks x 4 MMAs on shifted views of the stage, two commits.
+      // The WHOLE warp runs the loop and one elected lane issues: every address below is warp-uniform and, with the
+      // k-block loop unrolled, a compile-time offset from two descriptors per tile.  (The first version ran the loop in
+      // one lane with the k-block loop rolled: ~35 dependent ALU instructions + a register-to-uniform move per k-block
+      // sat right at the 320 cycles the four MMAs take, and any addition to the loop made the issuing thread the limit.)
+      const bool me = elect_one_sync();
+      const bool dbg_mma = dbg_on && me;
+      for (uint32_t ti = 0; ti < iters; ++ti) {
+        const uint32_t a = ti & 1u;
+        const int s = ti % kT3Stages;
+        if (dbg_mma) dbg_c = clock64();
+        mbar_wait(bar_acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+        if (dbg_mma) { const long long n_ = clock64(); dbg_t[1] += n_ - dbg_c; dbg_c = n_; }
+        mbar_wait(bar_full(s), (ti / kT3Stages) & 1u);
+        if (dbg_mma) { const long long n_ = clock64(); dbg_t[0] += n_ - dbg_c; dbg_c = n_; }
+        tc_fence_after();
+        if (dbg_mma && ti == 0) g.dbg[15] = clock64() - dbg_start;
+        const uint64_t a0 = umma_desc_sw128(stage_a(s, 0)), b0 = umma_desc_sw128(w_tile(0));
+        const uint32_t acc = tmem_base + a * 128u;
 #pragma unroll
-            for (int k = 0; k < kTcBlockK / 16; ++k)
-              umma2_bf16(tmem_base + a * 128u, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          if (ti == 0) {  // first tile: k-block kb of the weights, both halves
+            if (dbg_mma) dbg_c = clock64();
+            mbar_wait(bar_w(kb), 0u);
+            mbar_wait(bar_w_peer(kb), 0u);
+            if (dbg_mma) { const long long n_ = clock64(); dbg_t[5] += n_ - dbg_c; dbg_c = n_; }
           }
-          AZB_DBG_ADD(3);
+          const int tap = kb >> 1, shift = kT3HaloRows + (tap / 3 - 1) * 8 + (tap % 3 - 1);  // rows
+          const uint64_t ad = a0 + static_cast<uint64_t>(((kb & 1) * kT3HalfBytes + shift * 128) >> 4);
+          const uint64_t bd = b0 + static_cast<uint64_t>((kb * kT2WTile) >> 4);
+#pragma unroll
+          for (int k = 0; k < kTcBlockK / 16; ++k)
+            if (me) umma2_bf16(acc, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
+        }
+        if (dbg_mma) { const long long n_ = clock64(); dbg_t[3] += n_ - dbg_c; dbg_c = n_; }
+        if (me) {
           umma2_commit_multicast(bar_empty(s), 3u);     // the stage may be refilled (both CTAs)
           umma2_commit_multicast(bar_acc_full(a), 3u);  // the accumulator is complete (both CTAs' epilogues)
-          AZB_DBG_ADD(4);
         }
-        if (dbg_on) for (int k = 0; k < 6; ++k) g.dbg[4 + k] = dbg_t[k];
+        if (dbg_mma) { const long long n_ = clock64(); dbg_t[4] += n_ - dbg_c; dbg_c = n_; }
       }
+      if (dbg_mma) for (int k = 0; k < 6; ++k) g.dbg[4 + k] = dbg_t[k];
     }
     __syncwarp();
   } else if (warp == 9) {
     if (lane == 0 && iters > 0) {
       // ===== weight preload (once per launch), then the A producer: two 2-D TMA copies per tile =====
-      mbar_arrive_expect_tx(bar_w_full, kT2WBytes);
-      for (int kb = 0; kb < kTcKBlocks; ++kb)
-        tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w_full);
+      for (int kb = 0; kb < kTcKBlocks; ++kb) {
+        mbar_arrive_expect_tx(bar_w(kb), kT2WTile);
+        tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w(kb));
+      }
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
+      if (dbg_on) g.dbg[rank * 16 + 14] = clock64() - dbg_start;
       for (uint32_t i = 0; i < iters; ++i) {
         const int s = i % kT3Stages;
         AZB_DBG_T0();
