@@ -686,10 +686,16 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
   } else if (warp == 9) {
     if (lane == 0 && iters > 0) {
       // ===== weight preload (once per launch), then the A producer: two 2-D TMA copies per tile =====
-      for (int kb = 0; kb < kTcKBlocks; ++kb) {
+      // An SM takes in ~64 bytes per clock, so the 144 KB of weights are ~2.3 k cycles of its inbound path: only the
+      // first kWFirst k-blocks go ahead of the grid dependency (they cover the wait and the first MMAs), the first
+      // activation tile follows as soon as the previous layer is complete, and the remaining weights stream in behind
+      // it, ahead of the MMAs that need them (a k-block is consumed in ~200 cycles and fetched in ~128).
+      constexpr int kWFirst = 6;
+      auto fetch_w = [&](int kb) {
         mbar_arrive_expect_tx(bar_w(kb), kT2WTile);
         tma_bulk_g2s(w_tile(kb), g.w_tiles + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w(kb));
-      }
+      };
+      for (int kb = 0; kb < kWFirst; ++kb) fetch_w(kb);
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous layer's output is complete and visible
       if (dbg_on) g.dbg[rank * 16 + 14] = clock64() - dbg_start;
       for (uint32_t i = 0; i < iters; ++i) {
@@ -702,6 +708,8 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
         const uint32_t full = map_to_cta(bar_full(s), 0u);
         tma_tile2d_pair(stage_a(s, 0), &tmap_in, full, 0, r0);
         tma_tile2d_pair(stage_a(s, 1), &tmap_in, full, kTcBlockK, r0);
+        if (i == 0)
+          for (int kb = kWFirst; kb < kTcKBlocks; ++kb) fetch_w(kb);
         AZB_DBG_ADD(1);
       }
       if (dbg_on) { g.dbg[rank * 16 + 0] = dbg_t[0]; g.dbg[rank * 16 + 1] = dbg_t[1]; }
