@@ -293,6 +293,7 @@ struct azb_nnet {
         AZB_CUDA(cudaMemcpy(d_wtiles.as<uint8_t>() + c * wtile_copy_bytes, tiles.data(), wtile_copy_bytes, cudaMemcpyHostToDevice));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3SmemBytes));
+      AZB_CUDA(cudaFuncSetAttribute(k_tower_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
       AZB_CUDA(cudaFuncSetAttribute(k_stem_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
       {
@@ -364,6 +365,11 @@ int tc_mode() {
   }();
   return mode;
 }
+
+// The forward pass's 2R convolutions as ONE launch (k_tower_tc3: position-aligned tiles, a CTA pair takes its tiles through
+// every layer) instead of 2R launches of k_conv3x3_tc3.  AZB200_TOWER=0 keeps the layer-by-layer launches (the training
+// step always uses them); both produce the same bits (tests/test_nnet_gpu.py).
+bool g_tower = !(std::getenv("AZB200_TOWER") && std::getenv("AZB200_TOWER")[0] == '0');
 
 // One dense forward pass over the first *d_count (or max_batch) positions.
 int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
@@ -442,7 +448,68 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     AZB_CUDA(cudaMalloc(&d_dbg, 32 * 8));
     AZB_CUDA(cudaMemset(d_dbg, 0, 32 * 8));
   }
-  for (int blk = 0; blk < net->L.R; ++blk) {
+  bool tower_done = false;
+  if (use_pair && max_pairs > 0 && g_tower && !d_dbg) {
+    static int tower_pairs = -1;  // co-resident CTA pairs of the tower kernel (it must fit the device in one wave)
+    if (tower_pairs < 0) {
+      cudaLaunchConfig_t qc{};
+      qc.gridDim = dim3(148u);
+      qc.blockDim = dim3(kTwThreads);
+      qc.dynamicSmemBytes = kTwSmemBytes;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, k_tower_tc3, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      tower_pairs = n;
+    }
+    if (tower_pairs > 0) {
+      TowerTcArgs t{};
+      for (int i = 0; i < 3; ++i) t.act[i] = net->d_act[i].as<__nv_bfloat16>();
+      t.w_tiles = net->d_wtiles.as<uint8_t>();
+      t.bias = prm + net->L.tower_b;
+      t.count = d_count;
+      t.max_batch = max_batch;
+      t.n_layers = 2 * net->L.R;
+      static unsigned long long* d_tdbg = nullptr;  // AZB200_TOWER_DEBUG=1: per-layer timeline of CTA 0
+      if (!d_tdbg && std::getenv("AZB200_TOWER_DEBUG")) {
+        AZB_CUDA(cudaMalloc(&d_tdbg, 256 * 8));
+        AZB_CUDA(cudaMemset(d_tdbg, 0, 256 * 8));
+      }
+      t.dbg = d_tdbg;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2u * std::min<uint32_t>((max_batch + kTwTilePos - 1) / kTwTilePos, static_cast<uint32_t>(tower_pairs)));
+      cfg.blockDim = dim3(kTwThreads);
+      cfg.dynamicSmemBytes = kTwSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1]{};
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = use_pdl ? 1 : 0;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower_tc3, t, net->act_map[0], net->act_map[1], net->act_map[2]);
+      if (e == cudaSuccess) {
+        tower_done = true;
+        if (net->L.R & 1) std::swap(x, z);  // where the last block left its output
+        if (d_tdbg) {
+          static int printed = 0;
+          if (printed++ == 4) {
+            unsigned long long h[256];
+            AZB_CUDA(cudaMemcpy(h, d_tdbg, sizeof(h), cudaMemcpyDeviceToHost));
+            std::fprintf(stderr, "[azb200 tower] CTA 0: %llu cycles, %llu tiles per layer; per layer (cycles since start): weights requested | "
+                                 "first tile may be fetched | first tile in | first tile issued | last tile issued | last accumulator | last stores issued | last tile published\n", h[0], h[1]);
+            for (int l = 0; l < t.n_layers && l < 31; ++l) {
+              std::fprintf(stderr, "[azb200 tower] layer %2d:", l);
+              for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %8llu", h[8 + l * 8 + k]);
+              std::fprintf(stderr, "\n");
+            }
+          }
+        }
+      } else {
+        cudaGetLastError();
+        g_tower = false;  // refused: layer by layer from here on
+        if (std::getenv("AZB200_TIMING")) std::fprintf(stderr, "[azb200 nnet] tower launch refused (%s): layer-by-layer kernels\n", cudaGetErrorString(e));
+      }
+    }
+  }
+  for (int blk = 0; blk < net->L.R && !tower_done; ++blk) {
     ConvTcArgs a{};
     a.dbg = nullptr;
     a.count = d_count;
@@ -710,7 +777,7 @@ struct RoundEngine {
     }
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
     if (use_graph) {
-      for (int attempt = 0; attempt < 2 && !graph_exec; ++attempt) {
+      for (int attempt = 0; attempt < 3 && !graph_exec; ++attempt) {
         cudaGraph_t graph = nullptr;
         bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
@@ -723,7 +790,9 @@ struct RoundEngine {
         if (!ok) {
           cudaGetLastError();
           graph_exec = nullptr;
-          if (attempt == 0 && g_tc_pdl) g_tc_pdl = false;  // programmatic edges refused inside a capture: plain edges
+          if (std::getenv("AZB200_TIMING")) std::fprintf(stderr, "[azb200 rounds] graph capture failed (tower %d, pdl %d)\n", int(g_tower), int(g_tc_pdl));
+          if (g_tower) g_tower = false;        // the cooperative tower launch refused inside a capture: layer-by-layer kernels
+          else if (g_tc_pdl) g_tc_pdl = false;  // programmatic edges refused inside a capture: plain edges
           else break;
         }
       }

@@ -727,6 +727,329 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
 }
 
 // ================================================================================================
+// The whole residual tower in ONE launch (forward pass of the leaf evaluator): k_conv3x3_tc3's tile pipeline inside a
+// loop over the 2R layers, on tiles that never need another CTA pair's rows.
+//
+// Why: at the sizes a search round produces (~1 k positions = 3 tiles per CTA pair) a layer of k_conv3x3_tc3 spends
+// ~13 k cycles in its MMAs and ~11 k around them (AZB200_TC_DEBUG / AZB200_TOWER_DEBUG timelines, profiles/r2_tower.md):
+// the launch boundary (a CTA fills the SM's shared memory, so the next layer's CTA cannot be resident before this one has
+// left), barrier / TMEM set-up, the wait for the whole previous grid, the first tile's fetch, and the last tile's epilogue
+// with nothing behind it.  A first version of this kernel kept the 256-row tiles and put a grid-wide arrive / wait on a
+// global counter between the layers: the boundary (stores -> fence -> atomic -> every other CTA -> acquire -> TMA) cost
+// the same ~6 k cycles as the kernel boundary it replaced.
+//
+// So the dependency itself is removed.  In the padded layout a position is 56 rows that end with a zero row, and a 3x3
+// tap never reaches across it: a tile that starts on a position boundary and holds whole positions depends on NOTHING
+// outside itself, in any layer.  A tile is therefore 4 positions = 224 rows of a 256-row MMA (rows 224..255 are computed
+// and dropped: 12.5 % more MMA work than k_conv3x3_tc3's dense tiling), a CTA pair owns its tiles through all 2R layers,
+// and the only ordering left is inside the pair: the epilogue warps of both CTAs publish "my part of tile i of layer L is
+// in global memory" (stores -> __threadfence -> fence.proxy.async.global -> a per-warp counter in both CTAs' shared
+// memory), and the producer lane waits for the 16 counters before it asks TMA for tile i of layer L + 1.  With two or more
+// tiles per pair that wait is already over when the pipeline gets there.  No grid barrier, no cooperative launch, pairs
+// drift apart freely; set-up happens once; the next layer's first weight k-blocks are requested the moment the current
+// layer's last MMA has retired and land under the last tile's epilogue.
+// Phases of the tile barriers continue across layers (global tile number G = layer * iters + tile); the weight barriers
+// complete one phase per layer.  Results are bit-identical to the layer-by-layer kernels (same K order per output row).
+// ================================================================================================
+constexpr uint32_t kTwTilePos = 4;                                  // positions per tile
+constexpr uint32_t kTwTileRows = kTwTilePos * 56;                   // 224 rows are kept of the 256 computed
+struct TowerTcArgs {
+  __nv_bfloat16* act[3];   // padded activation buffers; act[0] holds the stem's output, the result is in act[R odd ? 2 : 0]
+  const uint8_t* w_tiles;  // layer l at + l * kTcKBlocks * kTcTileBytes
+  const float* bias;       // layer l at + l * 128
+  const uint32_t* count;   // positions this round (device), or nullptr
+  uint32_t max_batch;
+  int n_layers;            // 2 x residual blocks
+  unsigned long long* dbg; // [8 + 8 * n_layers] diagnostic timeline of CTA 0 (AZB200_TOWER_DEBUG=1), or nullptr
+};
+constexpr uint32_t kTwSmemBytes = kT3SmemBytes + 512 + 192;  // a second bias buffer (layers alternate), 18 + 4 more barriers
+constexpr int kTwThreads = kTcThreads + 32;                  // + the publisher warp
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// the smaller of two consecutive flags (one volatile read of this CTA's own shared memory: a cluster-scope load per flag
+// was measured at ~200 cycles)
+__device__ __forceinline__ uint32_t min2_volatile_shared(uint32_t cta_addr) {
+  uint32_t a, b;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(cta_addr) : "memory");
+  return min(a, b);
+}
+__device__ __forceinline__ void st_relaxed_cluster(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTwThreads, 1)
+k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+            const __grid_constant__ CUtensorMap map2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto w_tile = [&](int kb) { return base + kb * kT2WTile; };
+  auto stage_a = [&](int s, int half) { return base + kT2WBytes + s * kT3StageBytes + half * kT3HalfBytes; };
+  const uint32_t bars = base + kT2WBytes + kT3Stages * kT3StageBytes;
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 16u + 8u * s; };
+  auto bar_acc_full = [&](int a) { return bars + 32u + 8u * a; };
+  auto bar_acc_empty = [&](int a) { return bars + 48u + 8u * a; };
+  const uint32_t tmem_slot = bars + 80u;
+  const uint32_t done_w = bars + 128u;  // [2] u32 (16 bytes apart): tiles below this global number are in global memory, CTA r's rows at [4 r]
+  auto bar_st = [&](uint32_t G) { return bars + 1744u + 8u * (G & 3u); };  // 8 arrivals: the epilogue warps have issued tile G's stores
+  auto bar_w = [&](int kb) { return bars + 768u + 8u * kb; };
+  auto bar_w_peer = [&](int kb) { return bars + 768u + 144u + 8u * kb; };
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));    // bias of the even layers
+  float* s_bias1 = reinterpret_cast<float*>(smem_raw + (bars + 1088u - smem_u32(smem_raw)));  // ... of the odd layers
+  auto bar_w_free = [&](int kb) { return bars + 1600u + 8u * kb; };  // 1 arrival per layer: its last tile is done with k-block kb
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
+  const uint32_t rows = n_pos * kActPadded.pos_rows;
+  const uint32_t n_tiles = (n_pos + kTwTilePos - 1) / kTwTilePos;
+  const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;
+  auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kTwTileRows + rank * kTcTileM; };
+  const bool dbg_on = g.dbg != nullptr && blockIdx.x == 0;
+  const long long t_start = dbg_on ? clock64() : 0;
+  // diagnostic timeline of CTA 0 (AZB200_TOWER_DEBUG=1): g.dbg[8 + layer * 8 + k], cycles since the CTA started
+#define AZB_TW_MARK(k) do { if (dbg_on) g.dbg[8 + layer * 8 + (k)] = clock64() - t_start; } while (0)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kT3Stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full(a), 1);
+      mbar_init(bar_acc_empty(a), 16);
+    }
+    for (int kb = 0; kb < kTcKBlocks; ++kb) {
+      mbar_init(bar_w(kb), 1);
+      mbar_init(bar_w_peer(kb), 1);
+      mbar_init(bar_w_free(kb), 1);
+    }
+    for (uint32_t r = 0; r < 4u; ++r) mbar_init(bar_st(r), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map2)) : "memory");
+  }
+  if (threadIdx.x < 16) asm volatile("st.shared.u32 [%0], %1;" ::"r"(done_w + 4u * threadIdx.x), "r"(0u) : "memory");
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // buffer rotation of the residual blocks: conv1 reads X writes Y; conv2 reads Y, adds X, writes Z; then X <-> Z
+  auto in_of = [&](int layer) { const int b = layer >> 1; return (layer & 1) ? 1 : ((b & 1) ? 2 : 0); };
+  auto out_of = [&](int layer) { const int b = layer >> 1; return (layer & 1) ? ((b & 1) ? 0 : 2) : 1; };
+  auto res_of = [&](int layer) { const int b = layer >> 1; return (b & 1) ? 2 : 0; };  // conv2 only
+
+  if (iters == 0) {
+    // nothing to do for this pair
+  } else if (warp < 8) {
+    // ===== epilogue, 8 warps: TMEM lane quarter warp % 4, output channels 64 * (warp / 4) .. + 63 =====
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int q = warp & 3, half = warp >> 2;
+    const bool kept = rank * kTcTileM + q * 32 + lane < kTwTileRows;  // rows 224..255 of the MMA tile belong to the next tile
+    for (int layer = 0; layer < g.n_layers; ++layer) {
+      float* sb = (layer & 1) ? s_bias1 : s_bias;
+      if (threadIdx.x < kNetC) sb[threadIdx.x] = g.bias[layer * kNetC + threadIdx.x];
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the layer's bias is in place (and everyone has left layer - 1)
+      const __nv_bfloat16* residual = (layer & 1) ? g.act[res_of(layer)] : nullptr;
+      __nv_bfloat16* out = g.act[out_of(layer)];
+      for (uint32_t ti = 0; ti < iters; ++ti) {
+        const uint32_t G = static_cast<uint32_t>(layer) * iters + ti, a = G & 1u;
+        const uint32_t m = row0_of(ti) + q * 32 + lane;        // padded row
+        const uint32_t rem = m % kActPadded.pos_rows;
+        const bool real = kept && m < rows && (rem & 7u) != 7u && rem < 48u;  // not the zero column, not the zero row
+        uint4 res[8];
+        if (real && residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * kNetC + half * 64);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
+        }
+        mbar_wait(bar_acc_full(a), (G >> 1) & 1u);
+        if (ti + 1 == iters && threadIdx.x == 0) AZB_TW_MARK(5);  // last accumulator complete
+        tc_fence_after();
+        uint32_t acc0[32], acc1[32];
+        tmem_ld32x2(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128u + half * 64u, acc0, acc1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_acc_empty(a), 0u);  // one arrival per warp: the accumulator is in registers
+        if (real) {
+          uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + half * 64);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t* acc = c8 < 4 ? acc0 : acc1;
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + half * 64 + c8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sb + half * 64 + c8 * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const uint32_t rw[4] = {res[c8].x, res[c8].y, res[c8].z, res[c8].w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e]) + bb[2 * e];
+              float x1 = __uint_as_float(acc[(c8 & 3) * 8 + 2 * e + 1]) + bb[2 * e + 1];
+              if (residual) {
+                x0 += __uint_as_float(rw[e] << 16);
+                x1 += __uint_as_float(rw[e] & 0xFFFF0000u);
+              }
+              const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+              pk[e] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+            op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        // My stores of this tile are issued: tell the publisher warp (a CTA-scope release; the GPU-scope fence that makes
+        // them visible to the pair's TMA reads costs ~2 k cycles, MEMBAR.GPU + CCTL.IVALL, and is the publisher's to pay —
+        // on the epilogue warps it made them, not the tensor pipe, the tile period).
+        if (layer + 1 < g.n_layers) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_st(G));
+        }
+        if (ti + 1 == iters && threadIdx.x == 0) AZB_TW_MARK(6);  // last tile's stores issued
+      }
+    }
+  } else if (warp == 8) {
+    if (rank == 1) {
+      if (lane == 0) {
+        // relay: tell the leader's MMA warp, k-block by k-block and layer by layer, that this CTA's half of the weights is in
+        for (int layer = 0; layer < g.n_layers; ++layer)
+          for (int kb = 0; kb < kTcKBlocks; ++kb) {
+            mbar_wait(bar_w(kb), layer & 1);
+            mbar_arrive_cluster(bar_w_peer(kb), 0u);
+          }
+      }
+    } else {
+      // ===== MMA issuer of the pair (the whole warp runs the loop, one elected lane issues) =====
+      const bool me = elect_one_sync();
+      for (int layer = 0; layer < g.n_layers; ++layer) {
+        for (uint32_t ti = 0; ti < iters; ++ti) {
+          const uint32_t G = static_cast<uint32_t>(layer) * iters + ti, a = G & 1u;
+          const int s = static_cast<int>(G & 1u);
+          mbar_wait(bar_acc_empty(a), ((G >> 1) & 1u) ^ 1u);
+          mbar_wait(bar_full(s), (G >> 1) & 1u);
+          tc_fence_after();
+          if (ti == 0 && me) AZB_TW_MARK(2);  // first activation tile in
+          const uint64_t a0 = umma_desc_sw128(stage_a(s, 0)), b0 = umma_desc_sw128(w_tile(0));
+          const uint32_t acc = tmem_base + a * 128u;
+#pragma unroll
+          for (int kb = 0; kb < kTcKBlocks; ++kb) {
+            if (ti == 0) {  // first tile of the layer: k-block kb of its weights, both halves
+              mbar_wait(bar_w(kb), layer & 1);
+              mbar_wait(bar_w_peer(kb), layer & 1);
+            }
+            const int tap = kb >> 1, shift = kT3HaloRows + (tap / 3 - 1) * 8 + (tap % 3 - 1);  // rows
+            const uint64_t ad = a0 + static_cast<uint64_t>(((kb & 1) * kT3HalfBytes + shift * 128) >> 4);
+            const uint64_t bd = b0 + static_cast<uint64_t>((kb * kT2WTile) >> 4);
+#pragma unroll
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              if (me) umma2_bf16(acc, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128, (kb | k) ? 1u : 0u);
+            // the layer's last tile hands the weights back k-block by k-block: the next layer's stream in under it
+            if (me && ti + 1 == iters && layer + 1 < g.n_layers) umma2_commit_multicast(bar_w_free(kb), 3u);
+          }
+          if (me) {
+            umma2_commit_multicast(bar_empty(s), 3u);     // the stage may be refilled (both CTAs)
+            umma2_commit_multicast(bar_acc_full(a), 3u);  // the accumulator is complete (both CTAs' epilogues)
+            if (ti == 0) AZB_TW_MARK(3);          // first tile issued (its MMAs wait for the weights k-block by k-block)
+            if (ti + 1 == iters) AZB_TW_MARK(4);  // last tile issued
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ===== publisher: "this CTA's rows of every tile below G are in global memory", for the pair's two producers =====
+      // The eight epilogue warps' stores happen-before their arrivals, the arrivals before this thread's wait, and the
+      // cluster-scope fence is cumulative over all of it; the flag stores follow the fence.
+      const uint32_t own_flag = map_to_cta(done_w + 4u * rank, rank), peer_flag = map_to_cta(done_w + 4u * rank, rank ^ 1u);
+      for (int layer = 0; layer + 1 < g.n_layers; ++layer)
+        for (uint32_t ti = 0; ti < iters; ++ti) {
+          const uint32_t G = static_cast<uint32_t>(layer) * iters + ti;
+          mbar_wait(bar_st(G), (G >> 2) & 1u);
+          fence_acq_rel_cluster();
+          st_relaxed_cluster(own_flag, G + 1u);
+          st_relaxed_cluster(peer_flag, G + 1u);
+          if (ti + 1 == iters) AZB_TW_MARK(7);  // (diagnostic: the layer's last tile published)
+        }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===== weights of every layer and the activation tiles =====
+      // Layer 0 as k_conv3x3_tc3 (six k-blocks, the grid dependency, the first tile, the other twelve).  From then on the
+      // first tile of a layer depends only on the same tile of the layer before, so it is requested while the previous
+      // layer's last tile is still in the tensor pipe, and the weights follow k-block by k-block as that tile lets go of
+      // them (with one tile per pair the weights go first: the tile has to wait for its own epilogue anyway).
+      constexpr int kWFirst = 6;
+      uint32_t seen = 0u;  // every epilogue warp of the pair has published the tiles below this global number
+      for (int layer = 0; layer < g.n_layers; ++layer) {
+        const uint8_t* wl = g.w_tiles + static_cast<size_t>(layer) * kTcKBlocks * kTcTileBytes;
+        auto fetch_w = [&](int kb) {
+          if (layer > 0) mbar_wait(bar_w_free(kb), (layer - 1) & 1);  // the previous layer's last MMA on this k-block has retired
+          mbar_arrive_expect_tx(bar_w(kb), kT2WTile);
+          tma_bulk_g2s(w_tile(kb), wl + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w(kb));
+        };
+        const int in_idx = in_of(layer);
+        const CUtensorMap* tm = in_idx == 0 ? &map0 : (in_idx == 1 ? &map1 : &map2);
+        auto fetch_tile = [&](uint32_t i) {
+          const uint32_t G = static_cast<uint32_t>(layer) * iters + i;
+          const int s = static_cast<int>(G & 1u);
+          if (layer > 0) {  // tile i of the previous layer is in global memory: all 16 epilogue warps of the pair said so
+            const uint32_t need = G - iters + 1u;
+            if (seen < need) {
+              do {
+                seen = min2_volatile_shared(done_w);
+              } while (seen < need);
+              fence_acq_rel_cluster();     // what the pair's epilogue warps stored before the flags is visible to this thread ...
+              fence_proxy_async_global();  // ... and to the TMA reads it issues from here on
+            }
+          }
+          if (i == 0) AZB_TW_MARK(1);  // first tile of the layer may be fetched
+          mbar_wait(bar_empty(s), ((G >> 1) & 1u) ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full(s), 2u * kT3StageBytes);  // both CTAs' copies land on this barrier
+          const int r0 = static_cast<int>(row0_of(i)) - kT3HaloRows;  // negative for the first tile: zero-filled
+          const uint32_t full = map_to_cta(bar_full(s), 0u);
+          tma_tile2d_pair(stage_a(s, 0), tm, full, 0, r0);
+          tma_tile2d_pair(stage_a(s, 1), tm, full, kTcBlockK, r0);
+        };
+        if (layer == 0) {
+          AZB_TW_MARK(0);
+          for (int kb = 0; kb < kWFirst; ++kb) fetch_w(kb);
+          asm volatile("griddepcontrol.wait;" ::: "memory");  // the stem's output is complete and visible
+          fetch_tile(0u);
+          for (int kb = kWFirst; kb < kTcKBlocks; ++kb) fetch_w(kb);
+        } else if (iters == 1u) {
+          for (int kb = 0; kb < kTcKBlocks; ++kb) fetch_w(kb);
+          AZB_TW_MARK(0);  // all weights requested
+          fetch_tile(0u);
+        } else {
+          fetch_tile(0u);
+          for (int kb = 0; kb < kTcKBlocks; ++kb) fetch_w(kb);
+          AZB_TW_MARK(0);  // all weights requested
+        }
+        for (uint32_t i = 1; i < iters; ++i) fetch_tile(i);
+      }
+    }
+    __syncwarp();
+  }
+  if (dbg_on && threadIdx.x == 0) { g.dbg[0] = clock64() - t_start; g.dbg[1] = iters; }
+#undef AZB_TW_MARK
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+// ================================================================================================
 // Weight gradient of the 3x3 convolution on tcgen05 (building block of the training step):
 //   dW[tap][ci][co] = sum over padded rows R of X[R + 8*dy + dx][ci] * dZ[R][co]
 // In the padded layout the zero rows contribute nothing, so this is one plain product per tap,
