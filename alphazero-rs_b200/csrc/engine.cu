@@ -449,7 +449,12 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     AZB_CUDA(cudaMemset(d_dbg, 0, 32 * 8));
   }
   bool tower_done = false;
-  if (use_pair && max_pairs > 0 && g_tower && !d_dbg) {
+  // The tower's position-aligned tiles cost 12.5 % more MMA work and save the 2R launch boundaries: measured faster up to
+  // ~3.5 k positions per pass (profiles/r2_tower.md: 191 vs 216 us at 1014, 305 vs 325 at 2028, 656 vs 645 at 4096).  A
+  // caller-sized batch decides by its size; a device-counted round (the search: ~1 k positions on average, 3.4 k at most
+  // with 8192 slots) takes the tower unless the slot count says the rounds will be large.
+  const bool tower_size = d_count ? max_batch <= 16384u : max_batch <= 3072u;
+  if (use_pair && max_pairs > 0 && g_tower && tower_size && !d_dbg) {
     static int tower_pairs = -1;  // co-resident CTA pairs of the tower kernel (it must fit the device in one wave)
     if (tower_pairs < 0) {
       cudaLaunchConfig_t qc{};

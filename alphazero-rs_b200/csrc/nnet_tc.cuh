@@ -484,6 +484,19 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, uint32_t (&r0)[32], 
       : "r"(taddr + 32u));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256).  The epilogue's rows are 256 bytes apart, one per lane, so a
+// warp-wide access touches 32 lines whatever its width: half as many accesses = half as many L1 wavefronts.
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
 __device__ __forceinline__ void tma_tile2d_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t mbar_cluster, int c, int row) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
@@ -569,12 +582,12 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       if (real && g.residual) {
         const uint4* rp = reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(m) * kNetC + half * 64);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
+        for (int jj = 0; jj < 8; jj += 2) ld_global_256(rp + jj, res[jj], res[jj + 1]);
       }
       if (real && g.mask) {
         const uint4* mp = reinterpret_cast<const uint4*>(g.mask + static_cast<size_t>(m) * kNetC + half * 64);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) msk[jj] = mp[jj];
+        for (int jj = 0; jj < 8; jj += 2) ld_global_256(mp + jj, msk[jj], msk[jj + 1]);
       }
       AZB_DBG_T0();
       mbar_wait(bar_acc_full(a), (ti >> 1) & 1u);
@@ -589,8 +602,9 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
       if (lane == 0) mbar_arrive_cluster(bar_acc_empty(a), 0u);
       if (real) {
         uint4* op = reinterpret_cast<uint4*>(g.out + static_cast<size_t>(m) * kNetC + half * 64);
+        uint4 prev = make_uint4(0u, 0u, 0u, 0u);  // an even chunk waits for the odd one: one 32-byte store per two chunks
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {  // 8 output channels per 16-byte store
+        for (int c8 = 0; c8 < 8; ++c8) {  // 8 output channels per 16-byte chunk
           const uint32_t* acc = c8 < 4 ? acc0 : acc1;
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c8 * 8);
           const float4 b1 = *reinterpret_cast<const float4*>(s_bias + half * 64 + c8 * 8 + 4);
@@ -619,7 +633,8 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
             const __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
             pk[e] = *reinterpret_cast<const uint32_t*>(&p2);
           }
-          op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (c8 & 1) st_global_256(op + c8 - 1, prev, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          else prev = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       AZB_DBG_ADD(1);
@@ -872,7 +887,7 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
         if (real && residual) {
           const uint4* rp = reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * kNetC + half * 64);
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) res[jj] = rp[jj];
+          for (int jj = 0; jj < 8; jj += 2) ld_global_256(rp + jj, res[jj], res[jj + 1]);
         }
         mbar_wait(bar_acc_full(a), (G >> 1) & 1u);
         if (ti + 1 == iters && threadIdx.x == 0) AZB_TW_MARK(5);  // last accumulator complete
@@ -884,6 +899,7 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
         if (lane == 0) mbar_arrive_cluster(bar_acc_empty(a), 0u);  // one arrival per warp: the accumulator is in registers
         if (real) {
           uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * kNetC + half * 64);
+          uint4 prev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
             const uint32_t* acc = c8 < 4 ? acc0 : acc1;
@@ -903,7 +919,8 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
               const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
               pk[e] = *reinterpret_cast<const uint32_t*>(&p2);
             }
-            op[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (c8 & 1) st_global_256(op + c8 - 1, prev, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            else prev = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         // My stores of this tile are issued: tell the publisher warp (a CTA-scope release; the GPU-scope fence that makes

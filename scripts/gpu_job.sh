@@ -1,10 +1,14 @@
-# round-2 GPU job 36: tower on position-aligned tiles, pair-local ordering only
+# round-2 GPU job 39: full GPU suite + smoke + bench with the tower on by size
 mkdir -p gpurun_out
-export AZB200_LIB=build/variants/lib_tower8.so
-timeout 300 python -m pytest tests/test_nnet_gpu.py -x -q --timeout=120 --timeout-method=thread 2>&1 | tail -5
-for b in 1014 338; do AZB200_TOWER_DEBUG=1 timeout 120 python -c "
-import importlib,sys; sys.path.insert(0,'.'); azb=importlib.import_module('alphazero-rs_b200'); n=azb.NNet(seed=7,blocks=6); print(n.benchmark($b,8))" 2>&1 | grep "tower\|^[0-9]"; done > gpurun_out/j36_timeline.log 2>&1
-cat gpurun_out/j36_timeline.log
-timeout 120 python scripts/forward_sweep.py 6 100 2>&1 | tail -8 > gpurun_out/j36_sweep_tower.log; cat gpurun_out/j36_sweep_tower.log
-AZB200_TOWER=0 timeout 120 python scripts/forward_sweep.py 6 100 2>&1 | tail -8 > gpurun_out/j36_sweep_layers.log; cat gpurun_out/j36_sweep_layers.log
-for t in 1 0 1 0; do echo -n "tower=$t "; AZB200_TOWER=$t AZB200_TIMING=1 timeout 120 python scripts/bench_configs.py config3 2>&1 | grep -i "capture failed\|device_s" | cut -c1-200; done
+timeout 900 python -m pytest tests -x -q -m gpu --timeout=400 --timeout-method=thread > gpurun_out/j39_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/j39_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/j39_bench.log 2> gpurun_out/j39_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/j39_bench.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/j39_bench.log') if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'])
+print('nnet_forward', d['nnet_forward'].get('ms_per_pass'), d['nnet_forward'].get('roofline',{}).get('frac'))
+c3=d['config3']; print('config3', c3.get('device_s'), c3.get('roofline',{}).get('frac'), c3.get('e2e',{}).get('value'))
+print('config4', d['config4'].get('device_s_max_over_ranks'), 'config5', {k:d['config5'].get(k) for k in ('wall_s_rank0','selfplay_s','train_s','arena_s')})
+print('cpu', d.get('cpu_baseline',{}).get('value'))
+PY

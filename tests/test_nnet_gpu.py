@@ -197,16 +197,23 @@ def test_arena_two_networks(azb, oracle):
     assert res.tolist() == res2.tolist()
 
 
-def test_pair_kernel_equals_single_cta_kernel(azb, oracle, tmp_path):
-    """k_conv3x3_tc2 (CTA pair, cta_group::2, TMA im2col, resident weights) and k_conv3x3_tc<1> (one CTA,
-    cp.async gather, streamed weights) accumulate every output in the same K order in fp32: the two
-    implementations of the tower must agree bit for bit (the kernel is chosen once per process, so the
-    single-CTA run happens in a child process with AZB200_TC_PAIR=0)."""
+@pytest.mark.parametrize("n_pos", [25, 301, 1500, 3500])
+def test_tower_implementations_agree_bit_for_bit(azb, oracle, tmp_path, n_pos):
+    """Three implementations of the 2R-convolution tower accumulate every output in the same K order in fp32 and must agree
+    bit for bit: k_tower_tc3 (one launch, position-aligned tiles, a CTA pair takes its tiles through all layers; the
+    default up to ~3 k positions), k_conv3x3_tc3 launched layer by layer (AZB200_TOWER=0; also what 3500 positions use by
+    default) and k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout, streamed weights: AZB200_TC_PAIR=0).  The kernels
+    are chosen once per process, so the other two run in child processes.  Sizes: one tile, a ragged last tile, five tiles per
+    CTA pair, and a batch above the tower's size limit."""
     import os, subprocess, sys
-    feats = random_features(oracle, 25)
+    rng = np.random.default_rng(n_pos)  # disjoint random stone sets (not necessarily reachable positions)
+    feats = (rng.random((n_pos, 2, 6, 7)) < 0.3).astype(np.float32)
+    feats[:, 1] *= 1.0 - feats[:, 0]
     np.save(tmp_path / "feats.npy", feats)
     net = azb.NNet(seed=11, blocks=3, precision=azb.NNET_BF16_TC)
     pi, v = net.predict(feats)
+    pi2, v2 = net.predict(feats)  # and the same bits twice (the tower's hand-over between layers is a race if it is wrong)
+    assert np.array_equal(pi.view(np.uint32), pi2.view(np.uint32)) and np.array_equal(v.view(np.uint32), v2.view(np.uint32))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
         "import importlib, sys, numpy as np\n"
@@ -217,11 +224,11 @@ def test_pair_kernel_equals_single_cta_kernel(azb, oracle, tmp_path):
         "pi, v = net.predict(feats)\n"
         f"np.save({str(tmp_path / 'pi.npy')!r}, pi); np.save({str(tmp_path / 'v.npy')!r}, v)\n"
     )
-    env = dict(os.environ, AZB200_TC_PAIR="0")
-    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
-    pi1, v1 = np.load(tmp_path / "pi.npy"), np.load(tmp_path / "v.npy")
-    assert np.array_equal(pi.view(np.uint32), pi1.view(np.uint32))
-    assert np.array_equal(v.view(np.uint32), v1.view(np.uint32))
+    for var in ({"AZB200_TOWER": "0"}, {"AZB200_TC_PAIR": "0"}):
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, **var), timeout=300)
+        pi1, v1 = np.load(tmp_path / "pi.npy"), np.load(tmp_path / "v.npy")
+        assert np.array_equal(pi.view(np.uint32), pi1.view(np.uint32)), var
+        assert np.array_equal(v.view(np.uint32), v1.view(np.uint32)), var
 
 
 def test_config3_parameters_sampled_games(azb, oracle):
