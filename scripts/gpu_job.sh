@@ -1,14 +1,13 @@
-# round-2 GPU job 39: full GPU suite + smoke + bench with the tower on by size
+# round-2 GPU job 40: durations of the three kernels of a forward pass (stem, tower, heads) at 64 / 1014 / 3000 positions
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu --timeout=400 --timeout-method=thread > gpurun_out/j39_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/j39_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/j39_bench.log 2> gpurun_out/j39_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/j39_bench.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/j39_bench.log') if l.startswith('{')][-1])
-print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'])
-print('nnet_forward', d['nnet_forward'].get('ms_per_pass'), d['nnet_forward'].get('roofline',{}).get('frac'))
-c3=d['config3']; print('config3', c3.get('device_s'), c3.get('roofline',{}).get('frac'), c3.get('e2e',{}).get('value'))
-print('config4', d['config4'].get('device_s_max_over_ranks'), 'config5', {k:d['config5'].get(k) for k in ('wall_s_rank0','selfplay_s','train_s','arena_s')})
-print('cpu', d.get('cpu_baseline',{}).get('value'))
+for b in 64 1014 3000; do
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/j40_fwd_$b.csv python -c "
+import importlib,sys; sys.path.insert(0,'.'); azb=importlib.import_module('alphazero-rs_b200'); n=azb.NNet(seed=7,blocks=6); print(n.benchmark($b,4))" > /dev/null 2>&1
+python - <<PY
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/j40_fwd_$b.csv')) if len(r)>10]
+h=rows[0]; k=h.index('Kernel Name'); v=h.index('Metric Value')
+last=rows[-12:]
+print('batch $b:', [(r[k][:24], r[v]) for r in rows[-9:]])
 PY
+done
