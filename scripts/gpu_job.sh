@@ -1,13 +1,5 @@
-# round-2 GPU job 40: durations of the three kernels of a forward pass (stem, tower, heads) at 64 / 1014 / 3000 positions
+# round-2 GPU job 42: stem with fewer working CTAs at round sizes
 mkdir -p gpurun_out
-for b in 64 1014 3000; do
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/j40_fwd_$b.csv python -c "
-import importlib,sys; sys.path.insert(0,'.'); azb=importlib.import_module('alphazero-rs_b200'); n=azb.NNet(seed=7,blocks=6); print(n.benchmark($b,4))" > /dev/null 2>&1
-python - <<PY
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/j40_fwd_$b.csv')) if len(r)>10]
-h=rows[0]; k=h.index('Kernel Name'); v=h.index('Metric Value')
-last=rows[-12:]
-print('batch $b:', [(r[k][:24], r[v]) for r in rows[-9:]])
-PY
-done
+AZB200_LIB=build/variants/lib_stem.so timeout 400 python -m pytest tests/test_nnet_gpu.py tests/test_train_gpu.py -x -q --timeout=200 --timeout-method=thread 2>&1 | tail -3
+for v in head stem head stem; do echo "== $v"; AZB200_LIB=build/variants/lib_$v.so timeout 120 python scripts/forward_sweep.py 6 100 | tail -8; done > gpurun_out/j42_sweep.log 2>&1; head -18 gpurun_out/j42_sweep.log
+for v in head stem head stem; do echo -n "$v "; AZB200_LIB=build/variants/lib_$v.so timeout 120 python scripts/bench_configs.py config3 2>&1 | tail -1 | cut -c80-200; done
