@@ -350,6 +350,16 @@ uint32_t round_sim_budget(bool arena = false) {
   return n ? n : (arena ? 5u : 8u);  // (the arena share of config 4 with the cache: 2.49 s with 5, 2.57 with 16, 2.70 with 32)
 }
 
+// Slots of the lock-step rounds (network evaluator).  The persistent kernel of the fused evaluators holds one game per
+// co-resident warp; a round is a kernel per phase, so its slot count is free, and more slots are larger, fewer rounds: the
+// forward pass works on ~1.8 k instead of ~1 k positions and every launch's fixed cost is paid less often.  Config 3 (8192
+// games x 400 sims): 2960 slots 3.27 s, 4144 3.07, 4736 (the co-resident warps) 3.08-3.10, 6144 2.97, 8192 2.79-2.83.  The
+// games are the same games whatever the slot count (tests/test_selfplay_gpu.py).  AZB200_ROUND_SLOTS overrides.
+uint32_t round_slots(uint32_t resident_warps) {
+  static const uint32_t n = std::getenv("AZB200_ROUND_SLOTS") ? static_cast<uint32_t>(std::max(1, std::atoi(std::getenv("AZB200_ROUND_SLOTS")))) : 0u;
+  return n ? n : std::max<uint32_t>(resident_warps, 8192u);
+}
+
 // Programmatic dependent launch between the tower's layers (AZB200_TC_PDL=0 turns it off; the round graph's capture
 // also turns it off when the driver refuses programmatic edges inside a capture)
 bool g_tc_pdl = !(std::getenv("AZB200_TC_PDL") && std::getenv("AZB200_TC_PDL")[0] == '0');
@@ -1249,6 +1259,7 @@ int azb_coach_self_play_begin(azb_coach* c, uint64_t n_games, uint64_t first_gam
   int rc = resident_trees(c->cfg.device, &resident);
   if (rc) return rc;
   tm.lap("carveout+occupancy");
+  if (c->cfg.evaluator >= AZB_EVAL_NNET) resident = round_slots(resident);  // rounds are not tied to co-resident warps
   uint64_t n_trees = std::min<uint64_t>(n_games, resident);
   if (c->cfg.max_concurrent_games) n_trees = std::min<uint64_t>(n_trees, c->cfg.max_concurrent_games);
   // cudaMemGetInfo was measured to take up to 70 ms now and then: ask only when the pool has to change
@@ -1906,6 +1917,7 @@ int azb_arena_play_games_ex(const azb_config* cfg, uint64_t num, int32_t eval_a,
   size_t free_b = 0, total_b = 0;
   AZB_CUDA(cudaMemGetInfo(&free_b, &total_b));
   uint64_t by_mem = static_cast<uint64_t>(free_b) * 8 / 10 / (2 * tree_bytes(p));
+  resident = round_slots(resident);  // (the arena always runs as lock-step rounds)
   uint64_t n_slots = std::min<uint64_t>({G, resident, by_mem});
   if (cfg->max_concurrent_games) n_slots = std::min<uint64_t>(n_slots, cfg->max_concurrent_games);
   if (n_slots == 0) return fail(AZB_ERR_CAPACITY, "not enough device memory for one tree pair");
