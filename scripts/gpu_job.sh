@@ -1,14 +1,4 @@
-# round-2 GPU job 45: full GPU suite + smoke + bench with 8192 round slots
+# round-2 GPU job 46: round kernel occupancy at 8192 slots; slots beyond the games (no effect expected); round budget re-sweep
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu --timeout=400 --timeout-method=thread > gpurun_out/j45_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/j45_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/j45_bench.log 2> gpurun_out/j45_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/j45_bench.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/j45_bench.log') if l.startswith('{')][-1])
-print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'])
-print('nnet_forward', d['nnet_forward'].get('ms_per_pass'), d['nnet_forward'].get('roofline',{}).get('frac'))
-c3=d['config3']; print('config3', c3.get('device_s'), c3.get('roofline',{}).get('frac'), c3.get('e2e',{}).get('value'), c3.get('parity_checked'))
-print('config4', d['config4'].get('device_s_max_over_ranks'), 'config5', {k:d['config5'].get(k) for k in ('wall_s_rank0','selfplay_s','train_s','arena_s')})
-print('cpu', d.get('cpu_baseline',{}).get('value'))
-PY
+for v in rw28 rw32 rw40 rw28 rw32 rw40; do echo -n "$v "; AZB200_LIB=build/variants/lib_$v.so timeout 120 python scripts/bench_configs.py config3 2>&1 | tail -1 | cut -c80-140; done > gpurun_out/j46_rw.log 2>&1; cat gpurun_out/j46_rw.log
+for b in 8 12 16 6 8; do echo -n "round_sims=$b "; AZB200_ROUND_SIMS=$b timeout 120 python scripts/bench_configs.py config3 2>&1 | tail -1 | cut -c80-140; done > gpurun_out/j46_budget.log 2>&1; cat gpurun_out/j46_budget.log
