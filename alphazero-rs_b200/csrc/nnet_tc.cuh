@@ -766,8 +766,16 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
 // Phases of the tile barriers continue across layers (global tile number G = layer * iters + tile); the weight barriers
 // complete one phase per layer.  Results are bit-identical to the layer-by-layer kernels (same K order per output row).
 // ================================================================================================
-constexpr uint32_t kTwTilePos = 4;                                  // positions per tile
-constexpr uint32_t kTwTileRows = kTwTilePos * 56;                   // 224 rows are kept of the 256 computed
+// A unit of work is a run of WHOLE positions that nothing outside reaches into: 4 positions in one tile (224 rows kept of the
+// 256 computed, 12.5 % padding) or 9 positions in two consecutive tiles of the same pair (504 of 512, 1.6 %).  The two-tile
+// unit halves the padding but has half as many units to deal out and couples its two tiles (each needs 16 rows of the other
+// from the layer before); the kernel takes whichever gives the pair with the most work fewer tiles (tower_unit_pos).
+constexpr uint32_t kTwTilePos = 4;  // the grid is sized for the one-tile unit (the larger tile count)
+__host__ __device__ inline uint32_t tower_unit_pos(uint32_t n_pos, uint32_t n_pairs) {
+  const uint32_t t4 = (n_pos + 3u) / 4u, u9 = (n_pos + 8u) / 9u;
+  const uint32_t m4 = (t4 + n_pairs - 1u) / n_pairs, m9 = 2u * ((u9 + n_pairs - 1u) / n_pairs);
+  return m9 < m4 || (m9 == m4 && m9 > 2u) ? 9u : 4u;
+}
 struct TowerTcArgs {
   __nv_bfloat16* act[3];   // padded activation buffers; act[0] holds the stem's output, the result is in act[R odd ? 2 : 0]
   const uint8_t* w_tiles;  // layer l at + l * kTcKBlocks * kTcTileBytes
@@ -819,9 +827,12 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
   const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
   const uint32_t rows = n_pos * kActPadded.pos_rows;
-  const uint32_t n_tiles = (n_pos + kTwTilePos - 1) / kTwTilePos;
-  const uint32_t iters = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0u;
-  auto row0_of = [&](uint32_t i) { return (pair + i * n_pairs) * kTwTileRows + rank * kTcTileM; };
+  const uint32_t unit_pos = tower_unit_pos(n_pos, n_pairs), tpu = unit_pos == 9u ? 2u : 1u;  // tiles per unit
+  const uint32_t unit_rows = unit_pos * kActPadded.pos_rows;
+  const uint32_t n_units = (n_pos + unit_pos - 1u) / unit_pos;
+  const uint32_t iters = pair < n_units ? tpu * ((n_units - pair + n_pairs - 1u) / n_pairs) : 0u;  // tiles of this pair per layer
+  // tile i of the pair: sub-tile i % tpu of its unit i / tpu
+  auto row0_of = [&](uint32_t i) { return (pair + (i / tpu) * n_pairs) * unit_rows + (i % tpu) * kT2PairRows + rank * kTcTileM; };
   const bool dbg_on = g.dbg != nullptr && blockIdx.x == 0;
   const long long t_start = dbg_on ? clock64() : 0;
   // diagnostic timeline of CTA 0 (AZB200_TOWER_DEBUG=1): g.dbg[8 + layer * 8 + k], cycles since the CTA started
@@ -871,7 +882,7 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
     // ===== epilogue, 8 warps: TMEM lane quarter warp % 4, output channels 64 * (warp / 4) .. + 63 =====
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int q = warp & 3, half = warp >> 2;
-    const bool kept = rank * kTcTileM + q * 32 + lane < kTwTileRows;  // rows 224..255 of the MMA tile belong to the next tile
+    const uint32_t row_in_tile = rank * kTcTileM + q * 32 + lane;
     for (int layer = 0; layer < g.n_layers; ++layer) {
       float* sb = (layer & 1) ? s_bias1 : s_bias;
       if (threadIdx.x < kNetC) sb[threadIdx.x] = g.bias[layer * kNetC + threadIdx.x];
@@ -882,6 +893,7 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
         const uint32_t G = static_cast<uint32_t>(layer) * iters + ti, a = G & 1u;
         const uint32_t m = row0_of(ti) + q * 32 + lane;        // padded row
         const uint32_t rem = m % kActPadded.pos_rows;
+        const bool kept = (ti % tpu) * kT2PairRows + row_in_tile < unit_rows;  // the rows past the unit belong to another unit
         const bool real = kept && m < rows && (rem & 7u) != 7u && rem < 48u;  // not the zero column, not the zero row
         uint4 res[8];
         if (real && residual) {
@@ -1019,8 +1031,9 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
         auto fetch_tile = [&](uint32_t i) {
           const uint32_t G = static_cast<uint32_t>(layer) * iters + i;
           const int s = static_cast<int>(G & 1u);
-          if (layer > 0) {  // tile i of the previous layer is in global memory: all 16 epilogue warps of the pair said so
-            const uint32_t need = G - iters + 1u;
+          if (layer > 0) {  // what tile i reads of the previous layer is in global memory: both CTAs' publishers said so
+            // (a one-tile unit: the same tile; a two-tile unit: both tiles of the unit — each holds 16 rows the other needs)
+            const uint32_t need = G - iters + 1u + (tpu == 2u && (i & 1u) == 0u ? 1u : 0u);
             if (seen < need) {
               do {
                 seen = min2_volatile_shared(done_w);
@@ -1043,7 +1056,7 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
           asm volatile("griddepcontrol.wait;" ::: "memory");  // the stem's output is complete and visible
           fetch_tile(0u);
           for (int kb = kWFirst; kb < kTcKBlocks; ++kb) fetch_w(kb);
-        } else if (iters == 1u) {
+        } else if (iters <= tpu) {  // the first tile waits for the previous layer's LAST tile: the weights go first
           for (int kb = 0; kb < kTcKBlocks; ++kb) fetch_w(kb);
           AZB_TW_MARK(0);  // all weights requested
           fetch_tile(0u);
