@@ -381,10 +381,23 @@ int tc_mode() {
 // step always uses them); both produce the same bits (tests/test_nnet_gpu.py).
 bool g_tower = !(std::getenv("AZB200_TOWER") && std::getenv("AZB200_TOWER")[0] == '0');
 
-// One dense forward pass over the first *d_count (or max_batch) positions.
+// One dense forward pass over the first *d_count (or max_batch) positions.  With a second network of the same shape (the
+// arena's two players) the two towers share ONE launch of k_tower_tc3, its CTA pairs split between the models in proportion
+// to their positions; everything else (stem, heads, and the towers themselves when the one-launch tower does not apply)
+// runs per model.
 int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, uint32_t max_batch, float* d_pi,
-                 float* d_v, cudaStream_t st) {
+                 float* d_v, cudaStream_t st, azb_nnet* net2 = nullptr, const uint4* d_states2 = nullptr,
+                 const uint32_t* d_count2 = nullptr, float* d_pi2 = nullptr, float* d_v2 = nullptr) {
   if (max_batch == 0) return AZB_OK;
+  if (net2) {
+    const bool together = net->cfg.precision == AZB_NNET_BF16_TC && net2->cfg.precision == AZB_NNET_BF16_TC && tc_mode() == 3 &&
+                          net->L.R == net2->L.R && g_tower && d_count && d_count2 && max_batch <= 16384u &&
+                          !std::getenv("AZB200_TC_DEBUG") && !(std::getenv("AZB200_TOWER_PAIR") && std::getenv("AZB200_TOWER_PAIR")[0] == '0');
+    if (!together) {
+      const int rc = nnet_forward(net, d_states, d_count, max_batch, d_pi, d_v, st);
+      return rc ? rc : nnet_forward(net2, d_states2, d_count2, max_batch, d_pi2, d_v2, st);
+    }
+  }
   if (net->cfg.precision == AZB_NNET_FP32) {
     const size_t smem = (2 * kCells * kNetC + 256) * sizeof(float);
     const unsigned grid = std::min<uint32_t>(max_batch, 148u * 4u);
@@ -397,25 +410,34 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
   const ActLayout lay = mode == 3 ? kActPadded : kActDense;
   // + slack: the last 128-row TMA copy of a ragged batch runs a few rows past the batch
   const size_t act_bytes = (static_cast<size_t>(max_batch) + 8) * lay.pos_rows * kNetC * 2;
-  for (auto& b : net->d_act) AZB_CUDA(b.ensure(act_bytes));
-  for (int i = 0; i < 3; ++i)
-    if (net->act_map_ptr[i] != net->d_act[i].p || net->act_map_bytes[i] != net->d_act[i].bytes) {
-      // a fresh buffer: the padded layout's zero rows / columns are zeroed here once and never written again
-      AZB_CUDA(cudaMemsetAsync(net->d_act[i].p, 0, net->d_act[i].bytes, st));
-      if (mode == 3) {
-        const int rc = encode_act_map_rows(&net->act_map[i], net->d_act[i].p, net->d_act[i].bytes);
-        if (rc) return rc;
+  const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
+  // activation buffers + their TMA descriptors, then the stem into buffer 0
+  auto prepare_and_stem = [&](azb_nnet* n, const uint4* states, const uint32_t* count) -> int {
+    for (auto& b : n->d_act) AZB_CUDA(b.ensure(act_bytes));
+    for (int i = 0; i < 3; ++i)
+      if (n->act_map_ptr[i] != n->d_act[i].p || n->act_map_bytes[i] != n->d_act[i].bytes) {
+        // a fresh buffer: the padded layout's zero rows / columns are zeroed here once and never written again
+        AZB_CUDA(cudaMemsetAsync(n->d_act[i].p, 0, n->d_act[i].bytes, st));
+        if (mode == 3) {
+          const int rc = encode_act_map_rows(&n->act_map[i], n->d_act[i].p, n->d_act[i].bytes);
+          if (rc) return rc;
+        }
+        n->act_map_ptr[i] = n->d_act[i].p;
+        n->act_map_bytes[i] = n->d_act[i].bytes;
       }
-      net->act_map_ptr[i] = net->d_act[i].p;
-      net->act_map_bytes[i] = net->d_act[i].bytes;
-    }
+    k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes, st>>>(
+        n->d_params.as<float>(), n->L, n->d_stem_tab.as<float>(), states, count, max_batch, n->d_act[0].as<__nv_bfloat16>(), lay);
+    return AZB_OK;
+  };
+  {
+    int rc = prepare_and_stem(net, d_states, d_count);
+    if (!rc && net2) rc = prepare_and_stem(net2, d_states2, d_count2);
+    if (rc) return rc;
+  }
   __nv_bfloat16* x = net->d_act[0].as<__nv_bfloat16>();
   __nv_bfloat16* y = net->d_act[1].as<__nv_bfloat16>();
   __nv_bfloat16* z = net->d_act[2].as<__nv_bfloat16>();
   const float* prm = net->d_params.as<float>();
-  const size_t total = static_cast<size_t>(max_batch) * kCells * (kNetC / 8);
-  k_stem_bf16<<<static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 148u * 2u)), 1024, kStemSmemBytes, st>>>(
-      prm, net->L, net->d_stem_tab.as<float>(), d_states, d_count, max_batch, x, lay);
   const uint32_t tiles = (max_batch * kCells + kTcCtaRows - 1) / kTcCtaRows;
   const unsigned grid = std::min<uint32_t>(tiles, 148u);
   // Default: CTA pairs (tcgen05 cta_group::2) with resident weights; AZB200_TC_PAIR=0 selects the
@@ -477,10 +499,15 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     }
     if (tower_pairs > 0) {
       TowerTcArgs t{};
-      for (int i = 0; i < 3; ++i) t.act[i] = net->d_act[i].as<__nv_bfloat16>();
-      t.w_tiles = net->d_wtiles.as<uint8_t>();
-      t.bias = prm + net->L.tower_b;
-      t.count = d_count;
+      auto fill = [&](TowerModel& m, azb_nnet* n, const uint32_t* count) {
+        for (int i = 0; i < 3; ++i) m.act[i] = n->d_act[i].as<__nv_bfloat16>();
+        m.w_tiles = n->d_wtiles.as<uint8_t>();
+        m.bias = n->d_params.as<float>() + n->L.tower_b;
+        m.count = count;
+      };
+      fill(t.m[0], net, d_count);
+      if (net2) fill(t.m[1], net2, d_count2);
+      t.n_models = net2 ? 2 : 1;
       t.max_batch = max_batch;
       t.n_layers = 2 * net->L.R;
       static unsigned long long* d_tdbg = nullptr;  // AZB200_TOWER_DEBUG=1: per-layer timeline of CTA 0
@@ -490,7 +517,7 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
       }
       t.dbg = d_tdbg;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2u * std::min<uint32_t>((max_batch + kTwTilePos - 1) / kTwTilePos, static_cast<uint32_t>(tower_pairs)));
+      cfg.gridDim = dim3(2u * std::min<uint32_t>((net2 ? 2u : 1u) * ((max_batch + kTwTilePos - 1) / kTwTilePos), static_cast<uint32_t>(tower_pairs)));
       cfg.blockDim = dim3(kTwThreads);
       cfg.dynamicSmemBytes = kTwSmemBytes;
       cfg.stream = st;
@@ -499,7 +526,9 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = use_pdl ? 1 : 0;
-      const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower_tc3, t, net->act_map[0], net->act_map[1], net->act_map[2]);
+      azb_nnet* nb = net2 ? net2 : net;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower_tc3, t, net->act_map[0], net->act_map[1], net->act_map[2], nb->act_map[0],
+                                               nb->act_map[1], nb->act_map[2]);
       if (e == cudaSuccess) {
         tower_done = true;
         if (net->L.R & 1) std::swap(x, z);  // where the last block left its output
@@ -523,6 +552,10 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
         if (std::getenv("AZB200_TIMING")) std::fprintf(stderr, "[azb200 nnet] tower launch refused (%s): layer-by-layer kernels\n", cudaGetErrorString(e));
       }
     }
+  }
+  if (net2 && !tower_done) {  // (the shared launch did not happen: each model on its own, stems again)
+    const int rc = nnet_forward(net, d_states, d_count, max_batch, d_pi, d_v, st);
+    return rc ? rc : nnet_forward(net2, d_states2, d_count2, max_batch, d_pi2, d_v2, st);
   }
   for (int blk = 0; blk < net->L.R && !tower_done; ++blk) {
     ConvTcArgs a{};
@@ -553,6 +586,11 @@ int nnet_forward(azb_nnet* net, const uint4* d_states, const uint32_t* d_count, 
     cfg.numAttrs = (use_pdl && use_pair && max_pairs > 0) ? 1 : 0;
     const __nv_bfloat16* xin = x;
     AZB_CUDA(cudaLaunchKernelEx(&cfg, k_heads_bf16, prm, net->L, net->head_w, xin, d_count, max_batch, d_pi, d_v, lay));
+    if (net2) {  // (only after a shared tower launch: the result sits where the last block left it)
+      const __nv_bfloat16* xin2 = net2->d_act[(net2->L.R & 1) ? 2 : 0].as<__nv_bfloat16>();
+      const float* prm2 = net2->d_params.as<float>();
+      AZB_CUDA(cudaLaunchKernelEx(&cfg, k_heads_bf16, prm2, net2->L, net2->head_w, xin2, d_count2, max_batch, d_pi2, d_v2, lay));
+    }
   }
   AZB_CUDA(cudaGetLastError());
   if (d_dbg) {
@@ -757,21 +795,36 @@ struct RoundEngine {
       if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 2u, kTimesCap);
       AZB_CUDA(cudaGetLastError());
       if (any_net) {
-        for (int k = 0; k < 2; ++k) {
-          if (!nets[k] || rp.ev_kind[k] < AZB_EVAL_NNET) continue;
-          if (k == 1 && rp.mode != kModeArena) continue;
-          int rc = nnet_forward(nets[k], lf.state + static_cast<size_t>(k) * rp.leaf_cap, lf.count + k, rp.leaf_cap,
-                                lf.pi + static_cast<size_t>(k) * rp.leaf_cap * 8, lf.v + static_cast<size_t>(k) * rp.leaf_cap, stream);
-          if (rc) return rc;
+        const bool use0 = nets[0] && rp.ev_kind[0] >= AZB_EVAL_NNET;
+        const bool use1 = nets[1] && rp.ev_kind[1] >= AZB_EVAL_NNET && rp.mode == kModeArena;
+        auto fwd = [&](int k, int k2) {
+          return nnet_forward(nets[k], lf.state + static_cast<size_t>(k) * rp.leaf_cap, lf.count + k, rp.leaf_cap,
+                              lf.pi + static_cast<size_t>(k) * rp.leaf_cap * 8, lf.v + static_cast<size_t>(k) * rp.leaf_cap, stream,
+                              k2 < 0 ? nullptr : nets[k2], lf.state + static_cast<size_t>(std::max(k2, 0)) * rp.leaf_cap,
+                              lf.count + std::max(k2, 0), lf.pi + static_cast<size_t>(std::max(k2, 0)) * rp.leaf_cap * 8,
+                              lf.v + static_cast<size_t>(std::max(k2, 0)) * rp.leaf_cap);
+        };
+        int rc = AZB_OK;
+        if (use0 && use1 && nets[0] != nets[1]) rc = fwd(0, 1);  // the arena's two players: one tower launch for both
+        else {
+          if (use0) rc = fwd(0, -1);
+          if (!rc && use1) rc = fwd(1, -1);
         }
+        if (rc) return rc;
       }
       if (d_times) k_stamp<<<1, 1, 0, stream>>>(d_times, c.round, 3u, kTimesCap);
       return AZB_OK;
     };
-    if (any_net)
+    if (any_net) {  // launches of a round, for the statistics: k_compact + k_round + per model stem, tower (one launch or 2R), heads
+      const bool tower = g_tower && tc_mode() == 3 && rp.leaf_cap <= 16384u;
+      int n_tc = 0;
       for (int k = 0; k < 2; ++k)
-        if (nets[k] && rp.ev_kind[k] >= AZB_EVAL_NNET && (k == 0 || rp.mode == kModeArena))
-          per_round += (nets[k]->cfg.precision == AZB_NNET_FP32) ? 1 : 2 + 2 * nets[k]->L.R;
+        if (nets[k] && rp.ev_kind[k] >= AZB_EVAL_NNET && (k == 0 || rp.mode == kModeArena)) {
+          per_round += (nets[k]->cfg.precision == AZB_NNET_FP32) ? 1 : 2 + (tower ? 1 : 2 * nets[k]->L.R);
+          n_tc += nets[k]->cfg.precision != AZB_NNET_FP32;
+        }
+      if (tower && n_tc == 2 && nets[0] != nets[1] && nets[0]->L.R == nets[1]->L.R) per_round -= 1;  // the two towers share a launch
+    }
     // the progress word: what the last started round saw
     auto progress = [&](uint64_t* round_seen, uint32_t* live) {
       const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(h_progress);

@@ -776,12 +776,18 @@ __host__ __device__ inline uint32_t tower_unit_pos(uint32_t n_pos, uint32_t n_pa
   const uint32_t m4 = (t4 + n_pairs - 1u) / n_pairs, m9 = 2u * ((u9 + n_pairs - 1u) / n_pairs);
   return m9 < m4 || (m9 == m4 && m9 > 2u) ? 9u : 4u;
 }
-struct TowerTcArgs {
+struct TowerModel {
   __nv_bfloat16* act[3];   // padded activation buffers; act[0] holds the stem's output, the result is in act[R odd ? 2 : 0]
   const uint8_t* w_tiles;  // layer l at + l * kTcKBlocks * kTcTileBytes
   const float* bias;       // layer l at + l * 128
   const uint32_t* count;   // positions this round (device), or nullptr
-  uint32_t max_batch;
+};
+// One launch may carry TWO models of the same shape (the arena: the two players' leaf batches of a round).  The CTA pairs
+// are split between them in proportion to their tile counts, so two half-empty passes become one full one.
+struct TowerTcArgs {
+  TowerModel m[2];
+  int n_models;            // 1 or 2
+  uint32_t max_batch;      // per model
   int n_layers;            // 2 x residual blocks
   unsigned long long* dbg; // [8 + 8 * n_layers] diagnostic timeline of CTA 0 (AZB200_TOWER_DEBUG=1), or nullptr
 };
@@ -803,7 +809,8 @@ __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.ac
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTwThreads, 1)
 k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-            const __grid_constant__ CUtensorMap map2) {
+            const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+            const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map5) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto w_tile = [&](int kb) { return base + kb * kT2WTile; };
@@ -824,8 +831,25 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const uint32_t n_pos = g.count ? min(*g.count, g.max_batch) : g.max_batch;
+  // which model this pair works for, and as which of how many pairs
+  uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1, model = 0u;
+  const uint32_t n_pos0 = g.m[0].count ? min(*g.m[0].count, g.max_batch) : g.max_batch;
+  uint32_t n_pos = n_pos0;
+  if (g.n_models == 2) {
+    const uint32_t n_pos1 = g.m[1].count ? min(*g.m[1].count, g.max_batch) : g.max_batch;
+    const uint32_t t0 = (n_pos0 + 3u) / 4u, t1 = (n_pos1 + 3u) / 4u;
+    uint32_t p0 = n_pairs;  // pairs of model 0
+    if (t1 > 0u) p0 = t0 == 0u ? 0u : min(max((n_pairs * t0 + (t0 + t1) / 2u) / (t0 + t1), 1u), n_pairs - 1u);
+    if (pair >= p0) {
+      model = 1u;
+      pair -= p0;
+      n_pairs -= p0;
+      n_pos = n_pos1;
+    } else {
+      n_pairs = p0;
+    }
+  }
+  const TowerModel& gm = g.m[model];
   const uint32_t rows = n_pos * kActPadded.pos_rows;
   const uint32_t unit_pos = tower_unit_pos(n_pos, n_pairs), tpu = unit_pos == 9u ? 2u : 1u;  // tiles per unit
   const uint32_t unit_rows = unit_pos * kActPadded.pos_rows;
@@ -854,9 +878,9 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
     }
     for (uint32_t r = 0; r < 4u; ++r) mbar_init(bar_st(r), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(model ? &map3 : &map0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(model ? &map4 : &map1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(model ? &map5 : &map2)) : "memory");
   }
   if (threadIdx.x < 16) asm volatile("st.shared.u32 [%0], %1;" ::"r"(done_w + 4u * threadIdx.x), "r"(0u) : "memory");
   if (warp == 9) {
@@ -885,10 +909,10 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
     const uint32_t row_in_tile = rank * kTcTileM + q * 32 + lane;
     for (int layer = 0; layer < g.n_layers; ++layer) {
       float* sb = (layer & 1) ? s_bias1 : s_bias;
-      if (threadIdx.x < kNetC) sb[threadIdx.x] = g.bias[layer * kNetC + threadIdx.x];
+      if (threadIdx.x < kNetC) sb[threadIdx.x] = gm.bias[layer * kNetC + threadIdx.x];
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the layer's bias is in place (and everyone has left layer - 1)
-      const __nv_bfloat16* residual = (layer & 1) ? g.act[res_of(layer)] : nullptr;
-      __nv_bfloat16* out = g.act[out_of(layer)];
+      const __nv_bfloat16* residual = (layer & 1) ? gm.act[res_of(layer)] : nullptr;
+      __nv_bfloat16* out = gm.act[out_of(layer)];
       for (uint32_t ti = 0; ti < iters; ++ti) {
         const uint32_t G = static_cast<uint32_t>(layer) * iters + ti, a = G & 1u;
         const uint32_t m = row0_of(ti) + q * 32 + lane;        // padded row
@@ -1020,14 +1044,14 @@ k_tower_tc3(TowerTcArgs g, const __grid_constant__ CUtensorMap map0, const __gri
       constexpr int kWFirst = 6;
       uint32_t seen = 0u;  // every epilogue warp of the pair has published the tiles below this global number
       for (int layer = 0; layer < g.n_layers; ++layer) {
-        const uint8_t* wl = g.w_tiles + static_cast<size_t>(layer) * kTcKBlocks * kTcTileBytes;
+        const uint8_t* wl = gm.w_tiles + static_cast<size_t>(layer) * kTcKBlocks * kTcTileBytes;
         auto fetch_w = [&](int kb) {
           if (layer > 0) mbar_wait(bar_w_free(kb), (layer - 1) & 1);  // the previous layer's last MMA on this k-block has retired
           mbar_arrive_expect_tx(bar_w(kb), kT2WTile);
           tma_bulk_g2s(w_tile(kb), wl + static_cast<size_t>(kb) * kTcTileBytes + rank * kT2WTile, kT2WTile, bar_w(kb));
         };
         const int in_idx = in_of(layer);
-        const CUtensorMap* tm = in_idx == 0 ? &map0 : (in_idx == 1 ? &map1 : &map2);
+        const CUtensorMap* tm = model ? (in_idx == 0 ? &map3 : (in_idx == 1 ? &map4 : &map5)) : (in_idx == 0 ? &map0 : (in_idx == 1 ? &map1 : &map2));
         auto fetch_tile = [&](uint32_t i) {
           const uint32_t G = static_cast<uint32_t>(layer) * iters + i;
           const int s = static_cast<int>(G & 1u);
