@@ -1,6 +1,7 @@
-# round-2 GPU job 55: the bench on 8 GPUs with the final tree (own arm + reference arm)
+# round-2 GPU job 56: tower with groups of 4 tiles taken through all layers (depth-first by groups)
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/j55_bench8.log 2> gpurun_out/j55_bench8.err
-echo "bench8 rc=$?"; tail -c 300 gpurun_out/j55_bench8.err; cut -c1-200 gpurun_out/j55_bench8.log | tail -1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > gpurun_out/j55_ref8.log 2> gpurun_out/j55_ref8.err
-echo "ref8 rc=$?"; cut -c1-250 gpurun_out/j55_ref8.log | tail -1
+export AZB200_LIB=build/variants/lib_groups.so
+timeout 600 python -m pytest tests/test_nnet_gpu.py tests/test_arena_gpu.py tests/test_fullsize_parity_gpu.py -x -q --timeout=300 --timeout-method=thread 2>&1 | tail -3
+echo "== groups, tower for every size"; AZB200_TOWER_MAX=100000 timeout 120 python scripts/forward_sweep.py 6 100 | tail -8
+echo "== head (layer by layer above 3072)"; AZB200_LIB=build/variants/lib_head2.so timeout 120 python scripts/forward_sweep.py 6 100 | tail -8
+for v in head2 groups head2 groups head2 groups; do echo -n "$v "; AZB200_LIB=build/variants/lib_$v.so timeout 120 python scripts/bench_configs.py config3 2>&1 | tail -1 | cut -c100-125; done
