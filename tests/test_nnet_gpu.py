@@ -188,6 +188,24 @@ def test_selfplay_with_tensor_core_network_matches_oracle(azb, oracle):
         assert np.array_equal(tr["counts"][g, :n], o["counts"][:n])
 
 
+def test_network_games_do_not_depend_on_the_slot_count(azb):
+    """The lock-step rounds run min(games, 8192, memory) slots; a game's moves, root counts and samples must not depend on how
+    many games are in flight beside it (the round a leaf is evaluated in changes, the batch it shares changes, the evaluation
+    cache fills in another order: the per-position result does not).  200 games on 16 slots (recycled 12 times), on 64, and
+    all at once."""
+    net = azb.NNet(seed=5, blocks=2, precision=azb.NNET_BF16_TC)
+    ref = None
+    for slots in (0, 64, 16):
+        coach = azb.Coach(nnet=net, num_sims=40, seed=9, evaluator=azb.EVAL_NNET, max_concurrent_games=slots)
+        st = coach.self_play(200, 1000)
+        tr = coach.traces()
+        b, p, v = coach.export_samples()
+        got = (tr["plies"].tolist(), tr["actions"].tobytes(), tr["counts"].tobytes(), b.tobytes(), p.tobytes(), v.tobytes(), st["sims"])
+        if ref is None:
+            ref = got
+        assert got == ref, slots
+
+
 def test_arena_two_networks(azb, oracle):
     a = azb.NNet(seed=7, blocks=1, precision=azb.NNET_BF16_TC)
     b = azb.NNet(seed=8, blocks=1, precision=azb.NNET_BF16_TC)
