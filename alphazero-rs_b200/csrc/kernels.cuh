@@ -9,8 +9,10 @@ namespace azb {
 // Warps (= trees) per CTA of the search kernels.  A CTA's slot on its SM is free again only when ALL its warps are done, so
 // with back-to-back batches on two streams (azb_coach_self_play_begin / _end) small CTAs hand finished games' warp slots
 // to the next batch sooner.
+// Measured with the steps three deep (20 batches of 4096 x 800, three runs each): 4 warps per CTA 70.9-71.1 ms per batch,
+// 2 warps 69.7-69.8; the network rounds (config 3, config 4) are the same with either.
 #ifndef AZB_WARPS_PER_CTA
-#define AZB_WARPS_PER_CTA 4
+#define AZB_WARPS_PER_CTA 2
 #endif
 constexpr int kWarpsPerCta = AZB_WARPS_PER_CTA;
 // Resident warps per SM: 28 at 72 registers, 32 at 64, 36 at 56.  The persistent self-play kernel runs at 32: with
