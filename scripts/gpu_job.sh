@@ -1,4 +1,10 @@
-# round-2 GPU job 60: 2 warps per CTA everywhere: GPU suite, config 3 / config 4 against 4 warps per CTA
+# round-2 GPU job 62: the bench on the final build (2 warps per CTA), own arm
 mkdir -p gpurun_out
-AZB200_LIB=build/variants/lib_w2.so timeout 900 python -m pytest tests -x -q -m gpu --timeout=400 --timeout-method=thread 2>&1 | tail -3
-for v in w4 w2 w4 w2 w4 w2; do echo -n "$v "; AZB200_LIB=build/variants/lib_$v.so timeout 200 python scripts/bench_configs.py config3 config4 2>&1 | tail -2 | cut -c100-135 | tr '\n' ' '; echo; done
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/j62_bench.log 2> gpurun_out/j62_bench.err; echo "bench rc=$?"; tail -c 300 gpurun_out/j62_bench.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/j62_bench.log') if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','ms_per_step','steps','warmup')}, d['e2e']['value'], d['roofline']['frac'], d['clocks'], d['config']['single_batch_ms'])
+c3=d['config3']; print('config3', c3.get('device_s'), 'config4', d['config4'].get('device_s_max_over_ranks'), 'config5', d['config5'].get('wall_s_rank0'), 'config1', d['config1']['uniform_50_sims']['device_sims_per_sec'])
+print('cpu', d.get('cpu_baseline',{}).get('value'), 'ratio e2e/cpu', d['e2e']['value']/d['cpu_baseline']['value'])
+PY
