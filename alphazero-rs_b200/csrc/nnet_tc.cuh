@@ -757,12 +757,20 @@ k_conv3x3_tc3(ConvTcArgs g, const __grid_constant__ CUtensorMap tmap_in) {
 // tap never reaches across it: a tile that starts on a position boundary and holds whole positions depends on NOTHING
 // outside itself, in any layer.  A tile is therefore 4 positions = 224 rows of a 256-row MMA (rows 224..255 are computed
 // and dropped: 12.5 % more MMA work than k_conv3x3_tc3's dense tiling), a CTA pair owns its tiles through all 2R layers,
-// and the only ordering left is inside the pair: the epilogue warps of both CTAs publish "my part of tile i of layer L is
-// in global memory" (stores -> __threadfence -> fence.proxy.async.global -> a per-warp counter in both CTAs' shared
-// memory), and the producer lane waits for the 16 counters before it asks TMA for tile i of layer L + 1.  With two or more
-// tiles per pair that wait is already over when the pipeline gets there.  No grid barrier, no cooperative launch, pairs
-// drift apart freely; set-up happens once; the next layer's first weight k-blocks are requested the moment the current
-// layer's last MMA has retired and land under the last tile's epilogue.
+// and the only ordering left is inside the pair — "this CTA's rows of tile i of layer L are in global memory", from the
+// epilogue warps (generic-proxy stores) to the pair's two producer lanes (TMA = async-proxy reads of tile i of layer L + 1):
+//   epilogue warp   stores of the tile -> __syncwarp -> one arrive on a CTA-local mbarrier (ring of 4, 8 arrivals each);
+//   publisher warp  (one per CTA) waits for the ring entry -> fence.acq_rel.cluster, cumulative over the eight warps'
+//                   stores -> relaxed store of G + 1 into its flag in BOTH CTAs' shared memory.  The fence is
+//                   MEMBAR.GPU + CCTL.IVALL, ~2 k cycles: paid by the epilogue warps it made them, not the tensor pipe,
+//                   the tile period;
+//   producer lane   one volatile 8-byte read of the two flags (cached minimum) -> fence.acq_rel.cluster ->
+//                   fence.proxy.async.global (one proxy fence on the causality chain orders the generic store and the
+//                   TMA read) -> the two TMA copies.
+// With two or more tiles per pair the flags are up long before the pipeline gets there.  The next layer's first tile is
+// requested while the current layer's last tile is still in the tensor pipe, and that tile hands the weights back k-block by
+// k-block (one tcgen05.commit per k-block), so the next layer's 144 KB stream in under it.  No grid barrier, no cooperative
+// launch, pairs drift apart freely; set-up happens once.
 // Phases of the tile barriers continue across layers (global tile number G = layer * iters + tile); the weight barriers
 // complete one phase per layer.  Results are bit-identical to the layer-by-layer kernels (same K order per output row).
 // ================================================================================================
