@@ -1,10 +1,4 @@
-# round-2 GPU job 62: the bench on the final build (2 warps per CTA), own arm
+# round-2 GPU job 63: the bench on 4 GPUs (the one N of the driver's scaling run not yet exercised)
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/j62_bench.log 2> gpurun_out/j62_bench.err; echo "bench rc=$?"; tail -c 300 gpurun_out/j62_bench.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/j62_bench.log') if l.startswith('{')][-1])
-print({k:d[k] for k in ('value','ms_per_step','steps','warmup')}, d['e2e']['value'], d['roofline']['frac'], d['clocks'], d['config']['single_batch_ms'])
-c3=d['config3']; print('config3', c3.get('device_s'), 'config4', d['config4'].get('device_s_max_over_ranks'), 'config5', d['config5'].get('wall_s_rank0'), 'config1', d['config1']['uniform_50_sims']['device_sims_per_sec'])
-print('cpu', d.get('cpu_baseline',{}).get('value'), 'ratio e2e/cpu', d['e2e']['value']/d['cpu_baseline']['value'])
-PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/j63_bench4.log 2> gpurun_out/j63_bench4.err
+echo "bench4 rc=$?"; tail -c 300 gpurun_out/j63_bench4.err; cut -c1-250 gpurun_out/j63_bench4.log | tail -1
