@@ -215,14 +215,15 @@ def test_arena_two_networks(azb, oracle):
     assert res.tolist() == res2.tolist()
 
 
-@pytest.mark.parametrize("n_pos", [25, 301, 1500, 2500, 3500])
+@pytest.mark.parametrize("n_pos", [9, 25, 297, 301, 1185, 1500, 2500, 3071, 3500])
 def test_tower_implementations_agree_bit_for_bit(azb, oracle, tmp_path, n_pos):
     """Three implementations of the 2R-convolution tower accumulate every output in the same K order in fp32 and must agree
     bit for bit: k_tower_tc3 (one launch, position-aligned tiles, a CTA pair takes its tiles through all layers; the
     default up to ~3 k positions), k_conv3x3_tc3 launched layer by layer (AZB200_TOWER=0; also what 3500 positions use by
     default) and k_conv3x3_tc<1> (one CTA, cp.async gather, dense layout, streamed weights: AZB200_TC_PAIR=0).  The kernels
-    are chosen once per process, so the other two run in child processes.  Sizes: one tile, a ragged last tile, five tiles per
-    CTA pair (9-position two-tile units), 2500 positions (two-tile units, ragged), and a batch above the tower's size limit."""
+    are chosen once per process, so the other two run in child processes.  Sizes: one tile, one two-tile unit's worth, the last size with one tile
+    per CTA pair and the first with two, sizes that take the 9-position two-tile units (ragged last units), the largest
+    caller-sized batch that takes the tower and one above its size limit."""
     import os, subprocess, sys
     rng = np.random.default_rng(n_pos)  # disjoint random stone sets (not necessarily reachable positions)
     feats = (rng.random((n_pos, 2, 6, 7)) < 0.3).astype(np.float32)
