@@ -250,6 +250,22 @@ def test_tower_implementations_agree_bit_for_bit(azb, oracle, tmp_path, n_pos):
         assert np.array_equal(v.view(np.uint32), v1.view(np.uint32)), var
 
 
+@pytest.mark.parametrize("n_pos", [300, 1500, 2500])
+def test_tower_hand_over_is_not_a_race(azb, n_pos):
+    """k_tower_tc3 hands a tile from the epilogue warps' generic stores to the CTA pair's TMA reads of the next layer through a
+    publisher warp, two flags in shared memory and a reader-side proxy fence (csrc/nnet_tc.cuh).  If that ordering were wrong,
+    a pass would now and then read a stale row: 1000 passes over the same positions must give the same bits every time (one
+    tile per pair, several tiles per pair with two-tile units, ragged units)."""
+    rng = np.random.default_rng(100 + n_pos)
+    feats = (rng.random((n_pos, 2, 6, 7)) < 0.3).astype(np.float32)
+    feats[:, 1] *= 1.0 - feats[:, 0]
+    net = azb.NNet(seed=3, blocks=6, precision=azb.NNET_BF16_TC)
+    pi0, v0 = net.predict(feats)
+    for _ in range(1000):
+        pi, v = net.predict(feats)
+        assert np.array_equal(pi.view(np.uint32), pi0.view(np.uint32)) and np.array_equal(v.view(np.uint32), v0.view(np.uint32))
+
+
 def test_config3_parameters_sampled_games(azb, oracle):
     """BASELINE config 3 parameters (400 sims/move, ResNet-6x128 bf16 on the tcgen05 tower, seed 0xA1FA0) on a
     512-game batch — many M tiles per layer, rounds with thousands of pending leaves — and two of its games replayed
